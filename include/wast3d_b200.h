@@ -1,0 +1,165 @@
+/*
+ * wast3d_b200 — C ABI of the B200-native (sm_100a) hot path of WaSt3D's style-transfer
+ * optimisation step.  Plain pointers and sizes only; no torch types, no C++ exceptions.
+ * Every function returns an int status (WAST3D_OK == 0); wast3d_strerror() names it.
+ * All data pointers are DEVICE pointers unless the name ends in `_host`.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what the
+ * reference launches on: `<<<grid,block>>>` with no stream argument, forward.cu:408,450).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the
+ * reference repo root, facebookresearch/WaSt3D @ 786e4e1e).
+ */
+#ifndef WAST3D_B200_H_
+#define WAST3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WAST3D_ABI_VERSION 1
+
+enum wast3d_status {
+    WAST3D_OK = 0,
+    WAST3D_ERR_INVALID_ARGUMENT = 1, /* bad shape / null pointer / unsupported combination   */
+    WAST3D_ERR_CUDA = 2,             /* a CUDA runtime call or kernel failed                  */
+    WAST3D_ERR_ALLOC = 3,            /* an allocation callback returned NULL                  */
+    WAST3D_ERR_NO_DEVICE = 4,        /* no sm_100 device visible (there is no CPU fallback)   */
+    WAST3D_ERR_OVERFLOW = 5,         /* instance count does not fit 31 bits                   */
+    WAST3D_ERR_NON_RGB = 6           /* reserved: non-RGB channels need precomputed colours   */
+};
+
+const char* wast3d_strerror(int status);
+int wast3d_abi_version(void);
+/* Returns WAST3D_OK iff device `ordinal` exists and is compute capability 10.x. */
+int wast3d_device_check(int ordinal);
+
+/* Growable scratch buffers.  Replaces `std::function<char*(size_t)>`
+ * (submodules/diff-gaussian-rasterization/cuda_rasterizer/rasterizer.h:32-34) and the
+ * torch `resize_` lambdas of rasterize_points.cu:27-33.  Must return a device pointer to at
+ * least `bytes` bytes, 128-byte aligned (torch allocations are), or NULL on failure. */
+typedef void* (*wast3d_alloc_fn)(size_t bytes, void* user);
+
+/* Inputs shared by forward and backward — the union of the argument lists of
+ * CudaRasterizer::Rasterizer::forward / backward (rasterizer.h:30-92).  "Not provided"
+ * tensors are NULL, exactly like the size-0 tensors of the reference whose data_ptr is null
+ * (diff_gaussian_rasterization/__init__.py:213-223; forward.cu:205,241). */
+typedef struct wast3d_raster_params {
+    int P;               /* number of Gaussians                                            */
+    int D;               /* active SH degree 0..3                                          */
+    int M;               /* SH coefficients per Gaussian in `shs` (0 if shs == NULL)       */
+    int width, height;
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int prefiltered;     /* reference traps if a culled point is seen with this set        */
+    int debug;           /* synchronise + check after every stage (auxiliary.h:166-173)    */
+    const float* background;      /* [3]                                                   */
+    const float* means3D;         /* [P,3]                                                 */
+    const float* shs;             /* [P,M,3] or NULL                                       */
+    const float* colors_precomp;  /* [P,3]  or NULL                                        */
+    const float* opacities;       /* [P,1]                                                 */
+    const float* scales;          /* [P,3]  or NULL                                        */
+    const float* rotations;       /* [P,4]  or NULL (NOT normalised here, forward.cu:127)  */
+    const float* cov3D_precomp;   /* [P,6]  or NULL                                        */
+    const float* viewmatrix;      /* [16] as stored by scene/cameras.py:54 (transposed)    */
+    const float* projmatrix;      /* [16] full projection, same storage                    */
+    const float* campos;          /* [3]                                                   */
+    const float* sampling_offsets;/* [H,W,2] per-pixel sample jitter (forward.cu:287), or
+                                     NULL meaning all zero                                 */
+} wast3d_raster_params;
+
+/* Replaces RasterizeGaussiansCUDA -> CudaRasterizer::Rasterizer::forward
+ * (rasterize_points.cu:35-119, rasterizer_impl.cu:198-341).
+ * out_color [3,H,W], out_depth [H,W], radii [P] int32 (may be NULL -> internal).
+ * The three scratch buffers are opaque; keep them alive and pass them to backward.
+ * One documented layout fact is kept from the reference: the image
+ * buffer starts with final_T (float[H*W]) at offset 0, n_contrib (uint32[H*W]) follows at
+ * the next 128-byte boundary, so alpha = 1 - imgBuffer[:4*H*W].view(float32).
+ * Like the reference this performs ONE blocking device->host read of num_rendered. */
+int wast3d_raster_forward(const wast3d_raster_params* prm,
+                          wast3d_alloc_fn geom_alloc, void* geom_user,
+                          wast3d_alloc_fn binning_alloc, void* binning_user,
+                          wast3d_alloc_fn img_alloc, void* img_user,
+                          float* out_color, float* out_depth, int* radii,
+                          int* num_rendered_host, void* stream);
+
+/* Replaces RasterizeGaussiansBackwardCUDA -> Rasterizer::backward
+ * (rasterize_points.cu:121-206, rasterizer_impl.cu:345-446).
+ * Gradient outputs need NOT be zero-initialised: every element is written.
+ * dL_dmean2D [P,3], dL_dcolor [P,3], dL_dopacity [P,1], dL_dmean3D [P,3], dL_dcov3D [P,6],
+ * dL_dsh [P,M,3] (NULL allowed when M == 0), dL_dscale [P,3], dL_drot [P,4].
+ * dL_dconic [P,2,2] and dL_dcamViewDepth [P,1] are the reference's private scratch tensors
+ * (rasterize_points.cu:159,161); pass NULL unless a test wants to inspect them. */
+int wast3d_raster_backward(const wast3d_raster_params* prm, int num_rendered, const int* radii,
+                           void* geom_buffer, void* binning_buffer, void* img_buffer,
+                           const float* dL_dpix, const float* dL_ddepth,
+                           float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                           float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+                           float* dL_dscale, float* dL_drot, float* dL_dcamViewDepth,
+                           void* stream);
+
+/* Test/inspection hook (no reference equivalent is Python-visible; mirrors the state
+ * structs of rasterizer_impl.h:29-65).  Any output may be NULL.
+ * depths[P], means2D[P,2], conic_opacity[P,4], rgb[P,3], tiles_touched[P] (uint32),
+ * clamped[P,3] (bytes 0/1), point_list[num_rendered] (uint32), ranges[T,2] (uint32). */
+int wast3d_raster_export_state(const wast3d_raster_params* prm, int num_rendered,
+                               const void* geom_buffer, const void* binning_buffer,
+                               const void* img_buffer, float* depths, float* means2D,
+                               float* conic_opacity, float* rgb, uint32_t* tiles_touched,
+                               unsigned char* clamped, uint32_t* point_list, uint32_t* ranges,
+                               void* stream);
+
+/* Replaces markVisible -> checkFrustum (rasterize_points.cu:208-227,
+ * rasterizer_impl.cu:54-66,141-153).  present is bool[P] (1 byte each). */
+int wast3d_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                        const float* projmatrix, unsigned char* present, void* stream);
+
+/* Replaces distCUDA2 -> SimpleKNN::knn (submodules/simple-knn/spatial.cu:15-26,
+ * simple_knn.cu:185-221): mean of the 3 smallest squared distances to OTHER points
+ * (self excluded by index, simple_knn.cu:158,177).  points [P,3], mean_dist2 [P].
+ * Optional extension: nn_index [P,3] int32 (ties -> lowest index), or NULL.
+ * Scratch: call wast3d_knn_scratch_bytes(P) and pass a buffer of that size. */
+size_t wast3d_knn_scratch_bytes(int P);
+int wast3d_knn_dist2(int P, const float* points, float* mean_dist2, int32_t* nn_index,
+                     void* scratch, size_t scratch_bytes, void* stream);
+
+/* Cluster matching.  No native reference interface exists (the reference does this inline
+ * with torch.cdist + argmin/min: notebooks/10.visualize_and_fit_patch_to_multiple.ipynb
+ * cell 34, notebooks/29.2.Modify_style_clusters.ipynb cell 58); see SURVEY.md §8a M3/M5.
+ *
+ * wast3d_cluster_stats: per-cluster mean [K,3] and covariance (6 upper-tri: xx,xy,xz,yy,yz,zz)
+ * of member points; labels int32 in [0,K), points [n,3].  count [K] int32.
+ * Accumulated in double from sorted segments so the result is order-independent. */
+int wast3d_cluster_stats(int n, int K, const float* points, const int32_t* labels,
+                         float* mean, float* cov6, int32_t* count, void* stream);
+
+/* wast3d_nn_match: for each query row a[i] ([Na,3]) the index of the nearest b[j] ([Nb,3])
+ * = argmin_j cdist(a,b)[i,j] with ties to the lowest j; out_dist = that Euclidean distance.
+ * Decided on fp32 values computed in torch.cdist's operation order (oracle/match_oracle.c). */
+int wast3d_nn_match(int Na, int Nb, const float* a, const float* b, int32_t* out_idx,
+                    float* out_dist, void* stream);
+
+/* wast3d_w2_match: content clusters (mean_c [Kc,3], cov_c [Kc,6]) against style clusters
+ * (mean_s [Ks,3], cov_s [Ks,6]): out_idx[i] = argmin_j W2^2(N(mc_i,Sc_i), N(ms_j,Ss_j)),
+ *   W2^2 = |m1-m2|^2 + tr(S1) + tr(S2) - 2 tr((S1^1/2 S2 S1^1/2)^1/2)      
+ * ties to the lowest j; out_cost = that W2^2 (fp32, fixed operation order, see
+ * oracle/match_oracle.c).  A tcgen05 GEMM over augmented bf16-split descriptors gives a
+ * lower bound per pair; only pairs that can beat the row's running best get the exact
+ * Bures term.  stats (optional, [4] uint64): pairs, exact_evals, gemm_tiles, reserved. */
+int wast3d_w2_match(int Kc, int Ks, const float* mean_c, const float* cov_c,
+                    const float* mean_s, const float* cov_s, int32_t* out_idx, float* out_cost,
+                    unsigned long long* stats, void* stream);
+
+/* Fused Adam step over one flat fp32 parameter group (replaces torch.optim.Adam as configured
+ * in scene/gaussian_model.py:154-163: betas (0.9,0.999), eps 1e-15, no weight decay).
+ * step is the 1-based step count AFTER increment (bias corrections use it). */
+int wast3d_adam_step(size_t n, float* param, const float* grad, float* exp_avg,
+                     float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int step,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAST3D_B200_H_ */

@@ -1,0 +1,88 @@
+"""Shared input builders for the parity tests (seeded, sizes the oracle finishes in seconds)."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from wast3d_b200.scene import orbit_cameras, synthetic_gaussians, fov_y_from_x
+
+
+def raster_case(P=20000, W=320, H=240, seed=0, cam_index=1, degree=3, jitter=True, bg=(0.0, 0.0, 0.0),
+                log_scale_mu=-3.6, radius=4.03, fovx=0.6911, garden=False, use_precomp_color=False,
+                use_precomp_cov=False, scale_modifier=1.0):
+    """Activated rasteriser inputs as float32 numpy arrays (what `_C.rasterize_gaussians` gets)."""
+    g = synthetic_gaussians(P, seed=seed, garden=garden, log_scale_mu=log_scale_mu)
+    cam = orbit_cameras(8, radius, 2.0 if garden else 0.0, fovx, W, H, device="cpu", sphere=not garden)[cam_index]
+    q = g["rotations"] / np.linalg.norm(g["rotations"], axis=1, keepdims=True)
+    rng = np.random.default_rng(seed + 1000)
+    case = dict(
+        W=W, H=H, tan_fovx=math.tan(cam.FoVx / 2), tan_fovy=math.tan(cam.FoVy / 2),
+        bg=np.asarray(bg, np.float32), means3D=g["xyz"],
+        opacities=(1.0 / (1.0 + np.exp(-g["opacity_logits"]))).astype(np.float32),
+        view=cam.world_view_transform.numpy().copy(), proj=cam.full_proj_transform.numpy().copy(),
+        campos=cam.camera_center.numpy().copy(), D=degree, scale_modifier=scale_modifier,
+        sampling_offsets=(-rng.random((H, W, 2))).astype(np.float32) if jitter else None)
+    shs = np.concatenate([g["f_dc"], g["f_rest"]], 1).astype(np.float32)
+    if use_precomp_color:
+        case["colors_precomp"] = rng.random((P, 3)).astype(np.float32)
+    else:
+        case["shs"] = shs
+    scales = np.exp(g["log_scales"]).astype(np.float32)
+    if use_precomp_cov:
+        from wast3d_b200.scene import covariance_from_scaling_rotation
+        case["cov3D_precomp"] = covariance_from_scaling_rotation(
+            torch.from_numpy(scales), scale_modifier, torch.from_numpy(q.astype(np.float32))).numpy()
+    else:
+        case["scales"], case["rotations"] = scales, q.astype(np.float32)
+    return case
+
+
+def to_cuda(case: dict) -> dict:
+    return {k: (torch.from_numpy(np.ascontiguousarray(v)).cuda() if isinstance(v, np.ndarray) else v)
+            for k, v in case.items()}
+
+
+EMPTY = None
+
+
+def call_forward(tc: dict, debug=False):
+    """Run our `_C.rasterize_gaussians` on a CUDA case dict."""
+    from wast3d_b200.diff_gaussian_rasterization import _C
+    e = torch.empty(0)
+    g = lambda k: tc.get(k) if tc.get(k) is not None else e
+    return _C.rasterize_gaussians(
+        tc["bg"], tc["means3D"], g("colors_precomp"), tc["opacities"], g("scales"), g("rotations"),
+        tc["scale_modifier"], g("cov3D_precomp"), tc["view"], tc["proj"], tc["tan_fovx"], tc["tan_fovy"],
+        tc["H"], tc["W"], g("shs"), tc["D"], tc["campos"], False, debug, g("sampling_offsets"))
+
+
+def call_backward(tc: dict, fwd, dL_dpix, dL_ddepth, debug=False, scratch=True):
+    from wast3d_b200.diff_gaussian_rasterization import _C
+    e = torch.empty(0)
+    g = lambda k: tc.get(k) if tc.get(k) is not None else e
+    R, color, depth, radii, geom, binning, img = fwd
+    return _C.rasterize_gaussians_backward(
+        tc["bg"], tc["means3D"], radii, g("colors_precomp"), g("scales"), g("rotations"),
+        tc["scale_modifier"], g("cov3D_precomp"), tc["view"], tc["proj"], tc["tan_fovx"], tc["tan_fovy"],
+        dL_dpix, dL_ddepth, g("shs"), tc["D"], tc["campos"], geom, R, binning, img, debug,
+        g("sampling_offsets"), _return_scratch=scratch)
+
+
+def export(tc: dict, fwd):
+    from wast3d_b200.diff_gaussian_rasterization import _C
+    R, color, depth, radii, geom, binning, img = fwd
+    kw = dict(P=tc["means3D"].shape[0], D=tc["D"], M=(tc["shs"].shape[1] if tc.get("shs") is not None else 0),
+              W=tc["W"], H=tc["H"], tan_fovx=tc["tan_fovx"], tan_fovy=tc["tan_fovy"],
+              scale_modifier=tc["scale_modifier"], prefiltered=False, debug=False, bg=tc["bg"],
+              means3D=tc["means3D"], sh=tc.get("shs"), colors=tc.get("colors_precomp"),
+              opacity=tc["opacities"], scales=tc.get("scales"), rotations=tc.get("rotations"),
+              cov3D_precomp=tc.get("cov3D_precomp"), viewmatrix=tc["view"], projmatrix=tc["proj"],
+              campos=tc["campos"], sampling_offsets=tc.get("sampling_offsets"))
+    return _C.export_state(kw, R, geom, binning, img)
+
+
+def rel_l2(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / max(b.norm().item(), 1e-30))

@@ -1,0 +1,126 @@
+"""ctypes binding of libwast3d_b200.so (the C ABI declared in include/wast3d_b200.h).
+
+There is deliberately no fallback: if the library is missing, or a call is made without an
+sm_100 device, the caller gets a RuntimeError.  Nothing here imports or executes `oracle/`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libwast3d_b200.so"
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class RasterParams(C.Structure):
+    """struct wast3d_raster_params (include/wast3d_b200.h)."""
+
+    _fields_ = [
+        ("P", C.c_int), ("D", C.c_int), ("M", C.c_int),
+        ("width", C.c_int), ("height", C.c_int),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int), ("debug", C.c_int),
+        ("background", C.c_void_p), ("means3D", C.c_void_p), ("shs", C.c_void_p),
+        ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
+        ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
+        ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("sampling_offsets", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol of include/wast3d_b200.h
+_vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+SIGNATURES = {
+    "wast3d_strerror": (C.c_char_p, [_i]),
+    "wast3d_abi_version": (_i, []),
+    "wast3d_device_check": (_i, [_i]),
+    "wast3d_raster_forward": (_i, [C.POINTER(RasterParams), ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp,
+                                   _vp, _vp, _vp, C.POINTER(_i), _vp]),
+    "wast3d_raster_backward": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_raster_export_state": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_knn_scratch_bytes": (_sz, [_i]),
+    "wast3d_knn_dist2": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "wast3d_cluster_stats": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_nn_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_w2_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_adam_step": (_i, [_sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("WAST3D_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise RuntimeError(
+            f"{path} not found: build it with `python -m wast3d_b200._build` "
+            "(there is no CPU or PyTorch fallback for these kernels)")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str = "wast3d_b200"):
+    if status != 0:
+        msg = load().wast3d_strerror(status).decode()
+        raise RuntimeError(f"{what}: {msg} (status {status})")
+
+
+def require_device(t: torch.Tensor | None = None):
+    """The product path must fail loudly without the GPU (no silent eager fallback)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("wast3d_b200 needs a CUDA sm_100 device; there is no CPU fallback")
+    if t is not None and not t.is_cuda:
+        raise RuntimeError("wast3d_b200: expected a CUDA tensor, got one on " + str(t.device))
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def fptr(t: torch.Tensor | None, keep: list, dtype=torch.float32) -> int | None:
+    """data_ptr of a contiguous `dtype` CUDA view of t; None for empty/absent tensors
+    (the reference's "not provided" = size-0 tensor with null data_ptr)."""
+    if t is None or t.numel() == 0:
+        return None
+    if t.dtype != dtype:
+        raise RuntimeError(f"wast3d_b200: expected {dtype}, got {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError("wast3d_b200: expected a CUDA tensor, got one on " + str(t.device))
+    c = t.contiguous()
+    keep.append(c)
+    return c.data_ptr()
+
+
+class GrowBuffer:
+    """One of the three opaque byte buffers; plays resizeFunctional (rasterize_points.cu:27-33)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
+        self.error = None
+
+        def _alloc(nbytes, _user):
+            try:
+                self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+                return self.tensor.data_ptr()
+            except Exception as e:  # never let an exception cross the C boundary
+                self.error = e
+                return None
+
+        self.cb = ALLOC_FN(_alloc)

@@ -1,0 +1,183 @@
+// Shared device/host helpers and the opaque-buffer layouts of the rasteriser.
+// The layouts replace GeometryState / ImageState / BinningState of the reference
+// (cuda_rasterizer/rasterizer_impl.h:29-65, rasterizer_impl.cu:155-194); only the position of
+// final_T / n_contrib at the head of the image buffer is kept.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/wast3d_b200.h"
+
+namespace w3d {
+
+constexpr int TILE_X = 16;   // cuda_rasterizer/config.h:16-17
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+constexpr uint32_t CULLED_KEY = 0xFFFFFFFFu;
+
+#define W3D_CUDA_TRY(expr)                                                       \
+    do {                                                                         \
+        cudaError_t _e = (expr);                                                 \
+        if (_e != cudaSuccess) {                                                 \
+            w3d::set_last_cuda_error(_e, __FILE__, __LINE__);                    \
+            return WAST3D_ERR_CUDA;                                              \
+        }                                                                        \
+    } while (0)
+
+// After a kernel launch: always check the launch itself; with `debug` also synchronise
+// (the reference's CHECK_CUDA(A, debug), auxiliary.h:166-173).
+#define W3D_AFTER_LAUNCH(stream, debug)                                          \
+    do {                                                                         \
+        W3D_CUDA_TRY(cudaGetLastError());                                        \
+        if (debug) W3D_CUDA_TRY(cudaStreamSynchronize(stream));                  \
+    } while (0)
+
+void set_last_cuda_error(cudaError_t e, const char* file, int line);
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided chunk (or a null chunk for size queries) — plays the
+// role of obtain() (rasterizer_impl.h:21-27) / required<T>() (:67-73).
+struct Carver {
+    char* base;
+    size_t off;
+    explicit Carver(void* p) : base((char*)p), off(0) {}
+    template <typename T>
+    T* take(size_t count) {
+        off = align_up(off, 128);
+        T* p = base ? (T*)(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+    size_t bytes() const { return align_up(off, 128) + 128; }
+};
+
+// ---- radix sort / scan scratch sizes -------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;  // keys per block
+constexpr int RS_RADIX = 256;
+inline size_t rs_num_blocks(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
+inline size_t rs_hist_words(size_t n) { return rs_num_blocks(n) * RS_RADIX; }
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+inline size_t scan_num_blocks(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
+// block sums for a 2-level scan (level-1 sums are themselves scanned by one block in a loop)
+inline size_t scan_scratch_words(size_t n) { return scan_num_blocks(n) + 8; }
+
+// Per-Gaussian render record, 48 bytes, gathered with three 16-byte cp.async per instance.
+//   r0 = { mean2D.x, mean2D.y, view depth, cutoff half-extent x }
+//   r1 = { conic.x, conic.y, conic.z, opacity }                (forward.cu:254)
+//   r2 = { r, g, b, cutoff half-extent y }
+// The cutoff extents bound the region where alpha >= 1/255 can hold (forward.cu:354-356) and
+// are used only to skip work that the reference would skip pixel by pixel.
+struct GeomState {
+    float4* rec;             // [3P]
+    uint32_t* depth_key;     // [P]  float bits of view depth, CULLED_KEY if not rendered
+    uint32_t* tiles_touched; // [P]
+    int* internal_radii;     // [P]  used when the caller passes radii == NULL
+    uint8_t* clamped;        // [P]  bit c set <=> SH colour channel c was clamped (forward.cu:67-69)
+    uint32_t* key_tmp;       // [P]  radix ping-pong
+    uint32_t* order_a;       // [P]  Gaussian indices, final depth order lands here
+    uint32_t* order_b;       // [P]
+    uint32_t* offsets;       // [P]  exclusive scan of tiles_touched in depth order
+    uint32_t* rs_hist;       // [rs_hist_words(P)]
+    uint32_t* scan_scratch;  // [scan_scratch_words(max(P, rs_hist_words(P)))]
+    uint32_t* totals;        // [4]  {num_rendered, num_visible, ...}
+    float4* grad_rec;        // [3P] backward accumulators (see raster_backward.cu)
+
+    static GeomState carve(void* chunk, size_t P, size_t* bytes) {
+        Carver c(chunk);
+        GeomState g;
+        g.rec = c.take<float4>(3 * P);
+        g.depth_key = c.take<uint32_t>(P);
+        g.tiles_touched = c.take<uint32_t>(P);
+        g.internal_radii = c.take<int>(P);
+        g.clamped = c.take<uint8_t>(P);
+        g.key_tmp = c.take<uint32_t>(P);
+        g.order_a = c.take<uint32_t>(P);
+        g.order_b = c.take<uint32_t>(P);
+        g.offsets = c.take<uint32_t>(P);
+        g.rs_hist = c.take<uint32_t>(rs_hist_words(P));
+        size_t m = rs_hist_words(P) > P ? rs_hist_words(P) : P;
+        g.scan_scratch = c.take<uint32_t>(scan_scratch_words(m));
+        g.totals = c.take<uint32_t>(32);
+        g.grad_rec = c.take<float4>(3 * P);
+        if (bytes) *bytes = c.bytes();
+        return g;
+    }
+};
+
+struct ImageState {
+    float* final_T;       // [N]  offset 0 (alpha = 1 - final_T)
+    uint32_t* n_contrib;  // [N]
+    uint2* ranges;        // [T]
+    static ImageState carve(void* chunk, size_t N, size_t T, size_t* bytes) {
+        Carver c(chunk);
+        ImageState s;
+        s.final_T = c.take<float>(N);
+        s.n_contrib = c.take<uint32_t>(N);
+        s.ranges = c.take<uint2>(T);
+        if (bytes) *bytes = c.bytes();
+        return s;
+    }
+};
+
+struct BinningState {
+    uint32_t* keys_a;  // [R] tile ids in depth order, later the sorted tile ids
+    uint32_t* vals_a;  // [R] Gaussian ids; after the sort: the point list
+    uint32_t* keys_b;  // [R]
+    uint32_t* vals_b;  // [R]
+    uint32_t* rs_hist;       // [rs_hist_words(R)]
+    uint32_t* scan_scratch;  // [scan_scratch_words(rs_hist_words(R))]
+    static BinningState carve(void* chunk, size_t R, size_t* bytes) {
+        Carver c(chunk);
+        BinningState b;
+        b.keys_a = c.take<uint32_t>(R);
+        b.vals_a = c.take<uint32_t>(R);
+        b.keys_b = c.take<uint32_t>(R);
+        b.vals_b = c.take<uint32_t>(R);
+        b.rs_hist = c.take<uint32_t>(rs_hist_words(R));
+        b.scan_scratch = c.take<uint32_t>(scan_scratch_words(rs_hist_words(R)));
+        if (bytes) *bytes = c.bytes();
+        return b;
+    }
+};
+
+// number of bits needed to represent values in [0, n)
+inline int bits_for(uint32_t n) {
+    int b = 0;
+    while (b < 32 && (n - 1) >> b) ++b;
+    return n <= 1 ? 1 : b;
+}
+
+// ---- sort / scan launchers (scan_sort.cu) -------------------------------------------
+// out[i] = sum_{k<i} in[perm ? perm[k] : k]; total (optional) receives the full sum.
+int scan_exclusive_u32(const uint32_t* in, const uint32_t* perm, uint32_t* out, size_t n,
+                       uint32_t* scratch, uint32_t* total, cudaStream_t s, bool debug);
+// One stable LSD pass on bits [shift, shift+bits) (bits <= 8).  vals_in == NULL means iota.
+// keys_out == NULL means "do not write keys" (last pass).
+int radix_pass_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
+                   uint32_t* vals_out, size_t n, int shift, int bits, uint32_t* hist,
+                   uint32_t* scan_scratch, cudaStream_t s, bool debug);
+
+// ---- small device helpers -------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+}  // namespace w3d

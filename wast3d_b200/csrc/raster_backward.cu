@@ -1,0 +1,609 @@
+// Backward rasteriser for sm_100a: tile replay (K7) and the fused per-Gaussian chain rule (K8+K9).
+//
+// What it replaces (reference paths under submodules/diff-gaussian-rasterization/):
+//   renderCUDA (backward)       cuda_rasterizer/backward.cu:413-586   (10 atomicAdd per pixel-pair)
+//   computeCov2DCUDA            cuda_rasterizer/backward.cu:144-274
+//   preprocessCUDA (backward)   cuda_rasterizer/backward.cu:346-410 (+ :20-139 SH, :278-341 cov3D)
+//   Rasterizer::backward        cuda_rasterizer/rasterizer_impl.cu:345-446
+//   the ten torch::zeros of     rasterize_points.cu:157-166
+//
+// Design:
+//  * K7 keeps the reference's pixel-parallel back-to-front replay (same skip decisions, same
+//    recurrences) but never issues a per-pixel global atomic: the 10 partial gradients of a
+//    (warp, Gaussian) pair are reduced across the 32 pixels with a value-halving butterfly
+//    (13 shuffles instead of 50), added to a per-batch shared-memory accumulator (one shared
+//    atomic instruction per warp and Gaussian), and flushed once per (tile, Gaussian) with three
+//    16-byte vector atomics into a 48-byte gradient record.  Whole (warp, Gaussian) pairs that
+//    cannot contribute (alpha cutoff box misses the warp's 8x4 pixels, or the Gaussian lies
+//    behind every pixel's last contributor) are skipped before any per-pixel work, and batches
+//    behind the tile's last contributor are never loaded.
+//  * K8 and K9 are one kernel that consumes the gradient record, recomputes Sigma3D instead of
+//    reading a stored copy, and writes EVERY element of the eight output tensors (zeros for
+//    culled Gaussians), so no output memset is needed.
+//  Summation order across pixels differs from the reference's atomics (both are unordered);
+//  gradients agree to fp32 rounding, not bitwise (tests state the tolerance per tensor).
+#include "raster_math.cuh"
+
+namespace w3d {
+
+const uint32_t* point_list_ptr(const BinningState& b, uint32_t num_tiles);
+int validate_params(const wast3d_raster_params* p, bool forward);
+
+constexpr int BWD_BATCH = 256;
+constexpr int ACC_STRIDE = 12;
+// gradient record slots
+//  0 dmean2D.x  1 dmean2D.y  2 dconic.x  3 dconic.y | 4 dconic.w  5 dopacity  6 dviewdepth  7 - |
+//  8 dcolor.r   9 dcolor.g  10 dcolor.b  11 -
+
+// Sum v[0..11] over the warp.  On return lane L holds in the result the total of slot
+//   slot(L) = 6*b4 + 3*b3 + 2*b2 + b1   (b_k = bit k of L), valid when (2*b2+b1) < 3;
+// lanes L and L^1 hold the same value.
+__device__ __forceinline__ float warp_reduce12(const float (&v)[12], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+    float u[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float keep = h16 ? v[6 + i] : v[i];
+        const float send = h16 ? v[i] : v[6 + i];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    float w[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float keep = h8 ? u[3 + i] : u[i];
+        const float send = h8 ? u[i] : u[3 + i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float x[2];
+    {
+        // {w0,w1 | w2,pad}
+        const float keep0 = h4 ? w[2] : w[0];
+        const float send0 = h4 ? w[0] : w[2];
+        x[0] = keep0 + __shfl_xor_sync(0xffffffffu, send0, 4);
+        const float keep1 = h4 ? 0.0f : w[1];
+        const float send1 = h4 ? w[1] : 0.0f;
+        x[1] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 4);
+    }
+    const float keep = h2 ? x[1] : x[0];
+    const float send = h2 ? x[0] : x[1];
+    float y = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    return y;
+}
+
+__global__ void __launch_bounds__(TILE_PIX)
+render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                       const int W, const int H, const float* __restrict__ bg_color,
+                       const float4* __restrict__ rec, const float* __restrict__ sampling_offsets,
+                       const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+                       const float* __restrict__ dL_dpixels, const float* __restrict__ dL_ddepths,
+                       float4* __restrict__ grad_rec) {
+    __shared__ float4 s_r0[2][BWD_BATCH];
+    __shared__ float4 s_r1[2][BWD_BATCH];
+    __shared__ float4 s_r2[2][BWD_BATCH];
+    __shared__ uint32_t s_id[2][BWD_BATCH];
+    __shared__ __align__(16) float s_acc[BWD_BATCH * ACC_STRIDE];
+    __shared__ uint32_t s_touched[BWD_BATCH];
+    __shared__ uint32_t s_warp_max[TILE_PIX / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+
+    float2 pixf = make_float2((float)px, (float)py);
+    if (inside && sampling_offsets != nullptr) {
+        const float2 o = *reinterpret_cast<const float2*>(sampling_offsets + 2 * (size_t)pix_id);
+        pixf.x = (float)px + o.x;
+        pixf.y = (float)py + o.y;
+    }
+    const float inf = __int_as_float(0x7f800000);
+    float bx0 = inside ? pixf.x : inf, bx1 = inside ? pixf.x : -inf;
+    float by0 = inside ? pixf.y : inf, by1 = inside ? pixf.y : -inf;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
+        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
+        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
+    }
+
+    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+
+    // backward.cu:463-478
+    const float T_final = inside ? final_Ts[pix_id] : 0.f;
+    float T = T_final;
+    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+    const size_t HW = (size_t)H * W;
+    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, ddepth = 0.f;
+    if (inside) {
+        dpix0 = dL_dpixels[pix_id];
+        dpix1 = dL_dpixels[HW + pix_id];
+        dpix2 = dL_dpixels[2 * HW + pix_id];
+        ddepth = dL_ddepths ? dL_ddepths[pix_id] : 0.f;
+    }
+    // backward.cu:560-563 (pixel constant)
+    float bg_dot_dpixel = 0.f;
+    bg_dot_dpixel += bg_color[0] * dpix0;
+    bg_dot_dpixel += bg_color[1] * dpix1;
+    bg_dot_dpixel += bg_color[2] * dpix2;
+
+    // Nothing behind the tile's deepest last contributor can receive gradient.
+    const uint32_t warp_max_last = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0) s_warp_max[warp] = warp_max_last;
+    __syncthreads();
+    uint32_t n_eff = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_PIX / 32; ++w) n_eff = max(n_eff, s_warp_max[w]);
+    n_eff = min(n_eff, range.y - range.x);
+    const int n = (int)n_eff;
+    const int rounds = (n + BWD_BATCH - 1) / BWD_BATCH;
+
+    auto prefetch = [&](int b) {
+        const int p = b * BWD_BATCH + tid;
+        if (p < n) {
+            const uint32_t id = point_list[range.x + (uint32_t)(n - 1 - p)];
+            s_id[b & 1][tid] = id;
+            const float4* src = rec + 3 * (size_t)id;
+            cp_async16(&s_r0[b & 1][tid], src);
+            cp_async16(&s_r1[b & 1][tid], src + 1);
+            cp_async16(&s_r2[b & 1][tid], src + 2);
+        }
+        cp_async_commit();
+    };
+
+    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
+    float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
+    const float ddelx_dx = 0.5 * W;  // backward.cu:486-487
+    const float ddely_dy = 0.5 * H;
+
+    if (rounds > 0) prefetch(0);
+    for (int b = 0; b < rounds; ++b) {
+        // reset this batch's accumulators (nobody reads them until after the barrier below)
+        {
+            float4* z = reinterpret_cast<float4*>(s_acc + tid * ACC_STRIDE);
+            z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            s_touched[tid] = 0;
+        }
+        if (b + 1 < rounds) {
+            prefetch(b + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        const int cnt = min(BWD_BATCH, n - b * BWD_BATCH);
+        const float4* r0 = s_r0[b & 1];
+        const float4* r1 = s_r1[b & 1];
+        const float4* r2 = s_r2[b & 1];
+        if (warp_max_last > 0) {
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                const int jj = j0 + lane;
+                bool hit = false;
+                if (jj < cnt) {
+                    const uint32_t pos = (uint32_t)(n - 1 - (b * BWD_BATCH + jj));
+                    const float4 a = r0[jj];
+                    const float hy = r2[jj].w;
+                    hit = pos < warp_max_last &&
+                          !((a.x + a.w < bx0) || (a.x - a.w > bx1) || (a.y + hy < by0) ||
+                            (a.y - hy > by1));
+                }
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    const int j = j0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t pos = (uint32_t)(n - 1 - (b * BWD_BATCH + j));
+                    float v[12];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) v[i] = 0.f;
+                    bool active = false;
+                    // backward.cu:512-514: skip Gaussians behind this pixel's last contributor
+                    if (pos < last_contributor) {
+                        const float4 a = r0[j];
+                        const float4 con_o = r1[j];
+                        const float dx = __fsub_rn(a.x, pixf.x);
+                        const float dy = __fsub_rn(a.y, pixf.y);
+                        const float sy = __fmul_rn(__fmul_rn(con_o.z, dy), dy);
+                        const float sq = __fmaf_rn(dx, __fmul_rn(con_o.x, dx), sy);
+                        const float cr = __fmul_rn(__fmul_rn(con_o.y, dx), dy);
+                        const float power = __fmaf_rn(sq, -0.5f, -cr);
+                        if (!(power > 0.0f)) {
+                            const float G = expf(power);
+                            const float alpha = fminf(0.99f, __fmul_rn(con_o.w, G));
+                            if (!(alpha < 1.0f / 255.0f)) {
+                                active = true;
+                                const float4 c = r2[j];
+                                // backward.cu:529-563
+                                T = T / (1.f - alpha);
+                                const float dchannel_dcolor = alpha * T;
+                                float dL_dalpha = 0.0f;
+                                accum0 = last_alpha * last_c0 + (1.f - last_alpha) * accum0;
+                                last_c0 = c.x;
+                                dL_dalpha += (c.x - accum0) * dpix0;
+                                v[8] = dchannel_dcolor * dpix0;
+                                accum1 = last_alpha * last_c1 + (1.f - last_alpha) * accum1;
+                                last_c1 = c.y;
+                                dL_dalpha += (c.y - accum1) * dpix1;
+                                v[9] = dchannel_dcolor * dpix1;
+                                accum2 = last_alpha * last_c2 + (1.f - last_alpha) * accum2;
+                                last_c2 = c.z;
+                                dL_dalpha += (c.z - accum2) * dpix2;
+                                v[10] = dchannel_dcolor * dpix2;
+                                v[6] = dchannel_dcolor * ddepth;  // backward.cu:552
+
+                                dL_dalpha *= T;
+                                last_alpha = alpha;
+                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                                // backward.cu:567-583
+                                const float dL_dG = con_o.w * dL_dalpha;
+                                const float gdx = G * dx;
+                                const float gdy = G * dy;
+                                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+                                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+                                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                                v[1] = dL_dG * dG_ddely * ddely_dy;
+                                v[2] = -0.5f * gdx * dx * dL_dG;
+                                v[3] = -0.5f * gdx * dy * dL_dG;
+                                v[4] = -0.5f * gdy * dy * dL_dG;
+                                v[5] = G * dL_dalpha;
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, active)) {
+                        const float tot = warp_reduce12(v, lane);
+                        const int sub = ((lane >> 1) & 3);  // 2*b2 + b1
+                        const int slot = 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1) + sub;
+                        if (!(lane & 1) && sub < 3 && slot != 7 && slot != 11)
+                            atomicAdd(&s_acc[j * ACC_STRIDE + slot], tot);
+                        if (lane == 0) s_touched[j] = 1u;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // flush: one thread per Gaussian of the batch, three 16-byte vector reductions
+        if (tid < cnt && s_touched[tid]) {
+            const float4* a = reinterpret_cast<const float4*>(s_acc + tid * ACC_STRIDE);
+            float4* dst = grad_rec + 3 * (size_t)s_id[b & 1][tid];
+            atomicAdd(dst + 0, a[0]);
+            atomicAdd(dst + 1, a[1]);
+            atomicAdd(dst + 2, a[2]);
+        }
+        // the next iteration zeroes s_acc and prefetches into the other buffer; the barrier at
+        // the top of the next iteration orders those against this flush only partially, so:
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------ K8 + K9 ---------------
+constexpr int GB_THREADS = 128;
+constexpr int GB_WARPS = GB_THREADS / 32;
+constexpr int GB_SH_STRIDE = 49;
+
+__global__ void __launch_bounds__(GB_THREADS)
+gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
+                         const int* __restrict__ radii, const float* __restrict__ shs,
+                         const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
+                         const float* __restrict__ rotations, const float scale_modifier,
+                         const float* __restrict__ cov3D_precomp, const float* __restrict__ view,
+                         const float* __restrict__ proj, const float* __restrict__ campos,
+                         const float h_x, const float h_y, const float tan_fovx, const float tan_fovy,
+                         const float4* __restrict__ grad_rec, float* __restrict__ dL_dmean2D,
+                         float* __restrict__ dL_dconic_out, float* __restrict__ dL_dopacity,
+                         float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D,
+                         float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
+                         float* __restrict__ dL_dscale, float* __restrict__ dL_drot,
+                         float* __restrict__ dL_dviewdepth_out) {
+    __shared__ float s_sh[GB_WARPS][32 * GB_SH_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
+    const int warp_first = blockIdx.x * GB_THREADS + warp * 32;
+    const bool live = idx < P;
+    const bool vis = live && radii[idx] > 0;
+
+    float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
+    float3 dmean = make_float3(0.f, 0.f, 0.f);
+    float dcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float3 dscale = make_float3(0.f, 0.f, 0.f);
+    float4 drot = make_float4(0.f, 0.f, 0.f, 0.f);
+    float3 mean = make_float3(0.f, 0.f, 0.f);
+
+    if (vis) {
+        g0 = grad_rec[3 * (size_t)idx + 0];
+        g1 = grad_rec[3 * (size_t)idx + 1];
+        g2 = grad_rec[3 * (size_t)idx + 2];
+        mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+
+        float cov6[6];
+        float3 sc = make_float3(0.f, 0.f, 0.f);
+        float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cov3D_precomp != nullptr) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) cov6[k] = cov3D_precomp[6 * idx + k];
+        } else {
+            sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+            q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+            cov3d_from_scale_rot(sc, scale_modifier, q, cov6);
+        }
+
+        // ---- backward.cu:144-274 (computeCov2DCUDA)
+        Cov2DCtx cx;
+        const float3 cov2 = cov2d(mean, h_x, h_y, tan_fovx, tan_fovy, cov6, view, &cx);
+        const float3 dL_dconic = make_float3(g0.z, g0.w, g1.x);
+        const float limx = 1.3f * tan_fovx;
+        const float limy = 1.3f * tan_fovy;
+        const float x_grad_mul = cx.txtz < -limx || cx.txtz > limx ? 0 : 1;
+        const float y_grad_mul = cx.tytz < -limy || cx.tytz > limy ? 0 : 1;
+        const float3 t = cx.t;
+        const M3& T = cx.T;
+        const M3& Vrk = cx.Vrk;
+        const float a = cov2.x, b = cov2.y, c = cov2.z;
+        const float denom = a * c - b * b;
+        float dL_da = 0, dL_db = 0, dL_dc = 0;
+        const float denom2inv = 1.0f / ((denom * denom) + 0.0000001f);
+        if (denom2inv != 0) {
+            dL_da = denom2inv * (-c * c * dL_dconic.x + 2 * b * c * dL_dconic.y + (denom - a * c) * dL_dconic.z);
+            dL_dc = denom2inv * (-a * a * dL_dconic.z + 2 * a * b * dL_dconic.y + (denom - a * c) * dL_dconic.x);
+            dL_db = denom2inv * 2 * (b * c * dL_dconic.x - (denom + 2 * b * b) * dL_dconic.y + a * b * dL_dconic.z);
+
+            dcov[0] = (T.c[0][0] * T.c[0][0] * dL_da + T.c[0][0] * T.c[1][0] * dL_db + T.c[1][0] * T.c[1][0] * dL_dc);
+            dcov[3] = (T.c[0][1] * T.c[0][1] * dL_da + T.c[0][1] * T.c[1][1] * dL_db + T.c[1][1] * T.c[1][1] * dL_dc);
+            dcov[5] = (T.c[0][2] * T.c[0][2] * dL_da + T.c[0][2] * T.c[1][2] * dL_db + T.c[1][2] * T.c[1][2] * dL_dc);
+            dcov[1] = 2 * T.c[0][0] * T.c[0][1] * dL_da + (T.c[0][0] * T.c[1][1] + T.c[0][1] * T.c[1][0]) * dL_db + 2 * T.c[1][0] * T.c[1][1] * dL_dc;
+            dcov[2] = 2 * T.c[0][0] * T.c[0][2] * dL_da + (T.c[0][0] * T.c[1][2] + T.c[0][2] * T.c[1][0]) * dL_db + 2 * T.c[1][0] * T.c[1][2] * dL_dc;
+            dcov[4] = 2 * T.c[0][2] * T.c[0][1] * dL_da + (T.c[0][1] * T.c[1][2] + T.c[0][2] * T.c[1][1]) * dL_db + 2 * T.c[1][1] * T.c[1][2] * dL_dc;
+        }
+        const float dL_dT00 = 2 * (T.c[0][0] * Vrk.c[0][0] + T.c[0][1] * Vrk.c[0][1] + T.c[0][2] * Vrk.c[0][2]) * dL_da +
+                              (T.c[1][0] * Vrk.c[0][0] + T.c[1][1] * Vrk.c[0][1] + T.c[1][2] * Vrk.c[0][2]) * dL_db;
+        const float dL_dT01 = 2 * (T.c[0][0] * Vrk.c[1][0] + T.c[0][1] * Vrk.c[1][1] + T.c[0][2] * Vrk.c[1][2]) * dL_da +
+                              (T.c[1][0] * Vrk.c[1][0] + T.c[1][1] * Vrk.c[1][1] + T.c[1][2] * Vrk.c[1][2]) * dL_db;
+        const float dL_dT02 = 2 * (T.c[0][0] * Vrk.c[2][0] + T.c[0][1] * Vrk.c[2][1] + T.c[0][2] * Vrk.c[2][2]) * dL_da +
+                              (T.c[1][0] * Vrk.c[2][0] + T.c[1][1] * Vrk.c[2][1] + T.c[1][2] * Vrk.c[2][2]) * dL_db;
+        const float dL_dT10 = 2 * (T.c[1][0] * Vrk.c[0][0] + T.c[1][1] * Vrk.c[0][1] + T.c[1][2] * Vrk.c[0][2]) * dL_dc +
+                              (T.c[0][0] * Vrk.c[0][0] + T.c[0][1] * Vrk.c[0][1] + T.c[0][2] * Vrk.c[0][2]) * dL_db;
+        const float dL_dT11 = 2 * (T.c[1][0] * Vrk.c[1][0] + T.c[1][1] * Vrk.c[1][1] + T.c[1][2] * Vrk.c[1][2]) * dL_dc +
+                              (T.c[0][0] * Vrk.c[1][0] + T.c[0][1] * Vrk.c[1][1] + T.c[0][2] * Vrk.c[1][2]) * dL_db;
+        const float dL_dT12 = 2 * (T.c[1][0] * Vrk.c[2][0] + T.c[1][1] * Vrk.c[2][1] + T.c[1][2] * Vrk.c[2][2]) * dL_dc +
+                              (T.c[0][0] * Vrk.c[2][0] + T.c[0][1] * Vrk.c[2][1] + T.c[0][2] * Vrk.c[2][2]) * dL_db;
+
+        // W as in cov2d(): W.c[i][j] = view[4*j + i]
+        const float W00 = view[0], W01 = view[4], W02 = view[8];
+        const float W10 = view[1], W11 = view[5], W12 = view[9];
+        const float W20 = view[2], W21 = view[6], W22 = view[10];
+        const float dL_dJ00 = W00 * dL_dT00 + W01 * dL_dT01 + W02 * dL_dT02;
+        const float dL_dJ02 = W20 * dL_dT00 + W21 * dL_dT01 + W22 * dL_dT02;
+        const float dL_dJ11 = W10 * dL_dT10 + W11 * dL_dT11 + W12 * dL_dT12;
+        const float dL_dJ12 = W20 * dL_dT10 + W21 * dL_dT11 + W22 * dL_dT12;
+
+        const float tz = 1.f / t.z;
+        const float tz2 = tz * tz;
+        const float tz3 = tz2 * tz;
+        const float dL_dtx = x_grad_mul * -h_x * tz2 * dL_dJ02;
+        const float dL_dty = y_grad_mul * -h_y * tz2 * dL_dJ12;
+        const float dL_dtz = -h_x * tz2 * dL_dJ00 - h_y * tz2 * dL_dJ11 + (2 * h_x * t.x) * tz3 * dL_dJ02 + (2 * h_y * t.y) * tz3 * dL_dJ12;
+        dmean = xform_vec_4x3_T(make_float3(dL_dtx, dL_dty, dL_dtz), view);
+
+        // ---- backward.cu:372-401 (projection + view-depth terms)
+        const float4 m_hom = xform_point_4x4(mean, proj);
+        const float m_w = 1.0f / (m_hom.w + 0.0000001f);
+        const float mul1 = (proj[0] * mean.x + proj[4] * mean.y + proj[8] * mean.z + proj[12]) * m_w * m_w;
+        const float mul2 = (proj[1] * mean.x + proj[5] * mean.y + proj[9] * mean.z + proj[13]) * m_w * m_w;
+        float3 dm2;
+        dm2.x = (proj[0] * m_w - proj[3] * mul1) * g0.x + (proj[1] * m_w - proj[3] * mul2) * g0.y;
+        dm2.y = (proj[4] * m_w - proj[7] * mul1) * g0.x + (proj[5] * m_w - proj[7] * mul2) * g0.y;
+        dm2.z = (proj[8] * m_w - proj[11] * mul1) * g0.x + (proj[9] * m_w - proj[11] * mul2) * g0.y;
+        dm2.x += view[2] * g1.z;
+        dm2.y += view[6] * g1.z;
+        dm2.z += view[10] * g1.z;
+        dmean.x += dm2.x;
+        dmean.y += dm2.y;
+        dmean.z += dm2.z;
+
+        // ---- backward.cu:278-341 (Sigma3D -> scale, quaternion)
+        if (scales != nullptr) {
+            const M3 R = quat_to_R(q);
+            const float3 s = make_float3(scale_modifier * sc.x, scale_modifier * sc.y, scale_modifier * sc.z);
+            M3 S;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) S.c[i][j] = 0.0f;
+            S.c[0][0] = s.x; S.c[1][1] = s.y; S.c[2][2] = s.z;
+            const M3 Mm = m3_mul(S, R);
+            M3 dSig;
+            dSig.c[0][0] = dcov[0];        dSig.c[0][1] = 0.5f * dcov[1]; dSig.c[0][2] = 0.5f * dcov[2];
+            dSig.c[1][0] = 0.5f * dcov[1]; dSig.c[1][1] = dcov[3];        dSig.c[1][2] = 0.5f * dcov[4];
+            dSig.c[2][0] = 0.5f * dcov[2]; dSig.c[2][1] = 0.5f * dcov[4]; dSig.c[2][2] = dcov[5];
+            M3 M2;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) M2.c[i][j] = 2.0f * Mm.c[i][j];
+            const M3 dL_dM = m3_mul(M2, dSig);
+            const M3 Rt = m3_transpose(R);
+            M3 dMt = m3_transpose(dL_dM);
+            dscale.x = Rt.c[0][0] * dMt.c[0][0] + Rt.c[0][1] * dMt.c[0][1] + Rt.c[0][2] * dMt.c[0][2];
+            dscale.y = Rt.c[1][0] * dMt.c[1][0] + Rt.c[1][1] * dMt.c[1][1] + Rt.c[1][2] * dMt.c[1][2];
+            dscale.z = Rt.c[2][0] * dMt.c[2][0] + Rt.c[2][1] * dMt.c[2][1] + Rt.c[2][2] * dMt.c[2][2];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                dMt.c[0][k] *= s.x;
+                dMt.c[1][k] *= s.y;
+                dMt.c[2][k] *= s.z;
+            }
+            const float r = q.x, x = q.y, y = q.z, z = q.w;
+            drot.x = 2 * z * (dMt.c[0][1] - dMt.c[1][0]) + 2 * y * (dMt.c[2][0] - dMt.c[0][2]) + 2 * x * (dMt.c[1][2] - dMt.c[2][1]);
+            drot.y = 2 * y * (dMt.c[1][0] + dMt.c[0][1]) + 2 * z * (dMt.c[2][0] + dMt.c[0][2]) + 2 * r * (dMt.c[1][2] - dMt.c[2][1]) - 4 * x * (dMt.c[2][2] + dMt.c[1][1]);
+            drot.z = 2 * x * (dMt.c[1][0] + dMt.c[0][1]) + 2 * r * (dMt.c[2][0] - dMt.c[0][2]) + 2 * z * (dMt.c[1][2] + dMt.c[2][1]) - 4 * y * (dMt.c[2][2] + dMt.c[0][0]);
+            drot.w = 2 * r * (dMt.c[0][1] - dMt.c[1][0]) + 2 * x * (dMt.c[2][0] + dMt.c[0][2]) + 2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
+        }
+    }
+
+    // ---- backward.cu:20-139 (SH): staged in, gradients staged out through the same rows
+    if (shs != nullptr) {
+        const unsigned need = __ballot_sync(0xffffffffu, vis);
+        const int rows_valid = min(32, P - warp_first);
+        if (rows_valid > 0) {
+            const int row_floats = 3 * M;
+            const int used = 3 * (D + 1) * (D + 1);
+            float* row = s_sh[warp] + lane * GB_SH_STRIDE;
+            if (need)
+                stage_sh_rows(shs + (size_t)warp_first * row_floats, row_floats, used, rows_valid, need,
+                              s_sh[warp], GB_SH_STRIDE, lane);
+            __syncwarp();
+            if (vis) {
+                const float3 cam = make_float3(campos[0], campos[1], campos[2]);
+                const float3 dir_orig = make_float3(mean.x - cam.x, mean.y - cam.y, mean.z - cam.z);
+                const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
+                const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
+                const unsigned cb = clamped[idx];
+                float dRGB[3] = {g2.x, g2.y, g2.z};
+                dRGB[0] *= (cb & 1u) ? 0 : 1;
+                dRGB[1] *= (cb & 2u) ? 0 : 1;
+                dRGB[2] *= (cb & 4u) ? 0 : 1;
+
+                // pass 1: d(rgb)/d(dir), needs the coefficients
+                float ddir[3] = {0.f, 0.f, 0.f};
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float dx_ = 0.f, dy_ = 0.f, dz_ = 0.f;
+                    if (D > 0) {
+                        dx_ = -SH_C1 * row[9 + c];
+                        dy_ = -SH_C1 * row[3 + c];
+                        dz_ = SH_C1 * row[6 + c];
+                        if (D > 1) {
+                            dx_ += SH_C2[0] * y * row[12 + c] + SH_C2[2] * 2.f * -x * row[18 + c] + SH_C2[3] * z * row[21 + c] + SH_C2[4] * 2.f * x * row[24 + c];
+                            dy_ += SH_C2[0] * x * row[12 + c] + SH_C2[1] * z * row[15 + c] + SH_C2[2] * 2.f * -y * row[18 + c] + SH_C2[4] * 2.f * -y * row[24 + c];
+                            dz_ += SH_C2[1] * y * row[15 + c] + SH_C2[2] * 2.f * 2.f * z * row[18 + c] + SH_C2[3] * x * row[21 + c];
+                            if (D > 2) {
+                                dx_ += (SH_C3[0] * row[27 + c] * 3.f * 2.f * xy + SH_C3[1] * row[30 + c] * yz +
+                                        SH_C3[2] * row[33 + c] * -2.f * xy + SH_C3[3] * row[36 + c] * -3.f * 2.f * xz +
+                                        SH_C3[4] * row[39 + c] * (-3.f * xx + 4.f * zz - yy) +
+                                        SH_C3[5] * row[42 + c] * 2.f * xz + SH_C3[6] * row[45 + c] * 3.f * (xx - yy));
+                                dy_ += (SH_C3[0] * row[27 + c] * 3.f * (xx - yy) + SH_C3[1] * row[30 + c] * xz +
+                                        SH_C3[2] * row[33 + c] * (-3.f * yy + 4.f * zz - xx) +
+                                        SH_C3[3] * row[36 + c] * -3.f * 2.f * yz + SH_C3[4] * row[39 + c] * -2.f * xy +
+                                        SH_C3[5] * row[42 + c] * -2.f * yz + SH_C3[6] * row[45 + c] * -3.f * 2.f * xy);
+                                dz_ += (SH_C3[1] * row[30 + c] * xy + SH_C3[2] * row[33 + c] * 4.f * 2.f * yz +
+                                        SH_C3[3] * row[36 + c] * 3.f * (2.f * zz - xx - yy) +
+                                        SH_C3[4] * row[39 + c] * 4.f * 2.f * xz + SH_C3[5] * row[42 + c] * (xx - yy));
+                            }
+                        }
+                    }
+                    ddir[0] += dx_ * dRGB[c];
+                    ddir[1] += dy_ * dRGB[c];
+                    ddir[2] += dz_ * dRGB[c];
+                }
+                // dnormvdv (auxiliary.h:107-117)
+                {
+                    const float3 v = dir_orig;
+                    const float sum2 = v.x * v.x + v.y * v.y + v.z * v.z;
+                    const float invsum32 = 1.0f / sqrt(sum2 * sum2 * sum2);
+                    dmean.x += ((+sum2 - v.x * v.x) * ddir[0] - v.y * v.x * ddir[1] - v.z * v.x * ddir[2]) * invsum32;
+                    dmean.y += (-v.x * v.y * ddir[0] + (sum2 - v.y * v.y) * ddir[1] - v.z * v.y * ddir[2]) * invsum32;
+                    dmean.z += (-v.x * v.z * ddir[0] - v.y * v.z * ddir[1] + (sum2 - v.z * v.z) * ddir[2]) * invsum32;
+                }
+                // pass 2: d(rgb)/d(coefficients) overwrites this Gaussian's row
+                float basis[16];
+                basis[0] = SH_C0;
+                basis[1] = -SH_C1 * y; basis[2] = SH_C1 * z; basis[3] = -SH_C1 * x;
+                basis[4] = SH_C2[0] * xy; basis[5] = SH_C2[1] * yz; basis[6] = SH_C2[2] * (2.f * zz - xx - yy);
+                basis[7] = SH_C2[3] * xz; basis[8] = SH_C2[4] * (xx - yy);
+                basis[9] = SH_C3[0] * y * (3.f * xx - yy); basis[10] = SH_C3[1] * xy * z;
+                basis[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
+                basis[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+                basis[13] = SH_C3[4] * x * (4.f * zz - xx - yy); basis[14] = SH_C3[5] * z * (xx - yy);
+                basis[15] = SH_C3[6] * x * (xx - 3.f * yy);
+                const int ncoef = (D + 1) * (D + 1);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k < M) {
+                        const float bk = k < ncoef ? basis[k] : 0.f;
+                        row[3 * k + 0] = bk * dRGB[0];
+                        row[3 * k + 1] = bk * dRGB[1];
+                        row[3 * k + 2] = bk * dRGB[2];
+                    }
+                }
+            } else {
+                for (int e = 0; e < row_floats; ++e) row[e] = 0.f;
+            }
+            __syncwarp();
+            unstage_rows(dL_dsh + (size_t)warp_first * row_floats, row_floats, rows_valid, s_sh[warp],
+                         GB_SH_STRIDE, lane);
+        }
+    }
+
+    if (!live) return;
+    dL_dmean2D[3 * idx + 0] = g0.x;
+    dL_dmean2D[3 * idx + 1] = g0.y;
+    dL_dmean2D[3 * idx + 2] = 0.f;
+    dL_dcolor[3 * idx + 0] = g2.x;
+    dL_dcolor[3 * idx + 1] = g2.y;
+    dL_dcolor[3 * idx + 2] = g2.z;
+    dL_dopacity[idx] = g1.y;
+    dL_dmean3D[3 * idx + 0] = dmean.x;
+    dL_dmean3D[3 * idx + 1] = dmean.y;
+    dL_dmean3D[3 * idx + 2] = dmean.z;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = dcov[k];
+    dL_dscale[3 * idx + 0] = dscale.x;
+    dL_dscale[3 * idx + 1] = dscale.y;
+    dL_dscale[3 * idx + 2] = dscale.z;
+    *reinterpret_cast<float4*>(dL_drot + 4 * idx) = drot;
+    if (dL_dconic_out) *reinterpret_cast<float4*>(dL_dconic_out + 4 * idx) = make_float4(g0.z, g0.w, 0.f, g1.x);
+    if (dL_dviewdepth_out) dL_dviewdepth_out[idx] = g1.z;
+}
+
+}  // namespace w3d
+
+using namespace w3d;
+
+extern "C" int wast3d_raster_backward(const wast3d_raster_params* prm, int num_rendered,
+                                      const int* radii, void* geom_buffer, void* binning_buffer,
+                                      void* img_buffer, const float* dL_dpix, const float* dL_ddepth,
+                                      float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                                      float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                                      float* dL_dsh, float* dL_dscale, float* dL_drot,
+                                      float* dL_dcamViewDepth, void* stream_v) {
+    cudaStream_t s = (cudaStream_t)stream_v;
+    int st = validate_params(prm, false);
+    if (st != WAST3D_OK) return st;
+    const int P = prm->P, W = prm->width, H = prm->height;
+    if (P == 0) return WAST3D_OK;
+    if (num_rendered < 0 || !geom_buffer || !img_buffer || !binning_buffer || !dL_dpix ||
+        !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
+        !dL_drot || (prm->shs && prm->M > 0 && !dL_dsh))
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    const bool debug = prm->debug != 0;
+    const size_t N = (size_t)W * H;
+    const dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, 1);
+    const uint32_t num_tiles = grid.x * grid.y;
+    GeomState g = GeomState::carve(geom_buffer, P, nullptr);
+    ImageState im = ImageState::carve(img_buffer, N, num_tiles, nullptr);
+    BinningState bn = BinningState::carve(binning_buffer, (size_t)num_rendered, nullptr);
+    if (radii == nullptr) radii = g.internal_radii;
+
+    const float focal_y = H / (2.0f * prm->tan_fovy);
+    const float focal_x = W / (2.0f * prm->tan_fovx);
+
+    W3D_CUDA_TRY(cudaMemsetAsync(g.grad_rec, 0, 3 * (size_t)P * sizeof(float4), s));
+    if (num_rendered > 0) {
+        render_backward_kernel<<<grid, TILE_PIX, 0, s>>>(
+            im.ranges, point_list_ptr(bn, num_tiles), W, H, prm->background, g.rec,
+            prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec);
+        W3D_AFTER_LAUNCH(s, debug);
+    }
+    gaussian_backward_kernel<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
+        P, prm->D, prm->M, prm->means3D, radii, prm->shs, g.clamped, prm->scales, prm->rotations,
+        prm->scale_modifier, prm->cov3D_precomp, prm->viewmatrix, prm->projmatrix, prm->campos,
+        focal_x, focal_y, prm->tan_fovx, prm->tan_fovy, g.grad_rec, dL_dmean2D, dL_dconic,
+        dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dcamViewDepth);
+    W3D_AFTER_LAUNCH(s, debug);
+    return WAST3D_OK;
+}
+

@@ -1,0 +1,534 @@
+// Forward rasteriser for sm_100a: preprocess (K1), binning (K2-K5) and tile render (K6).
+//
+// What it replaces (reference paths under submodules/diff-gaussian-rasterization/):
+//   preprocessCUDA            cuda_rasterizer/forward.cu:155-256
+//   InclusiveSum + duplicateWithKeys + SortPairs + identifyTileRanges
+//                             cuda_rasterizer/rasterizer_impl.cu:70-138,279-320
+//   renderCUDA (forward)      cuda_rasterizer/forward.cu:261-390
+//   Rasterizer::forward       cuda_rasterizer/rasterizer_impl.cu:198-341
+//
+// Design differences (results are the same, see tests/):
+//  * K1 writes one 48-byte record per visible Gaussian (mean2D, depth, conic, opacity, rgb and
+//    the alpha-cutoff half extents) instead of seven separate arrays; SH coefficients are
+//    streamed with coalesced 16-byte loads through shared memory, only for Gaussians that
+//    survive culling and only up to the active degree.
+//  * The blend order (tile, depth, index) is produced by sorting the P Gaussians by depth
+//    (32-bit keys) and then stably partitioning the R instances by tile id (1-2 passes over
+//    8-byte pairs) instead of 6 passes over 12-byte (u64,u32) pairs.
+//  * K6 stages whole records (incl. rgb and depth) per batch with cp.async, double buffered;
+//    32 lanes test 32 Gaussians against the warp's 8x4 pixel block at once and the blend loop
+//    only visits survivors; warps retire independently (ballot) and the block leaves when all
+//    have (one __syncthreads_and per batch).
+#include "raster_math.cuh"
+
+namespace w3d {
+
+constexpr int PRE_THREADS = 128;
+constexpr int PRE_WARPS = PRE_THREADS / 32;
+constexpr int SH_MAX_ROW = 48;             // M = 16 coefficients x RGB
+constexpr int SH_STRIDE = SH_MAX_ROW + 1;  // odd -> conflict-free per-Gaussian reads
+
+// forward.cu:20-71.  `sh` points at this Gaussian's staged row (k-th coefficient at sh[3k..]).
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* sh, float3 pos, float3 campos,
+                                            unsigned* clamped_bits) {
+    float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
+    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
+    dir.x = dir.x / len;
+    dir.y = dir.y / len;
+    dir.z = dir.z / len;
+    float res[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float r = SH_C0 * sh[c];
+        if (deg > 0) {
+            const float x = dir.x, y = dir.y, z = dir.z;
+            r = r - SH_C1 * y * sh[3 + c] + SH_C1 * z * sh[6 + c] - SH_C1 * x * sh[9 + c];
+            if (deg > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z;
+                const float xy = x * y, yz = y * z, xz = x * z;
+                r = r + SH_C2[0] * xy * sh[12 + c] + SH_C2[1] * yz * sh[15 + c] +
+                    SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + SH_C2[3] * xz * sh[21 + c] +
+                    SH_C2[4] * (xx - yy) * sh[24 + c];
+                if (deg > 2) {
+                    r = r + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] +
+                        SH_C3[1] * xy * z * sh[30 + c] +
+                        SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
+                        SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
+                        SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] +
+                        SH_C3[5] * z * (xx - yy) * sh[42 + c] +
+                        SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+                }
+            }
+        }
+        r += 0.5f;
+        res[c] = r;
+    }
+    unsigned bits = 0;
+    if (res[0] < 0) bits |= 1u;
+    if (res[1] < 0) bits |= 2u;
+    if (res[2] < 0) bits |= 4u;
+    *clamped_bits = bits;
+    return make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
+}
+
+// Half extents of the axis-aligned box around { d : alpha(d) >= 1/255 } for conic (A,B,C) and
+// opacity o: alpha = o*exp(-q(d)), q = 0.5*(A dx^2 + C dy^2) + B dx dy, so the region is
+// q <= tau = ln(255 o) and |dx| <= sqrt(2 tau C / det), |dy| <= sqrt(2 tau A / det).
+// tau is padded for fp32 evaluation error of q (which grows with the conditioning A*C/det);
+// the box is used only to skip pixel blocks where the reference's per-pixel test
+// (forward.cu:355) is certain to reject.
+__device__ __forceinline__ float2 cutoff_extent(float A, float B, float C, float o) {
+    if (!(o >= 1.0f / 255.0f)) return make_float2(-1.0f, -1.0f);  // alpha <= o < 1/255 always
+    const double det = (double)A * (double)C - (double)B * (double)B;
+    const float inf = __int_as_float(0x7f800000);
+    if (!(det > 0.0) || !(A > 0.f) || !(C > 0.f)) return make_float2(inf, inf);
+    const double tau0 = log(255.0 * (double)o);
+    const double kappa = (double)A * (double)C / det;
+    const double tau = tau0 + 1e-3 + tau0 * (1e-3 + 4e-6 * kappa);
+    const float hx = (float)(sqrt(2.0 * tau * (double)C / det) * 1.001 + 0.05);
+    const float hy = (float)(sqrt(2.0 * tau * (double)A / det) * 1.001 + 0.05);
+    if (!(hx == hx) || !(hy == hy)) return make_float2(inf, inf);
+    return make_float2(hx, hy);
+}
+
+__global__ void __launch_bounds__(PRE_THREADS)
+preprocess_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
+                  const float* __restrict__ scales, const float scale_modifier,
+                  const float* __restrict__ rotations, const float* __restrict__ opacities,
+                  const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
+                  const float* __restrict__ colors_precomp, const float* __restrict__ viewmatrix,
+                  const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
+                  const int W, const int H, const float tan_fovx, const float tan_fovy,
+                  const float focal_x, const float focal_y, const dim3 grid,
+                  const bool prefiltered, int* __restrict__ radii, float4* __restrict__ rec,
+                  uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
+                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ flags) {
+    __shared__ float s_sh[PRE_WARPS][32 * SH_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const int warp_first = blockIdx.x * PRE_THREADS + warp * 32;
+    const bool live = idx < P;
+
+    bool visible = false;
+    int my_radius_i = 0;
+    uint32_t n_tiles = 0;
+    float3 p_orig = make_float3(0.f, 0.f, 0.f);
+    float3 p_view = make_float3(0.f, 0.f, 0.f);
+    float2 point_image = make_float2(0.f, 0.f);
+    float3 conic = make_float3(0.f, 0.f, 0.f);
+
+    if (live) {
+        p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+        // in_frustum (auxiliary.h:139-164): near plane only
+        p_view = xform_point_4x3(p_orig, viewmatrix);
+        if (p_view.z <= 0.2f) {
+            if (prefiltered) atomicOr(flags, 1u);  // reference: printf + __trap()
+        } else {
+            float4 p_hom = xform_point_4x4(p_orig, projmatrix);
+            float p_w = 1.0f / (p_hom.w + 0.0000001f);
+            float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
+
+            float cov6[6];
+            if (cov3D_precomp != nullptr) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) cov6[k] = cov3D_precomp[6 * idx + k];
+            } else {
+                const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+                const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+                cov3d_from_scale_rot(sc, scale_modifier, q, cov6);
+            }
+            float3 cov = cov2d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov6, viewmatrix, nullptr);
+
+            // EWA inverse (forward.cu:219-223)
+            float det = (cov.x * cov.z - cov.y * cov.y);
+            if (det != 0.0f) {
+                float det_inv = 1.f / det;
+                conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
+                float mid = 0.5f * (cov.x + cov.z);
+                float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
+                float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
+                float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
+                point_image = make_float2(ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H));
+                uint2 rect_min, rect_max;
+                tile_rect(point_image, (int)my_radius, rect_min, rect_max, grid);
+                n_tiles = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+                if (n_tiles != 0) {
+                    visible = true;
+                    my_radius_i = (int)my_radius;
+                }
+            }
+        }
+    }
+
+    // colour: SH -> RGB for survivors only
+    float3 rgb = make_float3(0.f, 0.f, 0.f);
+    unsigned clamp_bits = 0;
+    if (colors_precomp == nullptr) {
+        const unsigned need = __ballot_sync(0xffffffffu, visible);
+        if (need) {
+            const int rows_valid = min(32, P - warp_first);
+            const int row_floats = 3 * M;
+            const int used = 3 * (D + 1) * (D + 1);
+            stage_sh_rows(shs + (size_t)warp_first * row_floats, row_floats, used, rows_valid, need,
+                          s_sh[warp], SH_STRIDE, lane);
+            __syncwarp();
+            if (visible) rgb = sh_to_rgb(D, s_sh[warp] + lane * SH_STRIDE, p_orig, *reinterpret_cast<const float3*>(cam_pos) , &clamp_bits);
+        }
+    } else if (visible) {
+        rgb = make_float3(colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]);
+    }
+
+    if (!live) return;
+    radii[idx] = my_radius_i;
+    tiles_touched[idx] = visible ? n_tiles : 0u;
+    clamped[idx] = (uint8_t)clamp_bits;
+    depth_key[idx] = visible ? __float_as_uint(p_view.z) : CULLED_KEY;
+    if (visible) {
+        const float o = opacities[idx];
+        const float2 ext = cutoff_extent(conic.x, conic.y, conic.z, o);
+        rec[3 * idx + 0] = make_float4(point_image.x, point_image.y, p_view.z, ext.x);
+        rec[3 * idx + 1] = make_float4(conic.x, conic.y, conic.z, o);
+        rec[3 * idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, ext.y);
+    }
+}
+
+// rasterizer_impl.cu:54-66
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                    const float* __restrict__ viewmatrix, unsigned char* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    float3 p = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    float3 v = xform_point_4x3(p, viewmatrix);
+    present[idx] = v.z <= 0.2f ? 0 : 1;
+}
+
+// One thread per Gaussian in DEPTH order: emits (tile id, Gaussian id) for every tile of its
+// rectangle (row-major, like duplicateWithKeys rasterizer_impl.cu:98-109) at its scanned
+// offset.  Since inputs come in (depth, index) order a stable partition by tile id then gives
+// the reference's (tile, depth, index) order.
+__global__ void __launch_bounds__(256)
+emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
+                      const uint32_t* __restrict__ tiles_touched, const int* __restrict__ radii,
+                      const float4* __restrict__ rec, uint32_t* __restrict__ keys,
+                      uint32_t* __restrict__ vals, const dim3 grid) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P) return;
+    const uint32_t i = order[k];
+    if (tiles_touched[i] == 0) return;
+    uint32_t off = offsets[k];
+    const float4 r0 = rec[3 * i];
+    uint2 rect_min, rect_max;
+    tile_rect(make_float2(r0.x, r0.y), radii[i], rect_min, rect_max, grid);
+    for (uint32_t y = rect_min.y; y < rect_max.y; ++y)
+        for (uint32_t x = rect_min.x; x < rect_max.x; ++x) {
+            keys[off] = y * grid.x + x;
+            vals[off] = i;
+            ++off;
+        }
+}
+
+// rasterizer_impl.cu:116-138 on 32-bit tile ids
+__global__ void __launch_bounds__(256)
+tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ sorted_tiles, uint2* __restrict__ ranges) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= L) return;
+    const uint32_t cur = sorted_tiles[idx];
+    if (idx == 0)
+        ranges[cur].x = 0;
+    else {
+        const uint32_t prev = sorted_tiles[idx - 1];
+        if (cur != prev) {
+            ranges[prev].y = idx;
+            ranges[cur].x = idx;
+        }
+    }
+    if (idx == L - 1) ranges[cur].y = L;
+}
+
+// ------------------------------------------------------------------ K6 -------------------
+constexpr int RENDER_BATCH = 256;
+
+__global__ void __launch_bounds__(TILE_PIX)
+render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                      const int W, const int H, const float4* __restrict__ rec,
+                      const float* __restrict__ bg_color, const float* __restrict__ sampling_offsets,
+                      float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                      float* __restrict__ out_color, float* __restrict__ out_depth) {
+    __shared__ float4 s_r0[2][RENDER_BATCH];
+    __shared__ float4 s_r1[2][RENDER_BATCH];
+    __shared__ float4 s_r2[2][RENDER_BATCH];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // warp = 8x4 pixel block inside the 16x16 tile
+    const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+
+    float2 pixf = make_float2((float)px, (float)py);
+    if (inside && sampling_offsets != nullptr) {
+        const float2 o = *reinterpret_cast<const float2*>(sampling_offsets + 2 * (size_t)pix_id);
+        pixf.x = (float)px + o.x;
+        pixf.y = (float)py + o.y;
+    }
+    // bounding box of this warp's sample positions
+    const float inf = __int_as_float(0x7f800000);
+    float bx0 = inside ? pixf.x : inf, bx1 = inside ? pixf.x : -inf;
+    float by0 = inside ? pixf.y : inf, by1 = inside ? pixf.y : -inf;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
+        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
+        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
+    }
+
+    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+    const int n = (int)(range.y - range.x);
+    const int rounds = (n + RENDER_BATCH - 1) / RENDER_BATCH;
+
+    auto prefetch = [&](int b) {
+        const int p = b * RENDER_BATCH + tid;
+        if (p < n) {
+            const uint32_t id = point_list[range.x + p];
+            const float4* src = rec + 3 * (size_t)id;
+            cp_async16(&s_r0[b & 1][tid], src);
+            cp_async16(&s_r1[b & 1][tid], src + 1);
+            cp_async16(&s_r2[b & 1][tid], src + 2);
+        }
+        cp_async_commit();
+    };
+
+    bool done = !inside;
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+
+    if (rounds > 0) prefetch(0);
+    for (int b = 0; b < rounds; ++b) {
+        if (b + 1 < rounds) {
+            prefetch(b + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        bool warp_done = __all_sync(0xffffffffu, done);
+        if (!warp_done) {
+            const int cnt = min(RENDER_BATCH, n - b * RENDER_BATCH);
+            const float4* r0 = s_r0[b & 1];
+            const float4* r1 = s_r1[b & 1];
+            const float4* r2 = s_r2[b & 1];
+            for (int j0 = 0; j0 < cnt && !warp_done; j0 += 32) {
+                // 32 lanes test 32 Gaussians against the warp's sample box
+                const int jj = j0 + lane;
+                bool hit = false;
+                if (jj < cnt) {
+                    const float4 a = r0[jj];
+                    const float hy = r2[jj].w;
+                    // "not certainly outside" so that NaNs fall through to the exact test
+                    hit = !((a.x + a.w < bx0) || (a.x - a.w > bx1) || (a.y + hy < by0) ||
+                            (a.y - hy > by1));
+                }
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    const int j = j0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    if (!done) {
+                        const float4 a = r0[j];
+                        const float4 con_o = r1[j];
+                        // forward.cu:343-346, FMA structure pinned to the reference's SASS
+                        const float dx = __fsub_rn(a.x, pixf.x);
+                        const float dy = __fsub_rn(a.y, pixf.y);
+                        const float sy = __fmul_rn(__fmul_rn(con_o.z, dy), dy);
+                        const float sq = __fmaf_rn(dx, __fmul_rn(con_o.x, dx), sy);
+                        const float cr = __fmul_rn(__fmul_rn(con_o.y, dx), dy);
+                        const float power = __fmaf_rn(sq, -0.5f, -cr);
+                        if (!(power > 0.0f)) {
+                            const float alpha = fminf(0.99f, __fmul_rn(con_o.w, expf(power)));
+                            if (!(alpha < 1.0f / 255.0f)) {
+                                const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                                if (test_T < 0.0001f) {
+                                    done = true;
+                                } else {
+                                    const float4 c = r2[j];
+                                    C0 = __fmaf_rn(T, __fmul_rn(alpha, c.x), C0);
+                                    C1 = __fmaf_rn(T, __fmul_rn(alpha, c.y), C1);
+                                    C2 = __fmaf_rn(T, __fmul_rn(alpha, c.z), C2);
+                                    Dp = __fmaf_rn(T, __fmul_rn(alpha, a.z), Dp);
+                                    T = test_T;
+                                    last_contributor = (uint32_t)(b * RENDER_BATCH + j + 1);
+                                }
+                            }
+                        }
+                    }
+                    if (__all_sync(0xffffffffu, done)) {
+                        warp_done = true;
+                        break;
+                    }
+                }
+            }
+        }
+        // also fences the buffer that the next iteration's prefetch will overwrite
+        if (__syncthreads_and(warp_done)) break;
+    }
+    cp_async_wait<0>();
+
+    if (inside) {
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+        const size_t HW = (size_t)H * W;
+        out_color[pix_id] = __fmaf_rn(bg_color[0], T, C0);
+        out_color[HW + pix_id] = __fmaf_rn(bg_color[1], T, C1);
+        out_color[2 * HW + pix_id] = __fmaf_rn(bg_color[2], T, C2);
+        out_depth[pix_id] = Dp;
+    }
+}
+
+// ------------------------------------------------------------------ host -----------------
+static int tile_sort_passes(uint32_t num_tiles, int* bits_per_pass) {
+    const int bits = bits_for(num_tiles);
+    const int passes = (bits + 7) / 8;
+    *bits_per_pass = (bits + passes - 1) / passes;
+    return passes;
+}
+
+const uint32_t* point_list_ptr(const BinningState& b, uint32_t num_tiles) {
+    int bpp;
+    return (tile_sort_passes(num_tiles, &bpp) & 1) ? b.vals_b : b.vals_a;
+}
+const uint32_t* sorted_tiles_ptr(const BinningState& b, uint32_t num_tiles) {
+    int bpp;
+    return (tile_sort_passes(num_tiles, &bpp) & 1) ? b.keys_b : b.keys_a;
+}
+
+int validate_params(const wast3d_raster_params* p, bool forward) {
+    if (!p) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (p->P < 0 || p->width <= 0 || p->height <= 0) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (p->P == 0) return WAST3D_OK;
+    if (!p->means3D || (forward && !p->opacities) || !p->viewmatrix || !p->projmatrix || !p->campos ||
+        !p->background)
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    if ((p->shs == nullptr) == (p->colors_precomp == nullptr)) return WAST3D_ERR_INVALID_ARGUMENT;
+    const bool has_sr = p->scales != nullptr && p->rotations != nullptr;
+    if (has_sr == (p->cov3D_precomp != nullptr)) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (p->shs) {
+        if (p->D < 0 || p->D > 3 || p->M < (p->D + 1) * (p->D + 1) || p->M > 16)
+            return WAST3D_ERR_INVALID_ARGUMENT;
+    }
+    return WAST3D_OK;
+}
+
+}  // namespace w3d
+
+using namespace w3d;
+
+extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_alloc_fn geom_alloc,
+                                     void* geom_user, wast3d_alloc_fn binning_alloc,
+                                     void* binning_user, wast3d_alloc_fn img_alloc, void* img_user,
+                                     float* out_color, float* out_depth, int* radii,
+                                     int* num_rendered_host, void* stream_v) {
+    cudaStream_t s = (cudaStream_t)stream_v;
+    int st = validate_params(prm, true);
+    if (st != WAST3D_OK) return st;
+    if (!geom_alloc || !binning_alloc || !img_alloc || !out_color || !out_depth || !num_rendered_host)
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    const int P = prm->P, W = prm->width, H = prm->height;
+    const bool debug = prm->debug != 0;
+    const size_t N = (size_t)W * H;
+    *num_rendered_host = 0;
+    if (P == 0) {
+        // rasterize_points.cu:69-70,83: outputs stay at their zero fill, buffers stay empty
+        W3D_CUDA_TRY(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), s));
+        W3D_CUDA_TRY(cudaMemsetAsync(out_depth, 0, N * sizeof(float), s));
+        return WAST3D_OK;
+    }
+    const dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, 1);
+    const uint32_t num_tiles = grid.x * grid.y;
+
+    size_t geom_bytes, img_bytes;
+    GeomState::carve(nullptr, P, &geom_bytes);
+    ImageState::carve(nullptr, N, num_tiles, &img_bytes);
+    void* geom_chunk = geom_alloc(geom_bytes, geom_user);
+    void* img_chunk = img_alloc(img_bytes, img_user);
+    if (!geom_chunk || !img_chunk) return WAST3D_ERR_ALLOC;
+    GeomState g = GeomState::carve(geom_chunk, P, nullptr);
+    ImageState im = ImageState::carve(img_chunk, N, num_tiles, nullptr);
+    if (radii == nullptr) radii = g.internal_radii;
+
+    // rasterizer_impl.cu:224-225
+    const float focal_y = H / (2.0f * prm->tan_fovy);
+    const float focal_x = W / (2.0f * prm->tan_fovx);
+
+    W3D_CUDA_TRY(cudaMemsetAsync(g.totals, 0, 32 * sizeof(uint32_t), s));
+    preprocess_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(
+        P, prm->D, prm->M, prm->means3D, prm->scales, prm->scale_modifier, prm->rotations,
+        prm->opacities, prm->shs, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
+        prm->projmatrix, prm->campos, W, H, prm->tan_fovx, prm->tan_fovy, focal_x, focal_y, grid,
+        prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.totals + 1);
+    W3D_AFTER_LAUNCH(s, debug);
+
+    // depth order: 4 stable 8-bit passes on the float bits (positive floats order like uints)
+    st = radix_pass_u32(g.depth_key, nullptr, g.key_tmp, g.order_b, P, 0, 8, g.rs_hist, g.scan_scratch, s, debug);
+    if (st) return st;
+    st = radix_pass_u32(g.key_tmp, g.order_b, g.depth_key, g.order_a, P, 8, 8, g.rs_hist, g.scan_scratch, s, debug);
+    if (st) return st;
+    st = radix_pass_u32(g.depth_key, g.order_a, g.key_tmp, g.order_b, P, 16, 8, g.rs_hist, g.scan_scratch, s, debug);
+    if (st) return st;
+    st = radix_pass_u32(g.key_tmp, g.order_b, nullptr, g.order_a, P, 24, 8, g.rs_hist, g.scan_scratch, s, debug);
+    if (st) return st;
+
+    st = scan_exclusive_u32(g.tiles_touched, g.order_a, g.offsets, P, g.scan_scratch, g.totals, s, debug);
+    if (st) return st;
+
+    // the one blocking read the reference also has (rasterizer_impl.cu:283)
+    uint32_t host_totals[2] = {0, 0};
+    W3D_CUDA_TRY(cudaMemcpyAsync(host_totals, g.totals, sizeof(host_totals), cudaMemcpyDeviceToHost, s));
+    W3D_CUDA_TRY(cudaStreamSynchronize(s));
+    if (host_totals[1] & 1u) return WAST3D_ERR_INVALID_ARGUMENT;  // prefiltered violated
+    if (host_totals[0] > 0x7FFFFFFFu) return WAST3D_ERR_OVERFLOW;
+    const uint32_t R = host_totals[0];
+    *num_rendered_host = (int)R;
+
+    size_t bin_bytes;
+    BinningState::carve(nullptr, R, &bin_bytes);
+    void* bin_chunk = binning_alloc(bin_bytes, binning_user);
+    if (!bin_chunk) return WAST3D_ERR_ALLOC;
+    BinningState bn = BinningState::carve(bin_chunk, R, nullptr);
+
+    W3D_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, num_tiles * sizeof(uint2), s));
+    if (R > 0) {
+        emit_instances_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.order_a, g.offsets, g.tiles_touched,
+                                                               radii, g.rec, bn.keys_a, bn.vals_a, grid);
+        W3D_AFTER_LAUNCH(s, debug);
+        int bpp;
+        const int passes = tile_sort_passes(num_tiles, &bpp);
+        uint32_t *kin = bn.keys_a, *vin = bn.vals_a, *kout = bn.keys_b, *vout = bn.vals_b;
+        for (int p = 0; p < passes; ++p) {
+            st = radix_pass_u32(kin, vin, kout, vout, R, p * bpp, bpp, bn.rs_hist, bn.scan_scratch, s, debug);
+            if (st) return st;
+            uint32_t* t;
+            t = kin; kin = kout; kout = t;
+            t = vin; vin = vout; vout = t;
+        }
+        tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted_tiles_ptr(bn, num_tiles), im.ranges);
+        W3D_AFTER_LAUNCH(s, debug);
+    }
+
+    render_forward_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, point_list_ptr(bn, num_tiles), W, H, g.rec,
+                                                    prm->background, prm->sampling_offsets, im.final_T,
+                                                    im.n_contrib, out_color, out_depth);
+    W3D_AFTER_LAUNCH(s, debug);
+    return WAST3D_OK;
+}
+
+extern "C" int wast3d_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                                   const float* projmatrix, unsigned char* present, void* stream_v) {
+    (void)projmatrix;  // checkFrustum only uses the view-space depth (auxiliary.h:154)
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (P == 0) return WAST3D_OK;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, means3D, viewmatrix, present);
+    W3D_AFTER_LAUNCH(s, false);
+    return WAST3D_OK;
+}

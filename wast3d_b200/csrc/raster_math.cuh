@@ -1,0 +1,222 @@
+// Per-Gaussian projection maths shared by the forward and backward rasteriser kernels.
+// Expression shapes (operand order, parenthesisation) deliberately follow the reference so that
+// nvcc's default FMA contraction produces the same roundings:
+//   transformPoint4x3/4x4, ndc2Pix, getRect      cuda_rasterizer/auxiliary.h:41-77
+//   computeCov3D                                 cuda_rasterizer/forward.cu:118-152
+//   computeCov2D                                 cuda_rasterizer/forward.cu:74-113
+// The reference uses GLM (column-major mat3, operator* as in glm/detail/type_mat3x3.inl:486-520);
+// here a 9-float struct with the same element expressions replaces it.
+#pragma once
+#include "common.cuh"
+
+namespace w3d {
+
+__device__ const float SH_C0 = 0.28209479177387814f;
+__device__ const float SH_C1 = 0.4886025119029199f;
+__device__ const float SH_C2[] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                  -1.0925484305920792f, 0.5462742152960396f};
+__device__ const float SH_C3[] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                  0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                  -0.5900435899266435f};
+
+// c[col][row], like glm::mat3
+struct M3 {
+    float c[3][3];
+};
+
+__device__ __forceinline__ M3 m3_mul(const M3& a, const M3& b) {
+    M3 r;
+#pragma unroll
+    for (int col = 0; col < 3; ++col)
+#pragma unroll
+        for (int row = 0; row < 3; ++row)
+            r.c[col][row] = a.c[0][row] * b.c[col][0] + a.c[1][row] * b.c[col][1] +
+                            a.c[2][row] * b.c[col][2];
+    return r;
+}
+__device__ __forceinline__ M3 m3_transpose(const M3& a) {
+    M3 r;
+#pragma unroll
+    for (int col = 0; col < 3; ++col)
+#pragma unroll
+        for (int row = 0; row < 3; ++row) r.c[col][row] = a.c[row][col];
+    return r;
+}
+
+__device__ __forceinline__ float3 xform_point_4x3(const float3& p, const float* __restrict__ m) {
+    return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+                       m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+}
+__device__ __forceinline__ float4 xform_point_4x4(const float3& p, const float* __restrict__ m) {
+    return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12],
+                       m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
+                       m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14],
+                       m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
+}
+__device__ __forceinline__ float3 xform_vec_4x3_T(const float3& p, const float* __restrict__ m) {
+    return make_float3(m[0] * p.x + m[1] * p.y + m[2] * p.z, m[4] * p.x + m[5] * p.y + m[6] * p.z,
+                       m[8] * p.x + m[9] * p.y + m[10] * p.z);
+}
+
+// auxiliary.h:41-44 — note the double-precision literals of the reference.
+__device__ __forceinline__ float ndc_to_pix(float v, int S) { return ((v + 1.0) * S - 1.0) * 0.5; }
+
+// auxiliary.h:46-56
+__device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2& rect_min,
+                                          uint2& rect_max, const dim3 grid) {
+    rect_min = {min(grid.x, (unsigned)max((int)0, (int)((p.x - max_radius) / TILE_X))),
+                min(grid.y, (unsigned)max((int)0, (int)((p.y - max_radius) / TILE_Y)))};
+    rect_max = {min(grid.x, (unsigned)max((int)0, (int)((p.x + max_radius + TILE_X - 1) / TILE_X))),
+                min(grid.y, (unsigned)max((int)0, (int)((p.y + max_radius + TILE_Y - 1) / TILE_Y)))};
+}
+
+// Rotation matrix from the quaternion AS GIVEN (r,x,y,z) — not normalised (forward.cu:127).
+__device__ __forceinline__ M3 quat_to_R(const float4 q) {
+    const float r = q.x, x = q.y, y = q.z, z = q.w;
+    M3 R;
+    R.c[0][0] = 1.f - 2.f * (y * y + z * z);
+    R.c[0][1] = 2.f * (x * y - r * z);
+    R.c[0][2] = 2.f * (x * z + r * y);
+    R.c[1][0] = 2.f * (x * y + r * z);
+    R.c[1][1] = 1.f - 2.f * (x * x + z * z);
+    R.c[1][2] = 2.f * (y * z - r * x);
+    R.c[2][0] = 2.f * (x * z - r * y);
+    R.c[2][1] = 2.f * (y * z + r * x);
+    R.c[2][2] = 1.f - 2.f * (x * x + y * y);
+    return R;
+}
+
+__device__ __forceinline__ M3 scale_rot_M(const float3 scale, float mod, const float4 q) {
+    M3 S;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) S.c[i][j] = 0.0f;
+    S.c[0][0] = mod * scale.x;
+    S.c[1][1] = mod * scale.y;
+    S.c[2][2] = mod * scale.z;
+    return m3_mul(S, quat_to_R(q));
+}
+
+// forward.cu:118-152: Sigma = M^T M, six upper-triangular entries
+__device__ __forceinline__ void cov3d_from_scale_rot(const float3 scale, float mod, const float4 q,
+                                                     float* cov6) {
+    M3 M = scale_rot_M(scale, mod, q);
+    M3 Sg = m3_mul(m3_transpose(M), M);
+    cov6[0] = Sg.c[0][0];
+    cov6[1] = Sg.c[0][1];
+    cov6[2] = Sg.c[0][2];
+    cov6[3] = Sg.c[1][1];
+    cov6[4] = Sg.c[1][2];
+    cov6[5] = Sg.c[2][2];
+}
+
+struct Cov2DCtx {
+    float3 t;         // clamped view-space point
+    float txtz, tytz; // unclamped ratios (for the backward's gradient mask)
+    M3 T;             // W * J
+    M3 Vrk;
+};
+
+// forward.cu:74-113 (and the recomputation at backward.cu:166-194)
+__device__ __forceinline__ float3 cov2d(const float3& mean, float focal_x, float focal_y,
+                                        float tan_fovx, float tan_fovy, const float* cov3D,
+                                        const float* __restrict__ view, Cov2DCtx* ctx) {
+    float3 t = xform_point_4x3(mean, view);
+    const float limx = 1.3f * tan_fovx;
+    const float limy = 1.3f * tan_fovy;
+    const float txtz = t.x / t.z;
+    const float tytz = t.y / t.z;
+    t.x = min(limx, max(-limx, txtz)) * t.z;
+    t.y = min(limy, max(-limy, tytz)) * t.z;
+
+    M3 J;
+    J.c[0][0] = focal_x / t.z;
+    J.c[0][1] = 0.0f;
+    J.c[0][2] = -(focal_x * t.x) / (t.z * t.z);
+    J.c[1][0] = 0.0f;
+    J.c[1][1] = focal_y / t.z;
+    J.c[1][2] = -(focal_y * t.y) / (t.z * t.z);
+    J.c[2][0] = 0;
+    J.c[2][1] = 0;
+    J.c[2][2] = 0;
+
+    M3 Wm;
+    Wm.c[0][0] = view[0]; Wm.c[0][1] = view[4]; Wm.c[0][2] = view[8];
+    Wm.c[1][0] = view[1]; Wm.c[1][1] = view[5]; Wm.c[1][2] = view[9];
+    Wm.c[2][0] = view[2]; Wm.c[2][1] = view[6]; Wm.c[2][2] = view[10];
+
+    M3 T = m3_mul(Wm, J);
+
+    M3 Vrk;
+    Vrk.c[0][0] = cov3D[0]; Vrk.c[0][1] = cov3D[1]; Vrk.c[0][2] = cov3D[2];
+    Vrk.c[1][0] = cov3D[1]; Vrk.c[1][1] = cov3D[3]; Vrk.c[1][2] = cov3D[4];
+    Vrk.c[2][0] = cov3D[2]; Vrk.c[2][1] = cov3D[4]; Vrk.c[2][2] = cov3D[5];
+
+    M3 cov = m3_mul(m3_mul(m3_transpose(T), m3_transpose(Vrk)), T);
+    if (ctx) {
+        ctx->t = t;
+        ctx->txtz = txtz;
+        ctx->tytz = tytz;
+        ctx->T = T;
+        ctx->Vrk = Vrk;
+    }
+    // low-pass: every Gaussian at least one pixel wide (forward.cu:110-111)
+    return make_float3(cov.c[0][0] + 0.3f, cov.c[0][1], cov.c[1][1] + 0.3f);
+}
+
+// ---- per-warp SH staging -----------------------------------------------------------------
+// A warp owns 32 consecutive Gaussians; their SH blocks are contiguous in memory
+// (32 * M*3 floats).  Lanes stream that range with coalesced 16-byte (or 4-byte) loads into
+// shared memory with an odd row stride, so the later one-thread-per-Gaussian reads are
+// bank-conflict free.  Rows of Gaussians whose bit in `need` is clear are never touched, and
+// only the first `used` floats of a row (active degree) are fetched.
+__device__ __forceinline__ void stage_sh_rows(const float* __restrict__ g_rows, int row_floats,
+                                              int used, int rows_valid, unsigned need,
+                                              float* s_rows, int s_stride, int lane) {
+    if ((row_floats & 3) == 0 && ((size_t)g_rows & 15) == 0) {
+        const int row_v4 = row_floats >> 2;
+        const int total = rows_valid * row_v4;
+        const float4* g4 = reinterpret_cast<const float4*>(g_rows);
+        for (int q = lane; q < total; q += 32) {
+            const int g = q / row_v4, e = (q - g * row_v4) << 2;
+            if (((need >> g) & 1u) && e < used) {
+                float4 v = __ldg(g4 + q);
+                float* d = s_rows + g * s_stride + e;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        }
+    } else {
+        const int total = rows_valid * row_floats;
+        for (int q = lane; q < total; q += 32) {
+            const int g = q / row_floats, e = q - g * row_floats;
+            if (((need >> g) & 1u) && e < used) s_rows[g * s_stride + e] = __ldg(g_rows + q);
+        }
+    }
+}
+
+// Inverse: write rows from shared memory to a contiguous global range (every element of
+// rows_valid rows is written; used by the backward for dL_dsh).
+__device__ __forceinline__ void unstage_rows(float* __restrict__ g_rows, int row_floats,
+                                             int rows_valid, const float* s_rows, int s_stride,
+                                             int lane) {
+    if ((row_floats & 3) == 0 && ((size_t)g_rows & 15) == 0) {
+        const int row_v4 = row_floats >> 2;
+        const int total = rows_valid * row_v4;
+        float4* g4 = reinterpret_cast<float4*>(g_rows);
+        for (int q = lane; q < total; q += 32) {
+            const int g = q / row_v4, e = (q - g * row_v4) << 2;
+            const float* s = s_rows + g * s_stride + e;
+            g4[q] = make_float4(s[0], s[1], s[2], s[3]);
+        }
+    } else {
+        const int total = rows_valid * row_floats;
+        for (int q = lane; q < total; q += 32) {
+            const int g = q / row_floats, e = q - g * row_floats;
+            g_rows[q] = s_rows[g * s_stride + e];
+        }
+    }
+}
+
+}  // namespace w3d
