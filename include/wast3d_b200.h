@@ -152,6 +152,12 @@ int wast3d_w2_match(int Kc, int Ks, const float* mean_c, const float* cov_c,
                     const float* mean_s, const float* cov_s, int32_t* out_idx, float* out_cost,
                     unsigned long long* stats, void* stream);
 
+/* Test hook: wast3d_w2_match that additionally writes the tensor-core lower-bound matrix
+ * (margin already subtracted) to lb_dump [Kc,Ks]; used by tests to validate the tcgen05 path. */
+int wast3d_w2_match_debug(int Kc, int Ks, const float* mean_c, const float* cov_c,
+                          const float* mean_s, const float* cov_s, int32_t* out_idx,
+                          float* out_cost, unsigned long long* stats, float* lb_dump, void* stream);
+
 /* Fused Adam step over one flat fp32 parameter group (replaces torch.optim.Adam as configured
  * in scene/gaussian_model.py:154-163: betas (0.9,0.999), eps 1e-15, no weight decay).
  * step is the 1-based step count AFTER increment (bias corrections use it). */

@@ -179,3 +179,51 @@ def mark_visible(means3D, view):
     out = np.zeros(m.shape[0], np.uint8)
     lib().oracle_mark_visible(int(m.shape[0]), _p(m), _p(_f32(view)), _p(out))
     return out.astype(bool)
+
+
+# ----------------------------------------------------------------------------- matching / kNN
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def cdist(a, b, sqrt=True):
+    a, b = _f32(a), _f32(b)
+    out = np.zeros((a.shape[0], b.shape[0]), np.float32)
+    lib().oracle_cdist(a.shape[0], b.shape[0], _p(a), _p(b), _p(out), int(bool(sqrt)))
+    return out
+
+
+def nn_match(a, b):
+    a, b = _f32(a), _f32(b)
+    idx = np.zeros(a.shape[0], np.int32)
+    dist = np.zeros(a.shape[0], np.float32)
+    lib().oracle_nn_match(a.shape[0], b.shape[0], _p(a), _p(b), _p(idx), _p(dist))
+    return idx, dist
+
+
+def w2_match(mean_c, cov_c, mean_s, cov_s, want_matrix=False):
+    mean_c, cov_c, mean_s, cov_s = _f32(mean_c), _f32(cov_c), _f32(mean_s), _f32(cov_s)
+    Kc, Ks = mean_c.shape[0], mean_s.shape[0]
+    idx = np.zeros(Kc, np.int32)
+    cost = np.zeros(Kc, np.float32)
+    mat = np.zeros((Kc, Ks), np.float32) if want_matrix else None
+    lib().oracle_w2_match(Kc, Ks, _p(mean_c), _p(cov_c), _p(mean_s), _p(cov_s), _p(idx), _p(cost), _p(mat))
+    return (idx, cost, mat) if want_matrix else (idx, cost)
+
+
+def cluster_stats(points, labels, K):
+    points, labels = _f32(points), _i32(labels)
+    mean = np.zeros((K, 3), np.float32)
+    cov = np.zeros((K, 6), np.float32)
+    count = np.zeros(K, np.int32)
+    lib().oracle_cluster_stats(points.shape[0], int(K), _p(points), _p(labels), _p(mean), _p(cov), _p(count))
+    return mean, cov, count
+
+
+def knn(points, want_index=True):
+    points = _f32(points)
+    P = points.shape[0]
+    out = np.zeros(P, np.float32)
+    idx = np.zeros((P, 3), np.int32) if want_index else None
+    lib().oracle_knn(P, _p(points), _p(out), _p(idx))
+    return out, idx

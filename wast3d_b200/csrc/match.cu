@@ -1,0 +1,539 @@
+// Cluster matching on sm_100a: nearest style cluster per content cluster under the squared
+// 2-Wasserstein distance between Gaussians (wast3d_w2_match) and plain nearest point
+// (wast3d_nn_match = argmin of torch.cdist), plus the per-cluster statistics they consume.
+//
+// What it replaces: there is no native reference code; the reference materialises
+// torch.cdist(a, b) (a cuBLAS SGEMM over [-2a, |a|^2, 1] x [b, 1, |b|^2] plus sqrt) and takes
+// argmin / min / sort of the N x M matrix (aux_optimize_cluster_D_W_distance.py:73-82,253-256;
+// notebooks/10.visualize_and_fit_patch_to_multiple.ipynb cell 34; notebooks/29.2... cell 58).
+// The closed-form Gaussian W2 named by the north star does not exist in the reference
+// (SURVEY.md §8a M5): the cost definition and its fp32 operation order are those of
+// oracle/match_oracle.c, which these kernels reproduce bit for bit.
+//
+// Design (the cost matrix is never written to memory):
+//  1. prep: per cluster a 16-float exact descriptor (mean, cov, adj(cov), det) and a 16 x bf16
+//     GEMM operand row.  With u = (mean, sqrt(tr cov)) in R^4,
+//         W2^2(i,j) >= |u_i - v_j|^2 = |u_i|^2 + |v_j|^2 - 2 u_i.v_j        (Schatten-Hoelder)
+//     and the right-hand side is ONE tensor-core GEMM with K = 16: u and v are split into
+//     bf16 hi + lo parts (hi.hi + hi.lo + lo.hi = 12 products) and the norms ride along as
+//     (|u|^2_hi, |u|^2_lo, 1, 1) x (1, 1, |v|^2_hi, |v|^2_lo), pre-scaled by (1 - 2^-11) so that
+//     the GEMM output is already "lower bound minus error margin".
+//  2. match: one CTA = 128 content rows (UMMA M = 128) x a range of 128-column style tiles.
+//     Per tile one tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM), then each of the 128
+//     threads reads its row with tcgen05.ld and evaluates the exact fp32 cost only for columns
+//     whose bound can still beat the row's best so far; (cost, index) is merged across column
+//     ranges with a 64-bit atomicMin (cost bits high, index low => ties go to the lowest index).
+//  All waits on the MMA barrier are bounded; a timeout sets an error flag instead of hanging.
+#include "common.cuh"
+#include <cuda_bf16.h>
+#include <cfloat>
+
+namespace w3d {
+
+constexpr int MT_M = 128;       // content rows per CTA == UMMA M == TMEM lanes
+constexpr int MT_N = 128;       // style columns per tile == UMMA N == TMEM columns
+constexpr int MT_K = 16;        // one kind::f16 UMMA K step
+constexpr int W2_ITERS = 10;    // oracle/match_oracle.c
+constexpr float LB_SHRINK = 1.0f - 1.0f / 2048.0f;
+
+enum MatchMode { MODE_W2 = 0, MODE_NN = 1 };
+
+// ---------------------------------------------------------------- exact costs (== oracle) -----
+__device__ __forceinline__ float dotsym(const float* A, const float* B) {
+    float d = __fmul_rn(A[0], B[0]);
+    d = __fmaf_rn(A[3], B[3], d);
+    d = __fmaf_rn(A[5], B[5], d);
+    float o = __fmul_rn(A[1], B[1]);
+    o = __fmaf_rn(A[2], B[2], o);
+    o = __fmaf_rn(A[4], B[4], o);
+    return __fmaf_rn(2.f, o, d);
+}
+
+// oracle_w2_descriptor
+__device__ __forceinline__ void w2_descriptor(const float* mean, const float* c, float* desc) {
+    desc[0] = mean[0]; desc[1] = mean[1]; desc[2] = mean[2];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) desc[3 + k] = c[k];
+    float* adj = desc + 9;
+    adj[0] = __fmaf_rn(c[3], c[5], -__fmul_rn(c[4], c[4]));
+    adj[1] = __fmaf_rn(c[2], c[4], -__fmul_rn(c[1], c[5]));
+    adj[2] = __fmaf_rn(c[1], c[4], -__fmul_rn(c[2], c[3]));
+    adj[3] = __fmaf_rn(c[0], c[5], -__fmul_rn(c[2], c[2]));
+    adj[4] = __fmaf_rn(c[1], c[2], -__fmul_rn(c[0], c[4]));
+    adj[5] = __fmaf_rn(c[0], c[3], -__fmul_rn(c[1], c[1]));
+    float det = __fmul_rn(c[0], adj[0]);
+    det = __fmaf_rn(c[1], adj[1], det);
+    det = __fmaf_rn(c[2], adj[2], det);
+    desc[15] = fmaxf(det, 0.f);
+}
+
+// oracle_w2_cost_desc
+__device__ __forceinline__ float w2_cost(const float* d1, const float* d2) {
+    const float dx = __fsub_rn(d1[0], d2[0]), dy = __fsub_rn(d1[1], d2[1]), dz = __fsub_rn(d1[2], d2[2]);
+    const float dist2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    const float tr1 = __fadd_rn(__fadd_rn(d1[3], d1[6]), d1[8]);
+    const float tr2 = __fadd_rn(__fadd_rn(d2[3], d2[6]), d2[8]);
+    const float c2 = fmaxf(dotsym(d1 + 3, d2 + 3), 0.f);
+    const float c1 = fmaxf(dotsym(d1 + 9, d2 + 9), 0.f);
+    const float e3 = __fsqrt_rn(__fmul_rn(d1[15], d2[15]));
+    float s = __fsqrt_rn(c2);
+    const float two_e3 = __fmul_rn(2.f, e3);
+#pragma unroll
+    for (int it = 0; it < W2_ITERS; ++it) {
+        const float e2 = __fsqrt_rn(__fmaf_rn(two_e3, s, c1));
+        s = __fsqrt_rn(__fmaf_rn(2.f, e2, c2));
+    }
+    const float w = __fmaf_rn(-2.f, s, __fadd_rn(dist2, __fadd_rn(tr1, tr2)));
+    return fmaxf(w, 0.f);
+}
+
+// oracle_cdist_sq: desc = (x, y, z, |.|^2 as torch computes it)
+__device__ __forceinline__ float nn_cost_sq(const float* a, const float* b) {
+    float acc = 0.f;
+    acc = __fmaf_rn(__fmul_rn(-2.f, a[0]), b[0], acc);
+    acc = __fmaf_rn(__fmul_rn(-2.f, a[1]), b[1], acc);
+    acc = __fmaf_rn(__fmul_rn(-2.f, a[2]), b[2], acc);
+    acc = __fmaf_rn(a[3], 1.f, acc);
+    acc = __fmaf_rn(1.f, b[3], acc);
+    return fmaxf(acc, 0.f);
+}
+
+// ---------------------------------------------------------------- prep --------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// operand row (16 bf16): content side  [uh(4) | uh(4) | ul(4) | n_h n_l 1 1]
+//                        style side    [-2vh(4) | -2vl(4) | -2vh(4) | 1 1 n_h n_l]
+template <int MODE>
+__global__ void __launch_bounds__(128)
+match_prep_kernel(int K, const float* __restrict__ mean, const float* __restrict__ cov6, bool style_side,
+                  float* __restrict__ desc /*[K,16]*/, __nv_bfloat16* __restrict__ oper /*[Kpad,16]*/,
+                  int Kpad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Kpad) return;
+    __nv_bfloat16 row[16];
+    if (i < K) {
+        float d[16];
+        float u[4];
+        if (MODE == MODE_W2) {
+            w2_descriptor(mean + 3 * i, cov6 + 6 * i, d);
+            const float tr = __fadd_rn(__fadd_rn(d[3], d[6]), d[8]);
+            u[3] = sqrtf(fmaxf(tr, 0.f));
+        } else {
+            const float x = mean[3 * i], y = mean[3 * i + 1], z = mean[3 * i + 2];
+            d[0] = x; d[1] = y; d[2] = z;
+            d[3] = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));  // torch: (x^2+y^2)+z^2
+#pragma unroll
+            for (int k = 4; k < 16; ++k) d[k] = 0.f;
+            u[3] = 0.f;
+        }
+        u[0] = d[0]; u[1] = d[1]; u[2] = d[2];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) desc[16 * (size_t)i + k] = d[k];
+        const float nrm = (u[0] * u[0] + u[1] * u[1] + u[2] * u[2] + u[3] * u[3]) * LB_SHRINK;
+        __nv_bfloat16 nh, nl;
+        split_bf16(nrm, nh, nl);
+        // round the norm DOWN-ish: hi+lo may exceed nrm by < 2^-17 nrm, far inside the margin
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat16 h, l;
+            if (!style_side) {
+                split_bf16(u[k], h, l);
+                row[k] = h; row[4 + k] = h; row[8 + k] = l;
+            } else {
+                split_bf16(-2.f * u[k], h, l);
+                row[k] = h; row[4 + k] = l; row[8 + k] = h;
+            }
+        }
+        if (!style_side) { row[12] = nh; row[13] = nl; row[14] = one; row[15] = one; }
+        else { row[12] = one; row[13] = one; row[14] = nh; row[15] = nl; }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) row[k] = __float2bfloat16_rn(0.f);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(oper + 16 * (size_t)i);
+    const uint4* src = reinterpret_cast<const uint4*>(row);
+    dst[0] = src[0];
+    dst[1] = src[1];
+}
+
+// ---------------------------------------------------------------- tcgen05 plumbing --------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major, no swizzle: core matrix = 8 rows x 16 bytes, stored as 128 contiguous bytes.
+// Our tiles keep the two K core matrices of an 8-row group adjacent (LBO = 128 B) and
+// consecutive 8-row groups 256 B apart (SBO = 256 B).
+__device__ __forceinline__ uint64_t umma_desc_kmajor_noswizzle(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address  [0,14)
+    d |= (uint64_t)(128 >> 4) << 16;                // leading byte offset [16,30)
+    d |= (uint64_t)(256 >> 4) << 32;                // stride byte offset  [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version (sm_100)
+    return d;                                       // layout type 0 = SWIZZLE_NONE
+}
+// byte offset of (row r, k element e) inside such a tile
+__device__ __forceinline__ int tile_off(int r, int e) {
+    return (r >> 3) * 256 + (e >> 3) * 128 + (r & 7) * 16 + (e & 7) * 2;
+}
+constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+// ---------------------------------------------------------------- match -------------------------
+// grid = (row blocks, column splits); block = 128 threads (thread t <-> content row / TMEM lane t)
+template <int MODE>
+__global__ void __launch_bounds__(MT_M)
+match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __restrict__ desc_s,
+             const __nv_bfloat16* __restrict__ oper_c, const __nv_bfloat16* __restrict__ oper_s,
+             int tiles_per_split, unsigned long long* __restrict__ best_packed,
+             unsigned long long* __restrict__ stats, float* __restrict__ lb_dump, uint32_t* __restrict__ err_flag) {
+    __shared__ __align__(1024) uint8_t s_A[MT_M * MT_K * 2];
+    __shared__ __align__(1024) uint8_t s_B[MT_N * MT_K * 2];
+    __shared__ __align__(16) float s_desc[MT_N * 16];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_tmem;
+
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = blockIdx.x * MT_M + tid;
+    const int n_tiles = (Ks + MT_N - 1) / MT_N;
+    const int tile0 = blockIdx.y * tiles_per_split;
+    const int tile1 = min(n_tiles, tile0 + tiles_per_split);
+
+    if (warp == 0) tmem_alloc(&s_tmem, MT_N);
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // A tile: this thread's operand row (32 bytes) into the canonical layout
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(oper_c + 16 * (size_t)row);  // oper_c is padded to the grid
+        *reinterpret_cast<uint4*>(s_A + tile_off(tid, 0)) = src[0];
+        *reinterpret_cast<uint4*>(s_A + tile_off(tid, 8)) = src[1];
+    }
+    float dc[16];
+    if (row < Kc) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 v = *reinterpret_cast<const float4*>(desc_c + 16 * (size_t)row + 4 * k);
+            dc[4 * k] = v.x; dc[4 * k + 1] = v.y; dc[4 * k + 2] = v.z; dc[4 * k + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) dc[k] = 0.f;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = s_tmem;
+    const uint32_t idesc = umma_idesc_bf16_f32(MT_M, MT_N);
+
+    float best = __int_as_float(0x7f800000);     // cost that is compared/returned
+    float thresh = __int_as_float(0x7f800000);   // same in lower-bound units (== best for W2, best^2 for NN)
+    int best_j = -1;
+    unsigned long long n_exact = 0;
+    uint32_t parity = 0;
+    bool failed = false;
+
+    for (int t = tile0; t < tile1 && !failed; ++t) {
+        const int col0 = t * MT_N;
+        // B tile + exact descriptors of this tile's style clusters
+        {
+            const int j = col0 + tid;
+            const uint4* src = reinterpret_cast<const uint4*>(oper_s + 16 * (size_t)j);  // padded to tiles
+            *reinterpret_cast<uint4*>(s_B + tile_off(tid, 0)) = src[0];
+            *reinterpret_cast<uint4*>(s_B + tile_off(tid, 8)) = src[1];
+            float4* dd = reinterpret_cast<float4*>(s_desc + 16 * tid);
+            if (j < Ks) {
+                const float4* ds = reinterpret_cast<const float4*>(desc_s + 16 * (size_t)j);
+                dd[0] = ds[0]; dd[1] = ds[1]; dd[2] = ds[2]; dd[3] = ds[3];
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            umma_bf16(tmem_base, umma_desc_kmajor_noswizzle(smem_u32(s_A)),
+                      umma_desc_kmajor_noswizzle(smem_u32(s_B)), idesc, 0u);
+            umma_commit(&s_bar);
+        }
+        // bounded wait for the MMA (never hang the device on a protocol bug)
+        {
+            uint32_t spins = 0;
+            while (!mbar_try_wait(&s_bar, parity)) {
+                if (++spins > (1u << 22)) { failed = true; break; }
+            }
+            parity ^= 1u;
+        }
+        if (__syncthreads_or(failed)) { failed = true; break; }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+#pragma unroll 1
+        for (int c = 0; c < MT_N; c += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+            if (lb_dump != nullptr && row < Kc) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                    if (col0 + c + k < Ks) lb_dump[(size_t)row * Ks + col0 + c + k] = v[k];
+            }
+            // columns whose (margin-adjusted) lower bound can still beat this row's best
+            unsigned mask = 0;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+                if (row < Kc && col0 + c + k < Ks && !(v[k] > thresh)) mask |= 1u << k;
+            unsigned any = __reduce_or_sync(0xffffffffu, mask);
+            while (any) {  // ascending column order => ties keep the lowest index
+                const int k = __ffs(any) - 1;
+                any &= any - 1;
+                if ((mask >> k) & 1u) {
+                    ++n_exact;
+                    const int j = col0 + c + k;
+                    const float* dsj = s_desc + 16 * (c + k);
+                    if (MODE == MODE_W2) {
+                        const float w = w2_cost(dc, dsj);
+                        if (w < best) { best = w; thresh = w; best_j = j; }
+                    } else {
+                        const float sq = nn_cost_sq(dc, dsj);
+                        const float d = __fsqrt_rn(sq);
+                        if (d < best) { best = d; thresh = sq; best_j = j; }
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();  // all TMEM reads and s_B / s_desc reads done before the next tile overwrites them
+    }
+
+    if (failed && tid == 0) atomicOr(err_flag, 1u);
+    if (!failed && row < Kc && best_j >= 0) {
+        const unsigned long long packed = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)best_j;
+        atomicMin(best_packed + row, packed);
+    }
+    if (stats != nullptr) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) n_exact += __shfl_xor_sync(0xffffffffu, n_exact, d);
+        if ((tid & 31) == 0) atomicAdd(stats + 1, n_exact);
+        if (tid == 0) atomicAdd(stats + 2, (unsigned long long)max(tile1 - tile0, 0));
+    }
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, MT_N);
+}
+
+__global__ void match_finalize_kernel(int Kc, const unsigned long long* __restrict__ packed,
+                                      int32_t* __restrict__ out_idx, float* __restrict__ out_cost) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Kc) return;
+    const unsigned long long p = packed[i];
+    if (p == ~0ull) {
+        out_idx[i] = -1;
+        if (out_cost) out_cost[i] = __int_as_float(0x7f800000);
+    } else {
+        out_idx[i] = (int32_t)(p & 0xFFFFFFFFu);
+        if (out_cost) out_cost[i] = __uint_as_float((uint32_t)(p >> 32));
+    }
+}
+
+// ---------------------------------------------------------------- cluster statistics ------------
+// Two passes with double accumulators (atomicAdd(double) is native): order independent up to
+// double rounding, which vanishes in the final fp32 result.
+__global__ void __launch_bounds__(256)
+cluster_sum_kernel(int n, int K, const float* __restrict__ pts, const int32_t* __restrict__ labels,
+                   double* __restrict__ sum, int32_t* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = labels[i];
+    if (k < 0 || k >= K) return;
+    atomicAdd(count + k, 1);
+    atomicAdd(sum + 3 * k + 0, (double)pts[3 * i + 0]);
+    atomicAdd(sum + 3 * k + 1, (double)pts[3 * i + 1]);
+    atomicAdd(sum + 3 * k + 2, (double)pts[3 * i + 2]);
+}
+__global__ void cluster_mean_kernel(int K, double* __restrict__ sum, const int32_t* __restrict__ count) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int c = count[k];
+    for (int d = 0; d < 3; ++d) sum[3 * k + d] = c ? sum[3 * k + d] / c : 0.0;
+}
+__global__ void __launch_bounds__(256)
+cluster_cov_kernel(int n, int K, const float* __restrict__ pts, const int32_t* __restrict__ labels,
+                   const double* __restrict__ mean, double* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = labels[i];
+    if (k < 0 || k >= K) return;
+    const double dx = pts[3 * i] - mean[3 * k], dy = pts[3 * i + 1] - mean[3 * k + 1], dz = pts[3 * i + 2] - mean[3 * k + 2];
+    double* a = acc + 6 * k;
+    atomicAdd(a + 0, dx * dx); atomicAdd(a + 1, dx * dy); atomicAdd(a + 2, dx * dz);
+    atomicAdd(a + 3, dy * dy); atomicAdd(a + 4, dy * dz); atomicAdd(a + 5, dz * dz);
+}
+__global__ void cluster_out_kernel(int K, const double* __restrict__ mean, const double* __restrict__ acc,
+                                   const int32_t* __restrict__ count, float* __restrict__ mean_out,
+                                   float* __restrict__ cov_out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int c = count[k];
+    for (int d = 0; d < 3; ++d) mean_out[3 * k + d] = (float)mean[3 * k + d];
+    for (int d = 0; d < 6; ++d) cov_out[6 * k + d] = c ? (float)(acc[6 * k + d] / c) : 0.f;
+}
+
+// ---------------------------------------------------------------- host --------------------------
+template <int MODE>
+static int run_match(int Kc, int Ks, const float* mean_c, const float* cov_c, const float* mean_s,
+                     const float* cov_s, int32_t* out_idx, float* out_cost, unsigned long long* stats,
+                     float* lb_dump, cudaStream_t s) {
+    if (Kc < 0 || Ks < 0) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (Kc == 0) return WAST3D_OK;
+    if (!mean_c || !out_idx || (Ks > 0 && !mean_s)) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (MODE == MODE_W2 && (!cov_c || (Ks > 0 && !cov_s))) return WAST3D_ERR_INVALID_ARGUMENT;
+    const int Kc_pad = (Kc + MT_M - 1) / MT_M * MT_M;
+    const int Ks_pad = (Ks + MT_N - 1) / MT_N * MT_N;
+    // scratch (stream-ordered allocation keeps this call asynchronous)
+    Carver sizer(nullptr);
+    sizer.take<float>((size_t)Kc * 16); sizer.take<float>((size_t)(Ks > 0 ? Ks : 1) * 16);
+    sizer.take<__nv_bfloat16>((size_t)Kc_pad * 16); sizer.take<__nv_bfloat16>((size_t)(Ks_pad > 0 ? Ks_pad : MT_N) * 16);
+    sizer.take<unsigned long long>(Kc); sizer.take<uint32_t>(4);
+    void* chunk = nullptr;
+    W3D_CUDA_TRY(cudaMallocAsync(&chunk, sizer.bytes(), s));
+    Carver c(chunk);
+    float* desc_c = c.take<float>((size_t)Kc * 16);
+    float* desc_s = c.take<float>((size_t)(Ks > 0 ? Ks : 1) * 16);
+    __nv_bfloat16* oper_c = c.take<__nv_bfloat16>((size_t)Kc_pad * 16);
+    __nv_bfloat16* oper_s = c.take<__nv_bfloat16>((size_t)(Ks_pad > 0 ? Ks_pad : MT_N) * 16);
+    unsigned long long* packed = c.take<unsigned long long>(Kc);
+    uint32_t* err = c.take<uint32_t>(4);
+    int rc = WAST3D_OK;
+    do {
+        if (cudaMemsetAsync(packed, 0xFF, sizeof(unsigned long long) * (size_t)Kc, s) != cudaSuccess ||
+            cudaMemsetAsync(err, 0, 16, s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+        if (stats && cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+        match_prep_kernel<MODE><<<(Kc_pad + 127) / 128, 128, 0, s>>>(Kc, mean_c, cov_c, false, desc_c, oper_c, Kc_pad);
+        if (Ks > 0)
+            match_prep_kernel<MODE><<<(Ks_pad + 127) / 128, 128, 0, s>>>(Ks, mean_s, cov_s, true, desc_s, oper_s, Ks_pad);
+        if (cudaGetLastError() != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+        if (Ks > 0) {
+            const int row_blocks = Kc_pad / MT_M;
+            const int n_tiles = Ks_pad / MT_N;
+            int splits = (2 * 148 + row_blocks - 1) / row_blocks;   // aim for ~2 CTAs per SM
+            if (splits > n_tiles) splits = n_tiles;
+            if (splits < 1) splits = 1;
+            const int tiles_per_split = (n_tiles + splits - 1) / splits;
+            splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
+            match_kernel<MODE><<<dim3(row_blocks, splits), MT_M, 0, s>>>(Kc, Ks, desc_c, desc_s, oper_c, oper_s,
+                                                                        tiles_per_split, packed, stats, lb_dump, err);
+            if (cudaGetLastError() != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+            if (stats) {
+                const unsigned long long pairs = (unsigned long long)Kc * (unsigned long long)Ks;
+                if (cudaMemcpyAsync(stats, &pairs, sizeof(pairs), cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+            }
+        }
+        match_finalize_kernel<<<(Kc + 255) / 256, 256, 0, s>>>(Kc, packed, out_idx, out_cost);
+        if (cudaGetLastError() != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+        // the MMA-timeout flag is the only thing that needs the host; it is tiny and rare
+        uint32_t h_err = 0;
+        if (cudaMemcpyAsync(&h_err, err, sizeof(h_err), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+        if (h_err) rc = WAST3D_ERR_CUDA;
+    } while (0);
+    if (rc == WAST3D_ERR_CUDA) set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+    cudaFreeAsync(chunk, s);
+    return rc;
+}
+
+}  // namespace w3d
+
+using namespace w3d;
+
+extern "C" int wast3d_w2_match(int Kc, int Ks, const float* mean_c, const float* cov_c,
+                               const float* mean_s, const float* cov_s, int32_t* out_idx,
+                               float* out_cost, unsigned long long* stats, void* stream_v) {
+    return run_match<MODE_W2>(Kc, Ks, mean_c, cov_c, mean_s, cov_s, out_idx, out_cost, stats, nullptr,
+                              (cudaStream_t)stream_v);
+}
+
+extern "C" int wast3d_nn_match(int Na, int Nb, const float* a, const float* b, int32_t* out_idx,
+                               float* out_dist, void* stream_v) {
+    return run_match<MODE_NN>(Na, Nb, a, nullptr, b, nullptr, out_idx, out_dist, nullptr, nullptr,
+                              (cudaStream_t)stream_v);
+}
+
+// Test hook: also dumps the tensor-core lower-bound matrix [Kc,Ks] (see tests/test_match_gpu.py).
+extern "C" int wast3d_w2_match_debug(int Kc, int Ks, const float* mean_c, const float* cov_c,
+                                     const float* mean_s, const float* cov_s, int32_t* out_idx,
+                                     float* out_cost, unsigned long long* stats, float* lb_dump,
+                                     void* stream_v) {
+    return run_match<MODE_W2>(Kc, Ks, mean_c, cov_c, mean_s, cov_s, out_idx, out_cost, stats, lb_dump,
+                              (cudaStream_t)stream_v);
+}
+
+extern "C" int wast3d_cluster_stats(int n, int K, const float* points, const int32_t* labels,
+                                    float* mean, float* cov6, int32_t* count, void* stream_v) {
+    if (n < 0 || K < 0) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (K == 0) return WAST3D_OK;
+    if (!mean || !cov6 || !count || (n > 0 && (!points || !labels))) return WAST3D_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    double* buf = nullptr;
+    W3D_CUDA_TRY(cudaMallocAsync((void**)&buf, sizeof(double) * 9 * (size_t)K, s));
+    double* sum = buf;
+    double* acc = buf + 3 * (size_t)K;
+    int rc = WAST3D_OK;
+    do {
+        if (cudaMemsetAsync(buf, 0, sizeof(double) * 9 * (size_t)K, s) != cudaSuccess ||
+            cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)K, s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+        if (n > 0) cluster_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, K, points, labels, sum, count);
+        cluster_mean_kernel<<<(K + 255) / 256, 256, 0, s>>>(K, sum, count);
+        if (n > 0) cluster_cov_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, K, points, labels, sum, acc);
+        cluster_out_kernel<<<(K + 255) / 256, 256, 0, s>>>(K, sum, acc, count, mean, cov6);
+        if (cudaGetLastError() != cudaSuccess) rc = WAST3D_ERR_CUDA;
+    } while (0);
+    if (rc == WAST3D_ERR_CUDA) set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+    cudaFreeAsync(buf, s);
+    return rc;
+}
