@@ -23,8 +23,8 @@
  *    (explicit fma / IEEE div / IEEE sqrt), so assignments and costs are compared bit for bit.
  *  - oracle_knn: brute-force statement of SimpleKNN::knn's result
  *    (submodules/simple-knn/simple_knn.cu:131-145 updateKBest, :147-183 boxMeanDist): mean of the
- *    three smallest d^2 to other points, d^2 = fma(dz,dz,fma(dy,dy,dx*dx)) as in the reference's
- *    SASS, self excluded by index, FLT_MAX for missing neighbours.  Pinned on the GPU box against
+ *    three smallest d^2 to other points, d^2 = fma(dz,dz,fma(dx,dx,dy*dy)) (the contraction nvcc
+ *    picks for the reference; verified bit for bit against its sm_100 build), self excluded by index, FLT_MAX for missing neighbours.  Pinned on the GPU box against
  *    the real simple-knn (oracle/_ref) by tests/test_knn_gpu.py.
  *  - oracle_cluster_stats: per-cluster mean and covariance of member xyz (the statistics the
  *    notebooks derive from K-Means memberships); float64 accumulation, population covariance.
@@ -200,7 +200,7 @@ void oracle_knn(int P, const float* pts, float* mean_dist2, int32_t* nn_idx) {
         for (int j = 0; j < P; ++j) {
             if (j == i) continue;
             const float dx = pts[3 * j] - q[0], dy = pts[3 * j + 1] - q[1], dz = pts[3 * j + 2] - q[2];
-            float dist = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            float dist = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
             int32_t id = j;
             for (int k = 0; k < 3; ++k) { /* (distance, index) lexicographic; j ascending => ties keep lowest */
                 if (dist < bd[k]) {

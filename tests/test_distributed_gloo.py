@@ -1,0 +1,101 @@
+"""CPU, world_size 2 over gloo: the host logic of the two multi-GPU pieces."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from wast3d_b200 import distributed as wd
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 7, 16384, 16385):
+        for w in (1, 2, 3, 8):
+            b = [wd.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [e - s for s, e in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _grad_job(rank, world):
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.zeros(1000, 3)), torch.nn.Parameter(torch.zeros(1000, 15, 3)),
+          torch.nn.Parameter(torch.zeros(1000, 1)), torch.nn.Parameter(torch.zeros(7))]
+    g = torch.Generator().manual_seed(100 + rank)
+    for p in ps[:3]:
+        p.grad = torch.randn(p.shape, generator=g)
+    # ps[3] has no grad: must be skipped on every rank
+    wd.allreduce_gradients(ps, bucket_bytes=20000)  # forces several buckets incl. a packed one
+    return [p.grad.clone() if p.grad is not None else None for p in ps]
+
+
+def test_view_parallel_gradient_allreduce():
+    out = _run(_grad_job)
+    expect = []
+    for shape in [(1000, 3), (1000, 15, 3), (1000, 1)]:
+        tot = 0
+        for r in range(2):
+            pass
+        expect.append(shape)
+    gens = [torch.Generator().manual_seed(100 + r) for r in range(2)]
+    sums = []
+    per_rank = [[torch.randn(s, generator=gens[r]) for s in [(1000, 3), (1000, 15, 3), (1000, 1)]] for r in range(2)]
+    for i in range(3):
+        sums.append(per_rank[0][i] + per_rank[1][i])
+    for r in range(2):
+        for i in range(3):
+            assert torch.equal(out[r][i], sums[i])      # two-rank fp32 sum is order independent
+        assert out[r][3] is None
+
+
+def _match_job(rank, world):
+    from oracle import cpu
+    rng = np.random.default_rng(5)
+    a = torch.from_numpy(rng.normal(size=(1001, 3)).astype(np.float32))   # uneven shards
+    b = torch.from_numpy(rng.normal(size=(77, 3)).astype(np.float32))
+
+    def cpu_match(a_shard, b_all):  # stands in for wast3d_b200.matching.nn_match on CPU
+        i, d = cpu.nn_match(a_shard.numpy(), b_all.numpy())
+        return torch.from_numpy(i).long(), torch.from_numpy(d)
+
+    idx, cost = wd.sharded_match(cpu_match, [a], [b])
+    full_i, full_d = cpu.nn_match(a.numpy(), b.numpy())
+    return bool((idx.numpy() == full_i).all() and (cost.numpy() == full_d).all() and len(idx) == 1001)
+
+
+def test_sharded_matching_equals_unsharded():
+    assert _run(_match_job) == [True, True]
+
+
+def test_view_assignment():
+    cams = list(range(8))
+    seen = [wd.view_for_rank(cams, step, r, 4) for step in range(2) for r in range(4)]
+    assert seen == [0, 1, 2, 3, 4, 5, 6, 7]

@@ -5,8 +5,9 @@
 // Semantics kept bit for bit:
 //   * neighbours are the 3 smallest squared distances to OTHER points; self is excluded by
 //     index, not by distance, so duplicates give 0 (simple_knn.cu:158,177);
-//   * d^2 is evaluated as fma(dz,dz, fma(dy,dy, dx*dx)) with d = other - self, which is what
-//     nvcc emits for simple_knn.cu:134-135 (checked in the reference's sm_100 SASS);
+//   * d^2 is evaluated as fma(dz,dz, fma(dx,dx, dy*dy)) with d = other - self, which is what
+//     nvcc emits for simple_knn.cu:134-135 (checked against the reference's sm_100 build:
+//     of the 18 fma/sum orderings only this one reproduces its output bit for bit);
 //   * result = (b0 + b1 + b2) / 3.0f with FLT_MAX for missing neighbours (:182, P < 4).
 // Extension: the indices of the three neighbours, ties broken towards the lowest index.
 //
@@ -189,7 +190,7 @@ __device__ __forceinline__ void best3_insert(Best3& b, float dist, uint32_t id) 
 }
 __device__ __forceinline__ float knn_dist2(float px, float py, float pz, float qx, float qy, float qz) {
     const float dx = __fsub_rn(px, qx), dy = __fsub_rn(py, qy), dz = __fsub_rn(pz, qz);
-    return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 __global__ void __launch_bounds__(128)
