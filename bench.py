@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Benchmark of the style-transfer optimisation step (BASELINE.json metric:
+"style-opt iters/s @3M Gaussians at 1/2/4/8 B200; W2 cluster-match pairs/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c3|c2|c5]
+
+One step = render() forward (colour + depth, jittered samples) -> synthetic loss (L1 + 0.1 depth MSE
++ TV; no VGG: its weights need a network) -> backward through the rasteriser to the six leaf
+parameters -> [NCCL all-reduce of the gradients when N > 1] -> fused Adam step, on the synthetic
+3M-Gaussian garden scene at 1297x840 (BASELINE.json configs[2]; it fits one GPU).  With N GPUs
+every rank renders a different camera per step (view-parallel, weak scaling): `value` counts
+view-iterations of all ranks per second.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the same path
+(oracle/, all host threads, bounded sample) instead; the reference has no CPU rasteriser of its
+own (every tensor is created on "cuda"), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "style-opt iters/s @3M Gaussians (view-iterations of all GPUs per second)"
+UNIT = "iters/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c3", choices=["c2", "c3", "c5"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the kNN / matching side metrics")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def tv_loss(img):
+    return (img[:, :, 1:] - img[:, :, :-1]).abs().mean() + (img[:, 1:, :] - img[:, :-1, :]).abs().mean()
+
+
+def style_loss(out, tgt, dtgt):
+    img, depth = out["render"], out["depth"]
+    return (img - tgt).abs().mean() + 0.1 * ((depth - dtgt) ** 2).mean() + tv_loss(img)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = float(rows[0][2])
+        out["power_w_max"] = max(float(r[3]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i, n in enumerate(names):
+            if any(r[5 + i].strip().lower().startswith("active") for r in rows):
+                out["reasons"].append(n)
+        out["samples"] = len(rows)
+        return out
+
+
+# --------------------------------------------------------------------------------- CPU arm
+def cpu_sample(spec, seed=0, stride=10, threads=None):
+    """Bounded sample of the same workload for the CPU restatement: every `stride`-th Gaussian of
+    the scene, same camera, same resolution, same loss gradients shape."""
+    from oracle import cpu
+    from wast3d_b200.scene import scene_cameras, synthetic_gaussians
+    g = synthetic_gaussians(spec.P, seed=seed, garden=spec.garden, log_scale_mu=spec.log_scale_mu)
+    sel = slice(0, None, stride)
+    cam = scene_cameras(spec, 8, device="cpu")[0]
+    q = g["rotations"][sel] / np.linalg.norm(g["rotations"][sel], axis=1, keepdims=True)
+    rng = np.random.default_rng(seed + 5)
+    inp = cpu.RasterInputs(
+        W=spec.width, H=spec.height, tan_fovx=math.tan(cam.FoVx / 2), tan_fovy=math.tan(cam.FoVy / 2),
+        bg=np.zeros(3, np.float32), means3D=g["xyz"][sel],
+        opacities=1.0 / (1.0 + np.exp(-g["opacity_logits"][sel])), view=cam.world_view_transform.numpy(),
+        proj=cam.full_proj_transform.numpy(), campos=cam.camera_center.numpy(),
+        shs=np.concatenate([g["f_dc"][sel], g["f_rest"][sel]], 1), scales=np.exp(g["log_scales"][sel]),
+        rotations=q, D=3, sampling_offsets=-rng.random((spec.height, spec.width, 2)))
+    dpix = rng.normal(size=(3, spec.height, spec.width)).astype(np.float32) / (3 * spec.height * spec.width)
+    ddep = rng.normal(size=(spec.height, spec.width)).astype(np.float32) / (spec.height * spec.width)
+    if threads:
+        cpu.set_threads(threads)
+    return cpu, inp, dpix, ddep
+
+
+def cpu_step(cpu, inp, dpix, ddep):
+    fwd = cpu.forward_all(inp)
+    cpu.backward_all(inp, fwd, dpix, ddep)
+    return fwd["bin"]["R"]
+
+
+def run_reference(args, spec):
+    """--impl reference: the CPU restatement (oracle port) on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    stride = 10
+    cores = os.cpu_count() or 1
+    cpu, inp, dpix, ddep = cpu_sample(spec, stride=stride, threads=cores)
+    for _ in range(max(1, min(args.warmup, 2))):
+        R = cpu_step(cpu, inp, dpix, ddep)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        R = cpu_step(cpu, inp, dpix, ddep)
+    dt = (time.perf_counter() - t0) / steps
+    full = dt * stride  # per-Gaussian and per-instance work both scale with the subsampling stride
+    value = 1.0 / full
+    sample = (f"every {stride}th Gaussian of the {spec.P}-Gaussian scene ({inp.P} Gaussians, R={R}) at the full "
+              f"{spec.width}x{spec.height}, forward+backward, {steps} steps of {dt:.2f} s; value = 1/(t*{stride})")
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": args.warmup, "ms_per_step": full * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(spec, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(spec, n):
+    return {"workload": f"{spec.name}: synthetic garden-scale scene, {spec.P} Gaussians, {spec.width}x{spec.height}, "
+                        f"SH degree 3, render fwd (colour+depth) + loss + bwd + Adam",
+            "gaussians": spec.P, "width": spec.width, "height": spec.height, "views_per_step": n,
+            "parallelism": f"view-parallel x{n}" if n > 1 else "single GPU",
+            "l2_policy": "inputs_larger_than_L2 (parameters+state ~2.8 GB per step vs 126 MB L2)"}
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def instance_count(pc, cam, bg):
+    from wast3d_b200.diff_gaussian_rasterization import _C
+    e = torch.empty(0)
+    with torch.no_grad():
+        out = _C.rasterize_gaussians(
+            bg, pc.get_xyz, e, pc.get_opacity, pc.get_scaling, pc.get_rotation, 1.0, e,
+            cam.world_view_transform, cam.full_proj_transform, math.tan(cam.FoVx * 0.5),
+            math.tan(cam.FoVy * 0.5), cam.image_height, cam.image_width, pc.get_features,
+            pc.active_sh_degree, cam.camera_center, False, False, e)
+    return int(out[0]), int((out[3] > 0).sum().item())
+
+
+def main():
+    args = parse()
+    from wast3d_b200.scene import CONFIGS
+    spec = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference(args, spec)
+        return
+
+    import torch.distributed as dist
+    from wast3d_b200 import _lib, distributed as wd, matching
+    from wast3d_b200.gaussian_renderer import render
+    from wast3d_b200.scene import GaussianModel, PipelineParams, scene_cameras, synthetic_gaussians
+    from wast3d_b200.simple_knn._C import distCUDA2
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs CUDA devices (there is no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    torch.manual_seed(0)
+    arrs = synthetic_gaussians(spec.P, seed=0, garden=spec.garden, log_scale_mu=spec.log_scale_mu)
+    pc = GaussianModel.from_arrays(arrs, sh_degree=3, device=dev)
+    pc.spatial_lr_scale = 5.0
+    opt = pc.training_setup(fused=True)
+    cams = scene_cameras(spec, 8, device=dev)
+    pipe = PipelineParams()
+    bg = torch.zeros(3, device=dev)
+    H, W = spec.height, spec.width
+    gen = torch.Generator().manual_seed(1)
+    tgt_host = [torch.rand(3, H, W, generator=gen).pin_memory() for _ in range(2)]
+    dtgt_host = [(torch.rand(H, W, generator=gen) * 10).pin_memory() for _ in range(2)]
+    tgt_dev = [t.to(dev) for t in tgt_host]
+    dtgt_dev = [t.to(dev) for t in dtgt_host]
+    cam_host = [(c.world_view_transform.cpu().pin_memory(), c.full_proj_transform.cpu().pin_memory(),
+                 c.camera_center.cpu().pin_memory()) for c in cams]
+    params = pc.parameters()
+    last_R = [0]
+
+    def step(i, host_io):
+        cam = wd.view_for_rank(cams, i, rank, world)
+        k = i % 2
+        if host_io:  # this step's inputs come from pinned host memory
+            ci = cams.index(cam)
+            cam = cam.to(dev)  # shallow copy
+            cam.world_view_transform = cam_host[ci][0].to(dev, non_blocking=True)
+            cam.full_proj_transform = cam_host[ci][1].to(dev, non_blocking=True)
+            cam.camera_center = cam_host[ci][2].to(dev, non_blocking=True)
+            tgt = tgt_host[k].to(dev, non_blocking=True)
+            dtgt = dtgt_host[k].to(dev, non_blocking=True)
+        else:
+            tgt, dtgt = tgt_dev[k], dtgt_dev[k]
+        out = render(cam, pc, pipe, bg)
+        loss = style_loss(out, tgt, dtgt)
+        loss.backward()
+        if world > 1:
+            wd.allreduce_gradients(reversed(params), average=True)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        if host_io:
+            return loss.item()  # device -> host read of the step's result
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, host_io, first):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            step(first + i, host_io)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # warm-up (allocator, clocks, Adam state)
+    for i in range(max(args.warmup, 3)):
+        step(i, False)
+    it0 = max(args.warmup, 3)
+
+    # ---- timed region: K steps, dominant kernel bracketed by events inside the library
+    _lib.profile_enable(["render_backward"])
+    _lib.profile_read()
+    _lib.launch_count(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total = timed(args.steps, False, it0)
+    launches = _lib.launch_count(reset=True)
+    clocks = sampler.stop() if sampler else None
+    prof = _lib.profile_read()
+    _lib.profile_enable([])
+    ms_step = ms_total / args.steps
+    value = world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with host buffers
+    for i in range(2):
+        step(it0 + i, True)
+    ms_e2e = timed(args.steps, True, it0 + args.steps)
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    h2d = tgt_host[0].numel() * 4 + dtgt_host[0].numel() * 4 + sum(t.numel() * 4 for t in cam_host[0])
+
+    # ---- per-stage breakdown (separate short pass; events between stages perturb the step a little)
+    _lib.profile_enable(None)
+    _lib.profile_read()
+    nb = 5
+    timed(nb, False, it0)
+    stages = {k: round(v[0] / nb, 4) for k, v in _lib.profile_read().items()}
+    _lib.profile_enable([])
+
+    # instance count (R) of this rank's camera for the roofline: one direct call of the operator
+    R, vis = instance_count(pc, wd.view_for_rank(cams, it0, rank, world), bg)
+
+    hbm_peak, peak_src = peaks()
+    N = H * W
+    rb_ms, rb_calls = prof.get("render_backward", (0.0, 0))
+    rb_ms_avg = rb_ms / max(rb_calls, 1)
+    alg_bytes = 80.0 * R + 32.0 * N  # K7 reads 40 B/instance, 40 B/instance of gradient RMW, 32 B/pixel
+    achieved = alg_bytes / (rb_ms_avg * 1e-3) / 1e9 if rb_ms_avg > 0 else 0.0
+    fwd_bytes = 339.0 * spec.P + 216.0 * R + 32.0 * N
+    bwd_bytes = 931.0 * spec.P + 80.0 * R + 32.0 * N
+    adam_bytes = 7.0 * 4.0 * 59.0 * spec.P
+    roofline = {"bound": "hbm", "kernel": "render_backward_kernel (K7)", "achieved": round(achieved, 2),
+                "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": round(achieved / hbm_peak, 5), "traffic": None,
+                "kernel_ms": round(rb_ms_avg, 4), "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "K7 is FP32/SFU/atomic bound, not HBM bound (SURVEY §7); whole-step figure: "
+                        "step_algorithmic_GBps",
+                "step_algorithmic_GBps": round((fwd_bytes + bwd_bytes + adam_bytes) / (ms_step * 1e-3) / 1e9, 1),
+                "step_frac": round((fwd_bytes + bwd_bytes + adam_bytes) / (ms_step * 1e-3) / 1e9 / hbm_peak, 4)}
+
+    extra = {}
+    if not args.no_extra:
+        # W2 cluster-match pairs/s at BASELINE.json configs[3] shapes: 16384 content clusters sharded
+        # over the ranks against 4096 replicated style clusters
+        rng = np.random.default_rng(0)
+
+        def clusters(K):
+            m = rng.normal(size=(K, 3)) * 8.0
+            A = rng.normal(size=(K, 3, 3)) * rng.uniform(0.05, 0.6, size=(K, 1, 3))
+            S = A @ A.transpose(0, 2, 1)
+            c6 = np.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1)
+            return torch.from_numpy(m.astype(np.float32)).to(dev), torch.from_numpy(c6.astype(np.float32)).to(dev)
+        Kc, Ks = 16384, 4096
+        mc, cc = clusters(Kc)
+        ms_, cs = clusters(Ks)
+        s, e = wd.shard_bounds(Kc, rank, world)
+        for _ in range(3):
+            matching.w2_match(mc[s:e], cc[s:e], ms_, cs)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        reps = 20
+        for _ in range(reps):
+            idx, cost, st = matching.w2_match(mc[s:e], cc[s:e], ms_, cs, return_stats=True)
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        extra["w2_match"] = {"content_clusters": Kc, "style_clusters": Ks, "ms": round(float(t.item()), 4),
+                             "pairs_per_s": Kc * Ks / (float(t.item()) * 1e-3),
+                             "exact_eval_fraction": st["exact_evals"] / max(st["pairs"], 1)}
+        pts = pc.get_xyz.detach()
+        for _ in range(2):
+            distCUDA2(pts)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            distCUDA2(pts)
+        b.record()
+        barrier()
+        kms = a.elapsed_time(b) / 5
+        extra["knn"] = {"points": spec.P, "ms": round(kms, 3), "points_per_s": spec.P / (kms * 1e-3),
+                        "algorithmic_GBps": round(16.0 * spec.P / (kms * 1e-3) / 1e9, 2)}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        stride = 10
+        cores = os.cpu_count() or 1
+        cpu, inp, dpix, ddep = cpu_sample(spec, stride=stride, threads=cores)
+        cpu_step(cpu, inp, dpix, ddep)
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            Rs = cpu_step(cpu, inp, dpix, ddep)
+        dt = (time.perf_counter() - t0) / n
+        cpu_baseline = {"value": 1.0 / (dt * stride), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"oracle/ CPU restatement (OpenMP), every {stride}th Gaussian ({inp.P}, R={Rs}) at "
+                                  f"{W}x{H}, fwd+bwd {dt:.2f} s/step, scaled x{stride}; no Adam"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(spec, world), "impl": "ours",
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu_baseline, "stages_ms": stages,
+                "scene": {"visible_gaussians": vis, "tile_instances_R": R, "pixels": N}, "extra": extra}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,16 @@ int wast3d_adam_step(size_t n, float* param, const float* grad, float* exp_avg,
                      float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int step,
                      void* stream);
 
+/* Measurement hooks (bench.py): per-stage CUDA-event timing on the launching stream and a count
+ * of kernel launches issued by this library.  Slots: wast3d_profile_slots() names via
+ * wast3d_profile_slot_name(); enable a subset with a bit mask (0 = off, the default).
+ * wast3d_profile_read ADDS elapsed milliseconds / scope counts into the caller's arrays. */
+int wast3d_profile_set(unsigned slot_mask);
+int wast3d_profile_slots(void);
+const char* wast3d_profile_slot_name(int slot);
+int wast3d_profile_read(double* ms_per_slot, unsigned long long* scopes_per_slot);
+unsigned long long wast3d_launch_count(int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -202,8 +202,8 @@ void oracle_knn(int P, const float* pts, float* mean_dist2, int32_t* nn_idx) {
             const float dx = pts[3 * j] - q[0], dy = pts[3 * j + 1] - q[1], dz = pts[3 * j + 2] - q[2];
             float dist = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
             int32_t id = j;
-            for (int k = 0; k < 3; ++k) { /* (distance, index) lexicographic; j ascending => ties keep lowest */
-                if (dist < bd[k]) {
+            for (int k = 0; k < 3; ++k) { /* (distance, index) lexicographic: ties keep the lowest index */
+                if (dist < bd[k] || (dist == bd[k] && (uint32_t)id < (uint32_t)bi[k])) {
                     float td = bd[k]; int32_t ti = bi[k];
                     bd[k] = dist; bi[k] = id; dist = td; id = ti;
                 }

@@ -51,6 +51,11 @@ SIGNATURES = {
     "wast3d_nn_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_w2_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_w2_match_debug": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_profile_set": (_i, [C.c_uint]),
+    "wast3d_profile_slots": (_i, []),
+    "wast3d_profile_slot_name": (C.c_char_p, [_i]),
+    "wast3d_profile_read": (_i, [_vp, _vp]),
+    "wast3d_launch_count": (C.c_ulonglong, [_i]),
     "wast3d_adam_step": (_i, [_sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
 }
 
@@ -130,3 +135,32 @@ class GrowBuffer:
                 return None
 
         self.cb = ALLOC_FN(_alloc)
+
+
+def profile_slots() -> list:
+    lib = load()
+    return [lib.wast3d_profile_slot_name(i).decode() for i in range(lib.wast3d_profile_slots())]
+
+
+def profile_enable(names=None):
+    """Enable event timing for the named stages (None = all, [] = off)."""
+    slots = profile_slots()
+    mask = 0
+    for i, n in enumerate(slots):
+        if names is None or n in names:
+            mask |= 1 << i
+    load().wast3d_profile_set(mask)
+
+
+def profile_read() -> dict:
+    """{stage: (total_ms, scopes)} accumulated since the last read."""
+    lib = load()
+    n = lib.wast3d_profile_slots()
+    ms = (C.c_double * n)()
+    cnt = (C.c_ulonglong * n)()
+    check(lib.wast3d_profile_read(ms, cnt), "profile_read")
+    return {name: (ms[i], int(cnt[i])) for i, name in enumerate(profile_slots()) if cnt[i]}
+
+
+def launch_count(reset: bool = False) -> int:
+    return int(load().wast3d_launch_count(int(reset)))

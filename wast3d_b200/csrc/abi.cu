@@ -1,6 +1,9 @@
 // C-ABI housekeeping: status strings, device check, last CUDA error, state export for tests.
 #include "common.cuh"
 #include <cstring>
+#include <atomic>
+#include <mutex>
+#include <vector>
 
 namespace w3d {
 
@@ -14,6 +17,33 @@ void set_last_cuda_error(cudaError_t e, const char* file, int line) {
 }
 
 const uint32_t* point_list_ptr(const BinningState& b, uint32_t num_tiles);
+
+// ---- launch counter + event profiling ------------------------------------------------------
+static std::atomic<unsigned long long> g_launches{0};
+static unsigned g_prof_mask = 0;
+struct ProfRec { int slot; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof_recs;
+static std::mutex g_prof_mu;
+static const char* const kSlotNames[PS_COUNT] = {
+    "preprocess", "depth_sort", "scan", "emit_instances", "tile_sort", "tile_ranges", "render_forward",
+    "backward_zero", "render_backward", "gaussian_backward", "knn", "match", "adam"};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+ProfScope::ProfScope(int slot_, cudaStream_t s) : slot(slot_), stream(s), start(nullptr), on(false) {
+    if (!((g_prof_mask >> slot) & 1u)) return;
+    if (cudaEventCreate(&start) != cudaSuccess) return;
+    cudaEventRecord(start, stream);
+    on = true;
+}
+ProfScope::~ProfScope() {
+    if (!on) return;
+    cudaEvent_t stop;
+    if (cudaEventCreate(&stop) != cudaSuccess) { cudaEventDestroy(start); return; }
+    cudaEventRecord(stop, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_recs.push_back({slot, start, stop});
+}
 
 __global__ void export_geom_kernel(int P, const float4* __restrict__ rec,
                                    const uint32_t* __restrict__ tiles_touched_in,
@@ -107,4 +137,39 @@ extern "C" int wast3d_raster_export_state(const wast3d_raster_params* prm, int n
         W3D_CUDA_TRY(cudaMemcpyAsync(ranges, im.ranges, (size_t)num_tiles * sizeof(uint2),
                                      cudaMemcpyDeviceToDevice, s));
     return WAST3D_OK;
+}
+
+extern "C" int wast3d_profile_set(unsigned slot_mask) {
+    g_prof_mask = slot_mask;
+    return WAST3D_OK;
+}
+extern "C" int wast3d_profile_slots(void) { return PS_COUNT; }
+extern "C" const char* wast3d_profile_slot_name(int slot) {
+    return (slot >= 0 && slot < PS_COUNT) ? kSlotNames[slot] : "";
+}
+// Synchronises the recorded events, ADDS their durations (ms) and counts into the caller's arrays
+// of wast3d_profile_slots() entries, and clears the records.
+extern "C" int wast3d_profile_read(double* ms_per_slot, unsigned long long* scopes_per_slot) {
+    std::vector<ProfRec> recs;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        recs.swap(g_prof_recs);
+    }
+    int rc = WAST3D_OK;
+    for (auto& r : recs) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) {
+            rc = WAST3D_ERR_CUDA;
+            cudaGetLastError();
+        } else {
+            if (ms_per_slot) ms_per_slot[r.slot] += (double)ms;
+            if (scopes_per_slot) scopes_per_slot[r.slot] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    return rc;
+}
+extern "C" unsigned long long wast3d_launch_count(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
 }

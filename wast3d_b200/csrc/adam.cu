@@ -60,6 +60,7 @@ extern "C" int wast3d_adam_step(size_t n, float* param, const float* grad, float
     size_t blocks = (n / 4 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    w3d::ProfScope ps(w3d::PS_ADAM, s);
     w3d::adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, param, grad, exp_avg, exp_avg_sq, 1.0f - beta1,
                                                       beta2, 1.0f - beta2, step_size, bc2_sqrt, eps, vec_ok);
     W3D_AFTER_LAUNCH(s, false);

@@ -29,11 +29,28 @@ constexpr uint32_t CULLED_KEY = 0xFFFFFFFFu;
 // (the reference's CHECK_CUDA(A, debug), auxiliary.h:166-173).
 #define W3D_AFTER_LAUNCH(stream, debug)                                          \
     do {                                                                         \
+        w3d::count_launch();                                                     \
         W3D_CUDA_TRY(cudaGetLastError());                                        \
         if (debug) W3D_CUDA_TRY(cudaStreamSynchronize(stream));                  \
     } while (0)
 
 void set_last_cuda_error(cudaError_t e, const char* file, int line);
+void count_launch();
+
+// Optional per-stage timing with CUDA events on the launching stream (wast3d_profile_*):
+// a ProfScope brackets the launches of one stage; it does nothing unless its slot is enabled.
+enum ProfSlot {
+    PS_PREPROCESS = 0, PS_DEPTH_SORT, PS_SCAN, PS_EMIT, PS_TILE_SORT, PS_RANGES, PS_RENDER_FWD,
+    PS_BWD_ZERO, PS_RENDER_BWD, PS_GAUSS_BWD, PS_KNN, PS_MATCH, PS_ADAM, PS_COUNT
+};
+struct ProfScope {
+    int slot;
+    cudaStream_t stream;
+    cudaEvent_t start;
+    bool on;
+    ProfScope(int slot, cudaStream_t s);
+    ~ProfScope();
+};
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

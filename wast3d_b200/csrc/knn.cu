@@ -323,6 +323,7 @@ extern "C" int wast3d_knn_dist2(int P, const float* points, float* mean_dist2, i
     cudaStream_t s = (cudaStream_t)stream_v;
     KnnScratch k = KnnScratch::carve(scratch, P, nullptr);
     const int nb = (P + 255) / 256;
+    ProfScope ps(PS_KNN, s);
 
     knn_bbox_init_kernel<<<1, 32, 0, s>>>((int*)k.bbox);
     W3D_AFTER_LAUNCH(s, false);

@@ -450,6 +450,7 @@ static int run_match(int Kc, int Ks, const float* mean_c, const float* cov_c, co
     unsigned long long* packed = c.take<unsigned long long>(Kc);
     uint32_t* err = c.take<uint32_t>(4);
     int rc = WAST3D_OK;
+    ProfScope ps(PS_MATCH, s);
     do {
         if (cudaMemsetAsync(packed, 0xFF, sizeof(unsigned long long) * (size_t)Kc, s) != cudaSuccess ||
             cudaMemsetAsync(err, 0, 16, s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
@@ -476,6 +477,7 @@ static int run_match(int Kc, int Ks, const float* mean_c, const float* cov_c, co
         }
         match_finalize_kernel<<<(Kc + 255) / 256, 256, 0, s>>>(Kc, packed, out_idx, out_cost);
         if (cudaGetLastError() != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+        for (int l = 0; l < (Ks > 0 ? 4 : 2); ++l) count_launch();
         // the MMA-timeout flag is the only thing that needs the host; it is tiny and rare
         uint32_t h_err = 0;
         if (cudaMemcpyAsync(&h_err, err, sizeof(h_err), cudaMemcpyDeviceToHost, s) != cudaSuccess ||

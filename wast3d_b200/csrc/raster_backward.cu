@@ -591,13 +591,18 @@ extern "C" int wast3d_raster_backward(const wast3d_raster_params* prm, int num_r
     const float focal_y = H / (2.0f * prm->tan_fovy);
     const float focal_x = W / (2.0f * prm->tan_fovx);
 
-    W3D_CUDA_TRY(cudaMemsetAsync(g.grad_rec, 0, 3 * (size_t)P * sizeof(float4), s));
+    {
+        ProfScope ps(PS_BWD_ZERO, s);
+        W3D_CUDA_TRY(cudaMemsetAsync(g.grad_rec, 0, 3 * (size_t)P * sizeof(float4), s));
+    }
     if (num_rendered > 0) {
+        ProfScope ps(PS_RENDER_BWD, s);
         render_backward_kernel<<<grid, TILE_PIX, 0, s>>>(
             im.ranges, point_list_ptr(bn, num_tiles), W, H, prm->background, g.rec,
             prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec);
         W3D_AFTER_LAUNCH(s, debug);
     }
+    ProfScope ps_gb(PS_GAUSS_BWD, s);
     gaussian_backward_kernel<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, radii, prm->shs, g.clamped, prm->scales, prm->rotations,
         prm->scale_modifier, prm->cov3D_precomp, prm->viewmatrix, prm->projmatrix, prm->campos,

@@ -461,14 +461,19 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
     const float focal_x = W / (2.0f * prm->tan_fovx);
 
     W3D_CUDA_TRY(cudaMemsetAsync(g.totals, 0, 32 * sizeof(uint32_t), s));
+    {
+    ProfScope ps(PS_PREPROCESS, s);
     preprocess_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, prm->scales, prm->scale_modifier, prm->rotations,
         prm->opacities, prm->shs, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
         prm->projmatrix, prm->campos, W, H, prm->tan_fovx, prm->tan_fovy, focal_x, focal_y, grid,
         prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.totals + 1);
     W3D_AFTER_LAUNCH(s, debug);
+    }
 
     // depth order: 4 stable 8-bit passes on the float bits (positive floats order like uints)
+    {
+    ProfScope ps(PS_DEPTH_SORT, s);
     st = radix_pass_u32(g.depth_key, nullptr, g.key_tmp, g.order_b, P, 0, 8, g.rs_hist, g.scan_scratch, s, debug);
     if (st) return st;
     st = radix_pass_u32(g.key_tmp, g.order_b, g.depth_key, g.order_a, P, 8, 8, g.rs_hist, g.scan_scratch, s, debug);
@@ -477,9 +482,12 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
     if (st) return st;
     st = radix_pass_u32(g.key_tmp, g.order_b, nullptr, g.order_a, P, 24, 8, g.rs_hist, g.scan_scratch, s, debug);
     if (st) return st;
-
+    }
+    {
+    ProfScope ps(PS_SCAN, s);
     st = scan_exclusive_u32(g.tiles_touched, g.order_a, g.offsets, P, g.scan_scratch, g.totals, s, debug);
     if (st) return st;
+    }
 
     // the one blocking read the reference also has (rasterizer_impl.cu:283)
     uint32_t host_totals[2] = {0, 0};
@@ -498,23 +506,30 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
 
     W3D_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, num_tiles * sizeof(uint2), s));
     if (R > 0) {
+        {
+        ProfScope ps(PS_EMIT, s);
         emit_instances_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.order_a, g.offsets, g.tiles_touched,
                                                                radii, g.rec, bn.keys_a, bn.vals_a, grid);
         W3D_AFTER_LAUNCH(s, debug);
+        }
+        ProfScope* pts = new ProfScope(PS_TILE_SORT, s);
         int bpp;
         const int passes = tile_sort_passes(num_tiles, &bpp);
         uint32_t *kin = bn.keys_a, *vin = bn.vals_a, *kout = bn.keys_b, *vout = bn.vals_b;
         for (int p = 0; p < passes; ++p) {
             st = radix_pass_u32(kin, vin, kout, vout, R, p * bpp, bpp, bn.rs_hist, bn.scan_scratch, s, debug);
-            if (st) return st;
+            if (st) { delete pts; return st; }
             uint32_t* t;
             t = kin; kin = kout; kout = t;
             t = vin; vin = vout; vout = t;
         }
+        delete pts;
+        ProfScope ps(PS_RANGES, s);
         tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted_tiles_ptr(bn, num_tiles), im.ranges);
         W3D_AFTER_LAUNCH(s, debug);
     }
 
+    ProfScope ps_render(PS_RENDER_FWD, s);
     render_forward_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, point_list_ptr(bn, num_tiles), W, H, g.rec,
                                                     prm->background, prm->sampling_offsets, im.final_T,
                                                     im.n_contrib, out_color, out_depth);
