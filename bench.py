@@ -21,9 +21,7 @@ import argparse
 import json
 import math
 import os
-import subprocess
 import sys
-import tempfile
 import time
 from pathlib import Path
 
@@ -67,44 +65,80 @@ def style_loss(out, tgt, dtgt):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock, power and clock-event (throttle) reasons sampled DURING the timed region.
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Reads the same NVML counters `nvidia-smi --query-gpu=clocks.sm,...,clocks_event_reasons.*` prints,
+    but in-process from a background thread that is started BEFORE the warm-up (NVML initialisation
+    takes the driver lock for hundreds of milliseconds and must not land inside the timed region);
+    only samples between begin() and end() are reported."""
 
-    def __init__(self, index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
+
+    def __init__(self, index, period_s=0.02):
+        import threading
+        self.samples, self.t0, self.t1, self.ok = [], None, None, False
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
-                                      stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+            import pynvml as nv
+            nv.nvmlInit()
+            # LOCAL_RANK indexes CUDA_VISIBLE_DEVICES; map it to the physical NVML index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.period = period_s
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        nv, h = self.nv, self.h
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1e3,
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "source": "nvml (in-process thread)"}
+        if not self.ok:
+            out["error"] = getattr(self, "err", "nvml unavailable")
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(", ") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
-        os.unlink(self.f.name)
+        self._stop.set()
+        self.th.join(timeout=2)
+        rows = [r for r in self.samples if self.t0 is not None and self.t0 <= r[0] <= (self.t1 or 1e30)]
+        out["sm_max_mhz"] = self.max_sm
         if not rows:
             return out
-        sm = sorted(float(r[1]) for r in rows)
+        sm = sorted(r[1] for r in rows)
         out["sm_mhz"] = sm[len(sm) // 2]
-        out["sm_max_mhz"] = float(rows[0][2])
-        out["power_w_max"] = max(float(r[3]) for r in rows)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for i, n in enumerate(names):
-            if any(r[5 + i].strip().lower().startswith("active") for r in rows):
-                out["reasons"].append(n)
+        out["sm_mhz_min"] = sm[0]
+        out["power_w_max"] = round(max(r[2] for r in rows), 1)
+        bits = 0
+        for r in rows:
+            bits |= r[3]
+        for name, attr in self.REASONS:
+            if bits & int(getattr(self.nv, attr)):
+                out["reasons"].append(name)
         out["samples"] = len(rows)
         return out
 
@@ -275,6 +309,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    sampler = ClockSampler(local) if rank == 0 else None  # started here: NVML init stays outside the timed region
     # warm-up (allocator, clocks, Adam state)
     for i in range(max(args.warmup, 3)):
         step(i, False)
@@ -284,8 +319,11 @@ def main():
     _lib.profile_enable(["render_backward"])
     _lib.profile_read()
     _lib.launch_count(reset=True)
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.begin()
     ms_total = timed(args.steps, False, it0)
+    if sampler:
+        sampler.end()
     launches = _lib.launch_count(reset=True)
     clocks = sampler.stop() if sampler else None
     prof = _lib.profile_read()
@@ -320,9 +358,15 @@ def main():
     fwd_bytes = 339.0 * spec.P + 216.0 * R + 32.0 * N
     bwd_bytes = 931.0 * spec.P + 80.0 * R + 32.0 * N
     adam_bytes = 7.0 * 4.0 * 59.0 * spec.P
+    traffic, traffic_src = None, None
+    tj = ROOT / "profiles" / "ncu_traffic.json"
+    if tj.exists():
+        t = json.loads(tj.read_text()).get(args.config, {}).get("render_backward_kernel")
+        if t:
+            traffic, traffic_src = t["dram_read_bytes"] + t["dram_write_bytes"], t["source"]
     roofline = {"bound": "hbm", "kernel": "render_backward_kernel (K7)", "achieved": round(achieved, 2),
                 "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": round(achieved / hbm_peak, 5), "traffic": None,
+                "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "traffic_source": traffic_src,
                 "kernel_ms": round(rb_ms_avg, 4), "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "K7 is FP32/SFU/atomic bound, not HBM bound (SURVEY §7); whole-step figure: "
                         "step_algorithmic_GBps",
