@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define WAST3D_ABI_VERSION 1
+#define WAST3D_ABI_VERSION 2
 
 enum wast3d_status {
     WAST3D_OK = 0,
@@ -68,6 +68,17 @@ typedef struct wast3d_raster_params {
     const float* campos;          /* [3]                                                   */
     const float* sampling_offsets;/* [H,W,2] per-pixel sample jitter (forward.cu:287), or
                                      NULL meaning all zero                                 */
+    /* ---- model-space inputs (ABI v2) ------------------------------
+     * raw_params != 0 folds the activations that gaussian_renderer/__init__.py:61-90 applies
+     * through the GaussianModel getters (scene/gaussian_model.py:26-41,95-120) into K1/K9:
+     *   opacities = opacity LOGITS          (sigmoid applied here)
+     *   scales    = LOG scales              (exp applied here)
+     *   rotations = unnormalised quaternion (x / max(|x|, 1e-12) applied here, F.normalize)
+     *   shs       = _features_dc [P,1,3], shs_rest = _features_rest [P,M-1,3]
+     *               (torch.cat of get_features is never materialised)
+     * colors_precomp / cov3D_precomp must be NULL in this mode. */
+    int raw_params;
+    const float* shs_rest;        /* [P,M-1,3] or NULL when M == 1 (raw_params only)        */
 } wast3d_raster_params;
 
 /* Replaces RasterizeGaussiansCUDA -> CudaRasterizer::Rasterizer::forward
@@ -99,6 +110,19 @@ int wast3d_raster_backward(const wast3d_raster_params* prm, int num_rendered, co
                            float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
                            float* dL_dscale, float* dL_drot, float* dL_dcamViewDepth,
                            void* stream);
+
+/* Backward of a raw_params forward: gradients with respect to the six leaf parameters of
+ * GaussianModel (scene/gaussian_model.py:149-167), i.e. Rasterizer::backward followed by the
+ * autograd backward of sigmoid / exp / normalize / cat that the reference runs as separate
+ * torch kernels.  dL_dxyz [P,3], dL_dfeatures_dc [P,1,3], dL_dfeatures_rest [P,M-1,3],
+ * dL_dopacity_logit [P,1], dL_dlog_scale [P,3], dL_drotation [P,4]; every element is written.
+ * dL_dmean2D [P,3] (the viewspace_points gradient) is optional (NULL = not needed). */
+int wast3d_raster_backward_raw(const wast3d_raster_params* prm, int num_rendered, const int* radii,
+                               void* geom_buffer, void* binning_buffer, void* img_buffer,
+                               const float* dL_dpix, const float* dL_ddepth, float* dL_dxyz,
+                               float* dL_dfeatures_dc, float* dL_dfeatures_rest,
+                               float* dL_dopacity_logit, float* dL_dlog_scale, float* dL_drotation,
+                               float* dL_dmean2D, void* stream);
 
 /* Test/inspection hook (no reference equivalent is Python-visible; mirrors the state
  * structs of rasterizer_impl.h:29-65).  Any output may be NULL.

@@ -29,7 +29,7 @@ def test_python_binding_covers_header(built):
     _lib.load()
     assert _lib.MISSING == []
     assert sorted(_lib.SIGNATURES) == header_symbols()
-    assert _lib.load().wast3d_abi_version() == 1
+    assert _lib.load().wast3d_abi_version() == 2
     assert _lib.load().wast3d_strerror(0) == b"ok"
     assert b"no CPU fallback" in _lib.load().wast3d_strerror(4)
 
@@ -50,6 +50,13 @@ def test_product_path_fails_loudly_without_gpu(built):
         _C.rasterize_gaussians(torch.zeros(3), torch.zeros(4, 3), e, torch.zeros(4, 1), torch.ones(4, 3),
                                torch.ones(4, 4), 1.0, e, torch.eye(4), torch.eye(4), 1.0, 1.0, 16, 16,
                                torch.zeros(4, 1, 3), 0, torch.zeros(3), False, False, e)
+    with pytest.raises(RuntimeError):
+        from wast3d_b200.model_render import rasterize_model
+        from wast3d_b200.diff_gaussian_rasterization import GaussianRasterizationSettings
+        rs = GaussianRasterizationSettings(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0,
+                                           torch.zeros(3), False, False)
+        rasterize_model(torch.zeros(4, 3), torch.zeros(4, 3), torch.zeros(4, 1, 3), torch.zeros(4, 0, 3),
+                        torch.zeros(4, 1), torch.zeros(4, 3), torch.ones(4, 4), rs)
     with pytest.raises(RuntimeError):
         distCUDA2(torch.zeros(8, 3))
     with pytest.raises(RuntimeError):

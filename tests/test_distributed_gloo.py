@@ -53,7 +53,7 @@ def _grad_job(rank, world):
     for p in ps[:3]:
         p.grad = torch.randn(p.shape, generator=g)
     # ps[3] has no grad: must be skipped on every rank
-    wd.allreduce_gradients(ps, bucket_bytes=20000)  # forces several buckets incl. a packed one
+    wd.allreduce_gradients(ps, bucket_bytes=20000, small_bytes=5000)  # in-place chunks + one packed buffer
     return [p.grad.clone() if p.grad is not None else None for p in ps]
 
 
@@ -74,6 +74,57 @@ def test_view_parallel_gradient_allreduce():
         for i in range(3):
             assert torch.equal(out[r][i], sums[i])      # two-rank fp32 sum is order independent
         assert out[r][3] is None
+
+
+class _RangeSGD:
+    """CPU stand-in with FusedAdam's begin_step()/step_range() protocol (plain SGD on a flat range)."""
+
+    def __init__(self, params, lr):
+        self.param_groups = [{"params": list(params), "lr": lr}]
+        self.began = 0
+        self.ranges = []
+
+    def begin_step(self):
+        self.began += 1
+
+    def step_range(self, p, s0, e0):
+        self.ranges.append((id(p), s0, e0))
+        with torch.no_grad():
+            p.view(-1)[s0:e0] -= self.param_groups[0]["lr"] * p.grad.view(-1)[s0:e0]
+
+    def step(self):
+        raise AssertionError("world > 1 must take the overlapped path")
+
+
+def _step_job(rank, world):
+    ps = [torch.nn.Parameter(torch.ones(1000, 3)), torch.nn.Parameter(torch.ones(1000, 15, 3)),
+          torch.nn.Parameter(torch.ones(10, 1))]
+    g = torch.Generator().manual_seed(200 + rank)
+    for p in ps:
+        p.grad = torch.randn(p.shape, generator=g)
+    opt = _RangeSGD(ps, 0.5)
+    wd.allreduce_and_step(opt, average=True, chunk_bytes=40000)
+    covered = {}
+    for pid, s0, e0 in opt.ranges:
+        covered.setdefault(pid, []).append((s0, e0))
+    full = all(sorted(covered[id(p)])[0][0] == 0 and sorted(covered[id(p)])[-1][1] == p.numel() and
+               all(a[1] == b[0] for a, b in zip(sorted(covered[id(p)]), sorted(covered[id(p)])[1:])) for p in ps)
+    return [p.detach().clone() for p in ps], opt.began, full
+
+
+def test_overlapped_allreduce_and_step():
+    out = _run(_step_job)
+    gens = [torch.Generator().manual_seed(200 + r) for r in range(2)]
+    shapes = [(1000, 3), (1000, 15, 3), (10, 1)]
+    per_rank = [[torch.randn(s, generator=gens[r]) for s in shapes] for r in range(2)]
+    for r in range(2):
+        params, began, full = out[r]
+        assert began == 1 and full           # one step count bump, every element updated exactly once
+        for i in range(3):
+            expect = torch.ones(shapes[i]) - 0.5 * ((per_rank[0][i] + per_rank[1][i]) / 2)
+            assert torch.allclose(params[i], expect, rtol=0, atol=1e-6)
+    for i in range(3):
+        assert torch.equal(out[0][0][i], out[1][0][i])   # replicas stay bit-identical
 
 
 def _match_job(rank, world):

@@ -203,7 +203,7 @@ def test_autograd_module_and_render(built):
     bg = torch.tensor([0.0, 0.0, 0.0], device="cuda")
     torch.manual_seed(0)
     offs = -torch.rand(120, 160, 2, device="cuda")
-    out = render(cam, pc, PipelineParams(), bg, sampling_offsets=offs)
+    out = render(cam, pc, PipelineParams(fused_activations=False), bg, sampling_offsets=offs)
     assert set(out) == {"render", "depth", "viewspace_points", "visibility_filter", "radii"}
     loss = out["render"].mean() + 0.1 * out["depth"].mean()
     loss.backward()
@@ -216,6 +216,70 @@ def test_autograd_module_and_render(built):
     assert (out2["render"] - out["render"]).abs().max().item() <= 2e-4
     assert (out2["depth"] - out["depth"]).abs().max().item() <= 2e-4
     assert torch.equal(out2["radii"], out["radii"]) or (out2["radii"] != out["radii"]).float().mean() < 1e-3
+
+
+@pytest.mark.parametrize("P,sh_degree,active,W,H", [(5000, 3, 3, 160, 120), (4999, 3, 1, 97, 61),
+                                                     (777, 0, 0, 64, 48), (2050, 2, 2, 80, 80), (31, 1, 1, 33, 17)])
+def test_model_render_matches_unfused(built, P, sh_degree, active, W, H):
+    """Fused model-space path (raw_params: sigmoid/exp/normalize/cat folded into K1/K9) against the
+    reference-shaped op-by-op chain: same image (<= 1e-4, the north star's colour/depth bar) and the
+    same gradients of the six leaves (<= 1e-3 rel L2, the gradient bar)."""
+    from wast3d_b200.gaussian_renderer import render
+    from wast3d_b200.scene import GaussianModel, PipelineParams, orbit_cameras, synthetic_gaussians
+    arrs = synthetic_gaussians(P, seed=9, log_scale_mu=-3.3, sh_degree=sh_degree)
+    cam = orbit_cameras(4, 4.03, 0.0, 0.6911, W, H, device="cuda", sphere=True)[1]
+    bg = torch.tensor([0.1, 0.3, 0.2], device="cuda")
+    torch.manual_seed(0)
+    offs = -torch.rand(H, W, 2, device="cuda")
+    tgt = torch.rand(3, H, W, device="cuda")
+    res = []
+    for fused in (True, False):
+        pc = GaussianModel.from_arrays(arrs, sh_degree=sh_degree, device="cuda")
+        pc.active_sh_degree = active
+        out = render(cam, pc, PipelineParams(fused_activations=fused), bg, sampling_offsets=offs)
+        loss = ((out["render"] - tgt) ** 2).sum() + 0.1 * (out["depth"] ** 2).sum()
+        loss.backward()
+        res.append((out, pc))
+    (of, pf), (ou, pu) = res
+    assert (of["render"] - ou["render"]).abs().max().item() <= 1e-4
+    assert (of["depth"] - ou["depth"]).abs().max().item() <= 1e-4
+    assert (of["radii"] != ou["radii"]).float().mean().item() <= 1e-3
+    assert torch.equal(of["visibility_filter"], of["radii"] > 0)
+    names = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation")
+    for n, a, b in zip(names, pf.parameters(), pu.parameters()):
+        assert a.grad is not None and a.grad.shape == a.shape, n
+        if b.grad is None or b.numel() == 0:
+            continue
+        assert torch.isfinite(a.grad).all(), n
+        if b.grad.norm().item() > 1e-12:
+            assert rel_l2(a.grad, b.grad) <= 1e-3, (n, rel_l2(a.grad, b.grad))
+    assert rel_l2(of["viewspace_points"].grad, ou["viewspace_points"].grad) <= 1e-3
+    # culled Gaussians get exactly zero gradient on every leaf
+    culled = of["radii"] == 0
+    if culled.any():
+        for a in pf.parameters():
+            if a.numel():
+                assert a.grad.reshape(a.shape[0], -1)[culled].abs().max().item() == 0
+
+
+def test_model_render_rejects_bad_inputs(built):
+    from wast3d_b200.model_render import rasterize_model
+    from wast3d_b200.diff_gaussian_rasterization import GaussianRasterizationSettings
+    from wast3d_b200.scene import orbit_cameras
+    import math
+    cam = orbit_cameras(2, 4.0, 0.0, 0.7, 32, 32, device="cuda", sphere=True)[0]
+    rs = GaussianRasterizationSettings(32, 32, math.tan(cam.FoVx / 2), math.tan(cam.FoVy / 2),
+                                       torch.zeros(3, device="cuda"), 1.0, cam.world_view_transform,
+                                       cam.full_proj_transform, 0, cam.camera_center, False, False)
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    with pytest.raises(RuntimeError):  # non-contiguous parameter
+        rasterize_model(z(8, 3), z(8, 3), z(8, 1, 3), z(8, 0, 3), z(8, 1), z(8, 6)[:, ::2], z(8, 4), rs)
+    with pytest.raises(RuntimeError):  # CPU tensor: no fallback
+        rasterize_model(torch.zeros(8, 3), torch.zeros(8, 3), torch.zeros(8, 1, 3), torch.zeros(8, 0, 3),
+                        torch.zeros(8, 1), torch.zeros(8, 3), torch.zeros(8, 4), rs)
+    # empty scene renders the background... like the reference's zero-filled outputs (rasterize_points.cu:69)
+    c, d, r = rasterize_model(z(0, 3), z(0, 3), z(0, 1, 3), z(0, 15, 3), z(0, 1), z(0, 3), z(0, 4), rs)
+    assert c.abs().max().item() == 0 and d.abs().max().item() == 0 and r.numel() == 0
 
 
 @pytest.mark.parametrize("cfg", ["c2", "c3"])

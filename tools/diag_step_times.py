@@ -44,18 +44,32 @@ def main():
               f"cudaMalloc retries {st['num_alloc_retries']}, allocs {st['allocation.all.allocated']}")
 
     run(10, "cold steps 0-9")
-    run(16, "warm steps (sync each)")
-    # unsynchronised throughput
-    for tag, sampler in (("no sampler", False), ("nvidia-smi -lms 100 sampler", True), ("no sampler again", False)):
-        s = bench.ClockSampler(0) if sampler else None
+    import threading
+    for tag, period in (("no sampler", None), ("nvml 20 ms", 0.02), ("no sampler", None), ("nvml 100 ms", 0.1),
+                        ("nvml 20 ms clocks only", -0.02), ("no sampler", None)):
+        smp = None
+        if period is not None:
+            smp = bench.ClockSampler(0, period_s=abs(period))
+            if period < 0:  # clocks only: drop the power / reasons queries
+                nv, h = smp.nv, smp.h
+                smp._stop.set(); smp.th.join()
+                smp._stop = threading.Event()
+                def _run(smp=smp, nv=nv, h=h):
+                    while not smp._stop.is_set():
+                        smp.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), 0.0, 0))
+                        smp._stop.wait(0.02)
+                smp.th = threading.Thread(target=_run, daemon=True); smp.th.start()
+            time.sleep(0.3)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if smp: smp.begin()
         a.record()
-        for i in range(32):
+        for i in range(30):
             step(i)
         b.record()
         torch.cuda.synchronize()
-        print(f"{tag}: {a.elapsed_time(b) / 32:.3f} ms/step", s.stop() if s else "")
+        if smp: smp.end()
+        print(f"{tag}: {a.elapsed_time(b) / 30:.3f} ms/step", smp.stop() if smp else "")
 
 
 if __name__ == "__main__":

@@ -29,6 +29,7 @@ class RasterParams(C.Structure):
         ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
         ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
         ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("sampling_offsets", C.c_void_p),
+        ("raw_params", C.c_int), ("shs_rest", C.c_void_p),
     ]
 
 
@@ -42,6 +43,8 @@ SIGNATURES = {
                                    _vp, _vp, _vp, C.POINTER(_i), _vp]),
     "wast3d_raster_backward": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_raster_backward_raw": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_raster_export_state": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp]),
     "wast3d_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
@@ -118,6 +121,18 @@ def fptr(t: torch.Tensor | None, keep: list, dtype=torch.float32) -> int | None:
     return c.data_ptr()
 
 
+def bucket_bytes(n: int) -> int:
+    """Scratch sizes are rounded up to 1/16..1/8 of their magnitude (>= 1 MiB granules): the
+    binning buffer scales with the per-view instance count, and a slightly different size every
+    call would make torch's caching allocator cudaMalloc a fresh segment for every new camera
+    (tens of milliseconds each, and tens of GB of reserved memory after a few hundred steps)."""
+    n = int(n)
+    if n <= (1 << 20):
+        return n
+    g = 1 << max(20, n.bit_length() - 4)
+    return (n + g - 1) // g * g
+
+
 class GrowBuffer:
     """One of the three opaque byte buffers; plays resizeFunctional (rasterize_points.cu:27-33)."""
 
@@ -128,7 +143,7 @@ class GrowBuffer:
 
         def _alloc(nbytes, _user):
             try:
-                self.tensor = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+                self.tensor = torch.empty(bucket_bytes(nbytes), dtype=torch.uint8, device=self.device)
                 return self.tensor.data_ptr()
             except Exception as e:  # never let an exception cross the C boundary
                 self.error = e

@@ -132,12 +132,14 @@ struct ImageState {
     float* final_T;       // [N]  offset 0 (alpha = 1 - final_T)
     uint32_t* n_contrib;  // [N]
     uint2* ranges;        // [T]
+    uint32_t* tile_count; // [T]  instances per tile (counted while emitting)
     static ImageState carve(void* chunk, size_t N, size_t T, size_t* bytes) {
         Carver c(chunk);
         ImageState s;
         s.final_T = c.take<float>(N);
         s.n_contrib = c.take<uint32_t>(N);
         s.ranges = c.take<uint2>(T);
+        s.tile_count = c.take<uint32_t>(T);
         if (bytes) *bytes = c.bytes();
         return s;
     }

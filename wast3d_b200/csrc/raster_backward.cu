@@ -23,6 +23,7 @@
 //  Summation order across pixels differs from the reference's atomics (both are unordered);
 //  gradients agree to fp32 rounding, not bitwise (tests state the tolerance per tensor).
 #include "raster_math.cuh"
+#include <cstdlib>
 
 namespace w3d {
 
@@ -279,14 +280,209 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     cp_async_wait<0>();
 }
 
+// Variant: the reduce lanes add straight into the global gradient record (one 4-byte RED per
+// slot and (warp, Gaussian) hit) — no shared accumulator, no flush, one barrier per batch.
+__global__ void __launch_bounds__(TILE_PIX)
+render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                       const int W, const int H, const float* __restrict__ bg_color,
+                       const float4* __restrict__ rec, const float* __restrict__ sampling_offsets,
+                       const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+                       const float* __restrict__ dL_dpixels, const float* __restrict__ dL_ddepths,
+                       float4* __restrict__ grad_rec) {
+    __shared__ float4 s_r0[2][BWD_BATCH];
+    __shared__ float4 s_r1[2][BWD_BATCH];
+    __shared__ float4 s_r2[2][BWD_BATCH];
+    __shared__ uint32_t s_id[2][BWD_BATCH];
+    __shared__ uint32_t s_warp_max[TILE_PIX / 32];
+
+    float* grad_f = reinterpret_cast<float*>(grad_rec);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+
+    float2 pixf = make_float2((float)px, (float)py);
+    if (inside && sampling_offsets != nullptr) {
+        const float2 o = *reinterpret_cast<const float2*>(sampling_offsets + 2 * (size_t)pix_id);
+        pixf.x = (float)px + o.x;
+        pixf.y = (float)py + o.y;
+    }
+    const float inf = __int_as_float(0x7f800000);
+    float bx0 = inside ? pixf.x : inf, bx1 = inside ? pixf.x : -inf;
+    float by0 = inside ? pixf.y : inf, by1 = inside ? pixf.y : -inf;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
+        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
+        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
+    }
+
+    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
+
+    // backward.cu:463-478
+    const float T_final = inside ? final_Ts[pix_id] : 0.f;
+    float T = T_final;
+    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+    const size_t HW = (size_t)H * W;
+    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, ddepth = 0.f;
+    if (inside) {
+        dpix0 = dL_dpixels[pix_id];
+        dpix1 = dL_dpixels[HW + pix_id];
+        dpix2 = dL_dpixels[2 * HW + pix_id];
+        ddepth = dL_ddepths ? dL_ddepths[pix_id] : 0.f;
+    }
+    // backward.cu:560-563 (pixel constant)
+    float bg_dot_dpixel = 0.f;
+    bg_dot_dpixel += bg_color[0] * dpix0;
+    bg_dot_dpixel += bg_color[1] * dpix1;
+    bg_dot_dpixel += bg_color[2] * dpix2;
+
+    // Nothing behind the tile's deepest last contributor can receive gradient.
+    const uint32_t warp_max_last = __reduce_max_sync(0xffffffffu, last_contributor);
+    if (lane == 0) s_warp_max[warp] = warp_max_last;
+    __syncthreads();
+    uint32_t n_eff = 0;
+#pragma unroll
+    for (int w = 0; w < TILE_PIX / 32; ++w) n_eff = max(n_eff, s_warp_max[w]);
+    n_eff = min(n_eff, range.y - range.x);
+    const int n = (int)n_eff;
+    const int rounds = (n + BWD_BATCH - 1) / BWD_BATCH;
+
+    auto prefetch = [&](int b) {
+        const int p = b * BWD_BATCH + tid;
+        if (p < n) {
+            const uint32_t id = point_list[range.x + (uint32_t)(n - 1 - p)];
+            s_id[b & 1][tid] = id;
+            const float4* src = rec + 3 * (size_t)id;
+            cp_async16(&s_r0[b & 1][tid], src);
+            cp_async16(&s_r1[b & 1][tid], src + 1);
+            cp_async16(&s_r2[b & 1][tid], src + 2);
+        }
+        cp_async_commit();
+    };
+
+    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
+    float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
+    const float ddelx_dx = 0.5 * W;  // backward.cu:486-487
+    const float ddely_dy = 0.5 * H;
+
+    if (rounds > 0) prefetch(0);
+    for (int b = 0; b < rounds; ++b) {
+        // one barrier per batch: batch b has landed, and every warp is done with batch b-1 whose
+        // buffer the prefetch of b+1 overwrites
+        cp_async_wait<0>();
+        __syncthreads();
+        if (b + 1 < rounds) prefetch(b + 1);
+
+        const int cnt = min(BWD_BATCH, n - b * BWD_BATCH);
+        const float4* r0 = s_r0[b & 1];
+        const float4* r1 = s_r1[b & 1];
+        const float4* r2 = s_r2[b & 1];
+        if (warp_max_last > 0) {
+            for (int j0 = 0; j0 < cnt; j0 += 32) {
+                const int jj = j0 + lane;
+                bool hit = false;
+                if (jj < cnt) {
+                    const uint32_t pos = (uint32_t)(n - 1 - (b * BWD_BATCH + jj));
+                    const float4 a = r0[jj];
+                    const float hy = r2[jj].w;
+                    hit = pos < warp_max_last &&
+                          !((a.x + a.w < bx0) || (a.x - a.w > bx1) || (a.y + hy < by0) ||
+                            (a.y - hy > by1));
+                }
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                while (m) {
+                    const int j = j0 + __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint32_t pos = (uint32_t)(n - 1 - (b * BWD_BATCH + j));
+                    float v[12];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) v[i] = 0.f;
+                    bool active = false;
+                    // backward.cu:512-514: skip Gaussians behind this pixel's last contributor
+                    if (pos < last_contributor) {
+                        const float4 a = r0[j];
+                        const float4 con_o = r1[j];
+                        const float dx = __fsub_rn(a.x, pixf.x);
+                        const float dy = __fsub_rn(a.y, pixf.y);
+                        const float sy = __fmul_rn(__fmul_rn(con_o.z, dy), dy);
+                        const float sq = __fmaf_rn(dx, __fmul_rn(con_o.x, dx), sy);
+                        const float cr = __fmul_rn(__fmul_rn(con_o.y, dx), dy);
+                        const float power = __fmaf_rn(sq, -0.5f, -cr);
+                        if (!(power > 0.0f)) {
+                            const float G = expf(power);
+                            const float alpha = fminf(0.99f, __fmul_rn(con_o.w, G));
+                            if (!(alpha < 1.0f / 255.0f)) {
+                                active = true;
+                                const float4 c = r2[j];
+                                // backward.cu:529-563
+                                T = T / (1.f - alpha);
+                                const float dchannel_dcolor = alpha * T;
+                                float dL_dalpha = 0.0f;
+                                accum0 = last_alpha * last_c0 + (1.f - last_alpha) * accum0;
+                                last_c0 = c.x;
+                                dL_dalpha += (c.x - accum0) * dpix0;
+                                v[8] = dchannel_dcolor * dpix0;
+                                accum1 = last_alpha * last_c1 + (1.f - last_alpha) * accum1;
+                                last_c1 = c.y;
+                                dL_dalpha += (c.y - accum1) * dpix1;
+                                v[9] = dchannel_dcolor * dpix1;
+                                accum2 = last_alpha * last_c2 + (1.f - last_alpha) * accum2;
+                                last_c2 = c.z;
+                                dL_dalpha += (c.z - accum2) * dpix2;
+                                v[10] = dchannel_dcolor * dpix2;
+                                v[6] = dchannel_dcolor * ddepth;  // backward.cu:552
+
+                                dL_dalpha *= T;
+                                last_alpha = alpha;
+                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+
+                                // backward.cu:567-583
+                                const float dL_dG = con_o.w * dL_dalpha;
+                                const float gdx = G * dx;
+                                const float gdy = G * dy;
+                                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
+                                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
+                                v[0] = dL_dG * dG_ddelx * ddelx_dx;
+                                v[1] = dL_dG * dG_ddely * ddely_dy;
+                                v[2] = -0.5f * gdx * dx * dL_dG;
+                                v[3] = -0.5f * gdx * dy * dL_dG;
+                                v[4] = -0.5f * gdy * dy * dL_dG;
+                                v[5] = G * dL_dalpha;
+                            }
+                        }
+                    }
+                    if (__any_sync(0xffffffffu, active)) {
+                        const float tot = warp_reduce12(v, lane);
+                        const int sub = ((lane >> 1) & 3);  // 2*b2 + b1
+                        const int slot = 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1) + sub;
+                        if (!(lane & 1) && sub < 3 && slot != 7 && slot != 11)
+                            atomicAdd(grad_f + 12 * (size_t)s_id[b & 1][j] + slot, tot);
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+
 // ------------------------------------------------------------------ K8 + K9 ---------------
 constexpr int GB_THREADS = 128;
 constexpr int GB_WARPS = GB_THREADS / 32;
 constexpr int GB_SH_STRIDE = 49;
 
+// RAW: model-space inputs (wast3d_raster_params::raw_params): scales/rotations/SH arrive
+// un-activated, and the gradients written are those of the six GaussianModel leaves, i.e. this
+// kernel also does the autograd backward of exp / normalize / sigmoid / cat.  In RAW mode
+// dL_dsh is dL/d_features_dc [P,1,3] and dL_dsh_rest is dL/d_features_rest [P,M-1,3].
+template <bool RAW>
 __global__ void __launch_bounds__(GB_THREADS)
 gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                          const int* __restrict__ radii, const float* __restrict__ shs,
+                         const float* __restrict__ shs_rest, const float4* __restrict__ rec,
                          const uint8_t* __restrict__ clamped, const float* __restrict__ scales,
                          const float* __restrict__ rotations, const float scale_modifier,
                          const float* __restrict__ cov3D_precomp, const float* __restrict__ view,
@@ -296,9 +492,10 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                          float* __restrict__ dL_dconic_out, float* __restrict__ dL_dopacity,
                          float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D,
                          float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
+                         float* __restrict__ dL_dsh_rest,
                          float* __restrict__ dL_dscale, float* __restrict__ dL_drot,
                          float* __restrict__ dL_dviewdepth_out) {
-    __shared__ float s_sh[GB_WARPS][32 * GB_SH_STRIDE];
+    __shared__ __align__(16) float s_sh[GB_WARPS][32 * GB_SH_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
     const int warp_first = blockIdx.x * GB_THREADS + warp * 32;
@@ -321,12 +518,18 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         float cov6[6];
         float3 sc = make_float3(0.f, 0.f, 0.f);
         float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+        float q_denom = 1.f;
         if (cov3D_precomp != nullptr) {
 #pragma unroll
             for (int k = 0; k < 6; ++k) cov6[k] = cov3D_precomp[6 * idx + k];
         } else {
             sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
             q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+            if (RAW) {
+                sc = act_exp3(sc);
+                q_denom = quat_denom(q);
+                q = act_normalize4(q, q_denom);
+            }
             cov3d_from_scale_rot(sc, scale_modifier, q, cov6);
         }
 
@@ -440,6 +643,19 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
             drot.y = 2 * y * (dMt.c[1][0] + dMt.c[0][1]) + 2 * z * (dMt.c[2][0] + dMt.c[0][2]) + 2 * r * (dMt.c[1][2] - dMt.c[2][1]) - 4 * x * (dMt.c[2][2] + dMt.c[1][1]);
             drot.z = 2 * x * (dMt.c[1][0] + dMt.c[0][1]) + 2 * r * (dMt.c[2][0] - dMt.c[0][2]) + 2 * z * (dMt.c[1][2] + dMt.c[2][1]) - 4 * y * (dMt.c[2][2] + dMt.c[0][0]);
             drot.w = 2 * r * (dMt.c[0][1] - dMt.c[1][0]) + 2 * x * (dMt.c[2][0] + dMt.c[0][2]) + 2 * y * (dMt.c[1][2] + dMt.c[2][1]) - 4 * z * (dMt.c[1][1] + dMt.c[0][0]);
+            if (RAW) {
+                // exp backward: d/dlog_s = d/ds * s   (sc holds the activated scale)
+                dscale.x *= sc.x; dscale.y *= sc.y; dscale.z *= sc.z;
+                // normalize backward (x / max(|x|, eps)): (g - q_hat (q_hat . g)) / |x|; below eps the
+                // denominator is the constant eps and the map is linear
+                if (q_denom > 1e-12f) {
+                    const float dot = q.x * drot.x + q.y * drot.y + q.z * drot.z + q.w * drot.w;
+                    drot = make_float4((drot.x - q.x * dot) / q_denom, (drot.y - q.y * dot) / q_denom,
+                                       (drot.z - q.z * dot) / q_denom, (drot.w - q.w * dot) / q_denom);
+                } else {
+                    drot = make_float4(drot.x / q_denom, drot.y / q_denom, drot.z / q_denom, drot.w / q_denom);
+                }
+            }
         }
     }
 
@@ -449,11 +665,22 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         const int rows_valid = min(32, P - warp_first);
         if (rows_valid > 0) {
             const int row_floats = 3 * M;
+            const int rest_floats = 3 * (M - 1);
             const int used = 3 * (D + 1) * (D + 1);
-            float* row = s_sh[warp] + lane * GB_SH_STRIDE;
-            if (need)
-                stage_sh_rows(shs + (size_t)warp_first * row_floats, row_floats, used, rows_valid, need,
-                              s_sh[warp], GB_SH_STRIDE, lane);
+            // RAW: `row` addresses the linear _features_rest block so that row[3k + c] (k >= 1) is
+            // coefficient k of this Gaussian; the degree-0 term lives in registers (dc_grad).
+            float* row = RAW ? s_sh[warp] + lane * rest_floats - 3 : s_sh[warp] + lane * GB_SH_STRIDE;
+            float dc_grad[3] = {0.f, 0.f, 0.f};
+            if (need) {
+                if (RAW) {
+                    if (used > 3)
+                        stage_rows_linear(shs_rest + (size_t)warp_first * rest_floats, rest_floats, used - 3,
+                                          rows_valid, need, s_sh[warp], lane);
+                } else {
+                    stage_sh_rows(shs + (size_t)warp_first * row_floats, row_floats, used, rows_valid, need,
+                                  s_sh[warp], GB_SH_STRIDE, lane);
+                }
+            }
             __syncwarp();
             if (vis) {
                 const float3 cam = make_float3(campos[0], campos[1], campos[2]);
@@ -520,8 +747,13 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                 basis[13] = SH_C3[4] * x * (4.f * zz - xx - yy); basis[14] = SH_C3[5] * z * (xx - yy);
                 basis[15] = SH_C3[6] * x * (xx - 3.f * yy);
                 const int ncoef = (D + 1) * (D + 1);
+                if (RAW) {
+                    dc_grad[0] = basis[0] * dRGB[0];
+                    dc_grad[1] = basis[0] * dRGB[1];
+                    dc_grad[2] = basis[0] * dRGB[2];
+                }
 #pragma unroll
-                for (int k = 0; k < 16; ++k) {
+                for (int k = RAW ? 1 : 0; k < 16; ++k) {
                     if (k < M) {
                         const float bk = k < ncoef ? basis[k] : 0.f;
                         row[3 * k + 0] = bk * dRGB[0];
@@ -529,28 +761,48 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                         row[3 * k + 2] = bk * dRGB[2];
                     }
                 }
-            } else {
-                for (int e = 0; e < row_floats; ++e) row[e] = 0.f;
+            } else if (lane < rows_valid) {
+                for (int e = RAW ? 3 : 0; e < row_floats; ++e) row[e] = 0.f;
             }
             __syncwarp();
-            unstage_rows(dL_dsh + (size_t)warp_first * row_floats, row_floats, rows_valid, s_sh[warp],
-                         GB_SH_STRIDE, lane);
+            if (RAW) {
+                if (live) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
+                if (rest_floats > 0)
+                    unstage_rows_linear(dL_dsh_rest + (size_t)warp_first * rest_floats, rest_floats, rows_valid,
+                                        s_sh[warp], lane);
+            } else {
+                unstage_rows(dL_dsh + (size_t)warp_first * row_floats, row_floats, rows_valid, s_sh[warp],
+                             GB_SH_STRIDE, lane);
+            }
         }
     }
 
     if (!live) return;
-    dL_dmean2D[3 * idx + 0] = g0.x;
-    dL_dmean2D[3 * idx + 1] = g0.y;
-    dL_dmean2D[3 * idx + 2] = 0.f;
-    dL_dcolor[3 * idx + 0] = g2.x;
-    dL_dcolor[3 * idx + 1] = g2.y;
-    dL_dcolor[3 * idx + 2] = g2.z;
-    dL_dopacity[idx] = g1.y;
+    if (dL_dmean2D) {
+        dL_dmean2D[3 * idx + 0] = g0.x;
+        dL_dmean2D[3 * idx + 1] = g0.y;
+        dL_dmean2D[3 * idx + 2] = 0.f;
+    }
+    if (dL_dcolor) {
+        dL_dcolor[3 * idx + 0] = g2.x;
+        dL_dcolor[3 * idx + 1] = g2.y;
+        dL_dcolor[3 * idx + 2] = g2.z;
+    }
+    if (RAW) {
+        // sigmoid backward: d/dlogit = d/do * o (1 - o); o is the activated opacity of the record
+        float o = 0.f;
+        if (vis) o = rec[3 * (size_t)idx + 1].w;
+        dL_dopacity[idx] = g1.y * ((1.f - o) * o);
+    } else {
+        dL_dopacity[idx] = g1.y;
+    }
     dL_dmean3D[3 * idx + 0] = dmean.x;
     dL_dmean3D[3 * idx + 1] = dmean.y;
     dL_dmean3D[3 * idx + 2] = dmean.z;
+    if (dL_dcov3D) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = dcov[k];
+        for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = dcov[k];
+    }
     dL_dscale[3 * idx + 0] = dscale.x;
     dL_dscale[3 * idx + 1] = dscale.y;
     dL_dscale[3 * idx + 2] = dscale.z;
@@ -563,22 +815,13 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
 
 using namespace w3d;
 
-extern "C" int wast3d_raster_backward(const wast3d_raster_params* prm, int num_rendered,
-                                      const int* radii, void* geom_buffer, void* binning_buffer,
-                                      void* img_buffer, const float* dL_dpix, const float* dL_ddepth,
-                                      float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
-                                      float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
-                                      float* dL_dsh, float* dL_dscale, float* dL_drot,
-                                      float* dL_dcamViewDepth, void* stream_v) {
-    cudaStream_t s = (cudaStream_t)stream_v;
-    int st = validate_params(prm, false);
-    if (st != WAST3D_OK) return st;
+static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendered, const int* radii,
+                                void* geom_buffer, void* binning_buffer, void* img_buffer,
+                                const float* dL_dpix, const float* dL_ddepth, float* dL_dmean2D,
+                                float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
+                                float* dL_dcov3D, float* dL_dsh, float* dL_dsh_rest, float* dL_dscale,
+                                float* dL_drot, float* dL_dcamViewDepth, cudaStream_t s) {
     const int P = prm->P, W = prm->width, H = prm->height;
-    if (P == 0) return WAST3D_OK;
-    if (num_rendered < 0 || !geom_buffer || !img_buffer || !binning_buffer || !dL_dpix ||
-        !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
-        !dL_drot || (prm->shs && prm->M > 0 && !dL_dsh))
-        return WAST3D_ERR_INVALID_ARGUMENT;
     const bool debug = prm->debug != 0;
     const size_t N = (size_t)W * H;
     const dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, 1);
@@ -597,18 +840,62 @@ extern "C" int wast3d_raster_backward(const wast3d_raster_params* prm, int num_r
     }
     if (num_rendered > 0) {
         ProfScope ps(PS_RENDER_BWD, s);
-        render_backward_kernel<<<grid, TILE_PIX, 0, s>>>(
+        static const int variant = getenv("WAST3D_K7_VARIANT") ? atoi(getenv("WAST3D_K7_VARIANT")) : 1;
+        auto k7 = variant == 1 ? render_backward_direct_kernel : render_backward_kernel;
+        k7<<<grid, TILE_PIX, 0, s>>>(
             im.ranges, point_list_ptr(bn, num_tiles), W, H, prm->background, g.rec,
             prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec);
         W3D_AFTER_LAUNCH(s, debug);
     }
     ProfScope ps_gb(PS_GAUSS_BWD, s);
-    gaussian_backward_kernel<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
-        P, prm->D, prm->M, prm->means3D, radii, prm->shs, g.clamped, prm->scales, prm->rotations,
-        prm->scale_modifier, prm->cov3D_precomp, prm->viewmatrix, prm->projmatrix, prm->campos,
-        focal_x, focal_y, prm->tan_fovx, prm->tan_fovy, g.grad_rec, dL_dmean2D, dL_dconic,
-        dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dcamViewDepth);
+    auto gb = prm->raw_params ? gaussian_backward_kernel<true> : gaussian_backward_kernel<false>;
+    gb<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
+        P, prm->D, prm->M, prm->means3D, radii, prm->shs, prm->shs_rest, g.rec, g.clamped, prm->scales,
+        prm->rotations, prm->scale_modifier, prm->cov3D_precomp, prm->viewmatrix, prm->projmatrix,
+        prm->campos, focal_x, focal_y, prm->tan_fovx, prm->tan_fovy, g.grad_rec, dL_dmean2D, dL_dconic,
+        dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dsh_rest, dL_dscale, dL_drot,
+        dL_dcamViewDepth);
     W3D_AFTER_LAUNCH(s, debug);
     return WAST3D_OK;
 }
 
+extern "C" int wast3d_raster_backward(const wast3d_raster_params* prm, int num_rendered,
+                                      const int* radii, void* geom_buffer, void* binning_buffer,
+                                      void* img_buffer, const float* dL_dpix, const float* dL_ddepth,
+                                      float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                                      float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                                      float* dL_dsh, float* dL_dscale, float* dL_drot,
+                                      float* dL_dcamViewDepth, void* stream_v) {
+    int st = validate_params(prm, false);
+    if (st != WAST3D_OK) return st;
+    if (prm->raw_params) return WAST3D_ERR_INVALID_ARGUMENT;  // use wast3d_raster_backward_raw
+    if (prm->P == 0) return WAST3D_OK;
+    if (num_rendered < 0 || !geom_buffer || !img_buffer || !binning_buffer || !dL_dpix ||
+        !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale ||
+        !dL_drot || (prm->shs && prm->M > 0 && !dL_dsh))
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    return raster_backward_impl(prm, num_rendered, radii, geom_buffer, binning_buffer, img_buffer, dL_dpix,
+                                dL_ddepth, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D,
+                                dL_dcov3D, dL_dsh, nullptr, dL_dscale, dL_drot, dL_dcamViewDepth,
+                                (cudaStream_t)stream_v);
+}
+
+extern "C" int wast3d_raster_backward_raw(const wast3d_raster_params* prm, int num_rendered,
+                                          const int* radii, void* geom_buffer, void* binning_buffer,
+                                          void* img_buffer, const float* dL_dpix, const float* dL_ddepth,
+                                          float* dL_dxyz, float* dL_dfeatures_dc, float* dL_dfeatures_rest,
+                                          float* dL_dopacity_logit, float* dL_dlog_scale,
+                                          float* dL_drotation, float* dL_dmean2D, void* stream_v) {
+    int st = validate_params(prm, false);
+    if (st != WAST3D_OK) return st;
+    if (!prm->raw_params) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (prm->P == 0) return WAST3D_OK;
+    if (num_rendered < 0 || !geom_buffer || !img_buffer || !binning_buffer || !dL_dpix || !dL_dxyz ||
+        !dL_dfeatures_dc || (prm->M > 1 && !dL_dfeatures_rest) || !dL_dopacity_logit || !dL_dlog_scale ||
+        !dL_drotation)
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    return raster_backward_impl(prm, num_rendered, radii, geom_buffer, binning_buffer, img_buffer, dL_dpix,
+                                dL_ddepth, dL_dmean2D, nullptr, dL_dopacity_logit, nullptr, dL_dxyz, nullptr,
+                                dL_dfeatures_dc, dL_dfeatures_rest, dL_dlog_scale, dL_drotation, nullptr,
+                                (cudaStream_t)stream_v);
+}

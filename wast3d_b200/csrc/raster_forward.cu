@@ -28,9 +28,11 @@ constexpr int PRE_WARPS = PRE_THREADS / 32;
 constexpr int SH_MAX_ROW = 48;             // M = 16 coefficients x RGB
 constexpr int SH_STRIDE = SH_MAX_ROW + 1;  // odd -> conflict-free per-Gaussian reads
 
-// forward.cu:20-71.  `sh` points at this Gaussian's staged row (k-th coefficient at sh[3k..]).
-__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* sh, float3 pos, float3 campos,
-                                            unsigned* clamped_bits) {
+// forward.cu:20-71.  `sh` points at this Gaussian's staged row (k-th coefficient at sh[3k..],
+// k >= 1); the degree-0 coefficient is read from sh_dc (== sh unless the model-space path keeps
+// _features_dc and _features_rest apart).
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* sh_dc, const float* sh, float3 pos,
+                                            float3 campos, unsigned* clamped_bits) {
     float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
     const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
     dir.x = dir.x / len;
@@ -39,7 +41,7 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* sh, float3 pos
     float res[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float r = SH_C0 * sh[c];
+        float r = SH_C0 * sh_dc[c];
         if (deg > 0) {
             const float x = dir.x, y = dir.y, z = dir.z;
             r = r - SH_C1 * y * sh[3 + c] + SH_C1 * z * sh[6 + c] - SH_C1 * x * sh[9 + c];
@@ -91,11 +93,14 @@ __device__ __forceinline__ float2 cutoff_extent(float A, float B, float C, float
     return make_float2(hx, hy);
 }
 
+// RAW: model-space inputs (wast3d_raster_params::raw_params) — activations applied here.
+template <bool RAW>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                   const float* __restrict__ scales, const float scale_modifier,
                   const float* __restrict__ rotations, const float* __restrict__ opacities,
-                  const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
+                  const float* __restrict__ shs, const float* __restrict__ shs_rest,
+                  const float* __restrict__ cov3D_precomp,
                   const float* __restrict__ colors_precomp, const float* __restrict__ viewmatrix,
                   const float* __restrict__ projmatrix, const float* __restrict__ cam_pos,
                   const int W, const int H, const float tan_fovx, const float tan_fovy,
@@ -103,7 +108,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   const bool prefiltered, int* __restrict__ radii, float4* __restrict__ rec,
                   uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
                   uint8_t* __restrict__ clamped, uint32_t* __restrict__ flags) {
-    __shared__ float s_sh[PRE_WARPS][32 * SH_STRIDE];
+    __shared__ __align__(16) float s_sh[PRE_WARPS][32 * SH_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
     const int warp_first = blockIdx.x * PRE_THREADS + warp * 32;
@@ -133,8 +138,12 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
 #pragma unroll
                 for (int k = 0; k < 6; ++k) cov6[k] = cov3D_precomp[6 * idx + k];
             } else {
-                const float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
-                const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+                float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+                float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
+                if (RAW) {
+                    sc = act_exp3(sc);
+                    q = act_normalize4(q, quat_denom(q));
+                }
                 cov3d_from_scale_rot(sc, scale_modifier, q, cov6);
             }
             float3 cov = cov2d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov6, viewmatrix, nullptr);
@@ -167,12 +176,25 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
         const unsigned need = __ballot_sync(0xffffffffu, visible);
         if (need) {
             const int rows_valid = min(32, P - warp_first);
-            const int row_floats = 3 * M;
             const int used = 3 * (D + 1) * (D + 1);
-            stage_sh_rows(shs + (size_t)warp_first * row_floats, row_floats, used, rows_valid, need,
-                          s_sh[warp], SH_STRIDE, lane);
-            __syncwarp();
-            if (visible) rgb = sh_to_rgb(D, s_sh[warp] + lane * SH_STRIDE, p_orig, *reinterpret_cast<const float3*>(cam_pos) , &clamp_bits);
+            const float3 cam = *reinterpret_cast<const float3*>(cam_pos);
+            if (RAW) {
+                // _features_dc [P,1,3] read per thread, _features_rest [P,M-1,3] copied linearly
+                float dc[3] = {0.f, 0.f, 0.f};
+                if (visible) { dc[0] = shs[3 * idx]; dc[1] = shs[3 * idx + 1]; dc[2] = shs[3 * idx + 2]; }
+                const int rest_floats = 3 * (M - 1);
+                if (used > 3)
+                    stage_rows_linear(shs_rest + (size_t)warp_first * rest_floats, rest_floats, used - 3,
+                                      rows_valid, need, s_sh[warp], lane);
+                if (visible) rgb = sh_to_rgb(D, dc, s_sh[warp] + lane * rest_floats - 3, p_orig, cam, &clamp_bits);
+            } else {
+                const int row_floats = 3 * M;
+                stage_sh_rows(shs + (size_t)warp_first * row_floats, row_floats, used, rows_valid, need,
+                              s_sh[warp], SH_STRIDE, lane);
+                __syncwarp();
+                const float* row = s_sh[warp] + lane * SH_STRIDE;
+                if (visible) rgb = sh_to_rgb(D, row, row, p_orig, cam, &clamp_bits);
+            }
         }
     } else if (visible) {
         rgb = make_float3(colors_precomp[3 * idx], colors_precomp[3 * idx + 1], colors_precomp[3 * idx + 2]);
@@ -184,7 +206,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     clamped[idx] = (uint8_t)clamp_bits;
     depth_key[idx] = visible ? __float_as_uint(p_view.z) : CULLED_KEY;
     if (visible) {
-        const float o = opacities[idx];
+        const float o = RAW ? act_sigmoid(opacities[idx]) : opacities[idx];
         const float2 ext = cutoff_extent(conic.x, conic.y, conic.z, o);
         rec[3 * idx + 0] = make_float4(point_image.x, point_image.y, p_view.z, ext.x);
         rec[3 * idx + 1] = make_float4(conic.x, conic.y, conic.z, o);
@@ -202,47 +224,119 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
     present[idx] = v.z <= 0.2f ? 0 : 1;
 }
 
-// One thread per Gaussian in DEPTH order: emits (tile id, Gaussian id) for every tile of its
-// rectangle (row-major, like duplicateWithKeys rasterizer_impl.cu:98-109) at its scanned
-// offset.  Since inputs come in (depth, index) order a stable partition by tile id then gives
-// the reference's (tile, depth, index) order.
-__global__ void __launch_bounds__(256)
+// Emits (tile id, Gaussian id) for every tile of every visible Gaussian's rectangle, Gaussians in
+// DEPTH order and a Gaussian's tiles row-major (like duplicateWithKeys rasterizer_impl.cu:98-109),
+// so that a stable partition by tile id yields the reference's (tile, depth, index) order.
+// A warp owns 32 depth-consecutive Gaussians; their instances form one contiguous output range
+// [off_0, off_31 + n_31) which the 32 lanes write with coalesced stores: lane p finds its
+// Gaussian with a 5-step shuffle binary search over the scanned offsets.  Persistent grid; every
+// block also counts instances per tile in shared memory (flushed once), from which the per-tile
+// ranges follow by a scan — identifyTileRanges (rasterizer_impl.cu:116-138) never has to read
+// the sorted keys.
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_MAX_SMEM_TILES = 12288;  // 48 KB of counters; larger grids count in global memory
+
+__global__ void __launch_bounds__(EMIT_THREADS)
 emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
                       const uint32_t* __restrict__ tiles_touched, const int* __restrict__ radii,
                       const float4* __restrict__ rec, uint32_t* __restrict__ keys,
-                      uint32_t* __restrict__ vals, const dim3 grid) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= P) return;
-    const uint32_t i = order[k];
-    if (tiles_touched[i] == 0) return;
-    uint32_t off = offsets[k];
-    const float4 r0 = rec[3 * i];
-    uint2 rect_min, rect_max;
-    tile_rect(make_float2(r0.x, r0.y), radii[i], rect_min, rect_max, grid);
-    for (uint32_t y = rect_min.y; y < rect_max.y; ++y)
-        for (uint32_t x = rect_min.x; x < rect_max.x; ++x) {
-            keys[off] = y * grid.x + x;
-            vals[off] = i;
-            ++off;
+                      uint32_t* __restrict__ vals, uint32_t* __restrict__ tile_count, const dim3 grid,
+                      const int num_tiles, const bool smem_hist) {
+    extern __shared__ uint32_t s_count[];
+    if (smem_hist) {
+        for (int t = threadIdx.x; t < num_tiles; t += EMIT_THREADS) s_count[t] = 0;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = EMIT_THREADS / 32;
+    const int n_chunks = (P + 31) / 32;
+    for (int chunk = blockIdx.x * warps_per_block + (threadIdx.x >> 5); chunk < n_chunks;
+         chunk += gridDim.x * warps_per_block) {
+        const int k = chunk * 32 + lane;
+        uint32_t id = 0, n = 0, off = 0xFFFFFFFFu, xy0 = 0, w = 1;
+        if (k < P) {
+            id = order[k];
+            n = tiles_touched[id];
+            off = offsets[k];
+            if (n != 0) {
+                const float4 r0 = rec[3 * (size_t)id];
+                uint2 rect_min, rect_max;
+                tile_rect(make_float2(r0.x, r0.y), radii[id], rect_min, rect_max, grid);
+                xy0 = rect_min.x | (rect_min.y << 16);
+                w = rect_max.x - rect_min.x;
+            }
         }
-}
-
-// rasterizer_impl.cu:116-138 on 32-bit tile ids
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(uint32_t L, const uint32_t* __restrict__ sorted_tiles, uint2* __restrict__ ranges) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= L) return;
-    const uint32_t cur = sorted_tiles[idx];
-    if (idx == 0)
-        ranges[cur].x = 0;
-    else {
-        const uint32_t prev = sorted_tiles[idx - 1];
-        if (cur != prev) {
-            ranges[prev].y = idx;
-            ranges[cur].x = idx;
+        const uint32_t begin = __shfl_sync(0xffffffffu, off, 0);
+        const uint32_t end = __reduce_max_sync(0xffffffffu, k < P ? off + n : 0u);
+        for (uint32_t p0 = begin; p0 < end; p0 += 32) {   // warp-uniform trip count
+            const uint32_t p = p0 + lane;
+            // largest lane l with off_l <= p (offsets are non-decreasing; lanes past P hold UINT_MAX)
+            int l = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, off, l + step);   // l + step <= 31
+                if (v <= p) l += step;
+            }
+            const uint32_t o = __shfl_sync(0xffffffffu, off, l);
+            const uint32_t src_xy0 = __shfl_sync(0xffffffffu, xy0, l);
+            const uint32_t src_w = __shfl_sync(0xffffffffu, w, l);
+            const uint32_t src_id = __shfl_sync(0xffffffffu, id, l);
+            if (p < end) {
+                const uint32_t t = p - o;
+                const uint32_t ty = t / src_w, tx = t - ty * src_w;
+                const uint32_t tile = ((src_xy0 >> 16) + ty) * grid.x + (src_xy0 & 0xFFFFu) + tx;
+                keys[p] = tile;
+                vals[p] = src_id;
+                if (smem_hist) atomicAdd(&s_count[tile], 1u);
+                else atomicAdd(&tile_count[tile], 1u);
+            }
         }
     }
-    if (idx == L - 1) ranges[cur].y = L;
+    if (smem_hist) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < num_tiles; t += EMIT_THREADS) {
+            const uint32_t c = s_count[t];
+            if (c) atomicAdd(&tile_count[t], c);
+        }
+    }
+}
+
+// ranges[t] = [sum of counts before t, + count) — one block, replaces identifyTileRanges.
+__global__ void __launch_bounds__(1024)
+tile_ranges_from_counts_kernel(int num_tiles, const uint32_t* __restrict__ tile_count,
+                               uint2* __restrict__ ranges) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < num_tiles; base += 1024) {
+        const int t = base + threadIdx.x;
+        const uint32_t c = t < num_tiles ? tile_count[t] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = s_warp[lane], wi = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, wi, d);
+                if (lane >= d) wi += u;
+            }
+            s_warp[lane] = wi - v;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t start = s_carry + s_warp[warp] + incl - c;
+        if (t < num_tiles) ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = start + c;
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------ K6 -------------------
@@ -397,11 +491,6 @@ const uint32_t* point_list_ptr(const BinningState& b, uint32_t num_tiles) {
     int bpp;
     return (tile_sort_passes(num_tiles, &bpp) & 1) ? b.vals_b : b.vals_a;
 }
-const uint32_t* sorted_tiles_ptr(const BinningState& b, uint32_t num_tiles) {
-    int bpp;
-    return (tile_sort_passes(num_tiles, &bpp) & 1) ? b.keys_b : b.keys_a;
-}
-
 int validate_params(const wast3d_raster_params* p, bool forward) {
     if (!p) return WAST3D_ERR_INVALID_ARGUMENT;
     if (p->P < 0 || p->width <= 0 || p->height <= 0) return WAST3D_ERR_INVALID_ARGUMENT;
@@ -414,6 +503,10 @@ int validate_params(const wast3d_raster_params* p, bool forward) {
     if (has_sr == (p->cov3D_precomp != nullptr)) return WAST3D_ERR_INVALID_ARGUMENT;
     if (p->shs) {
         if (p->D < 0 || p->D > 3 || p->M < (p->D + 1) * (p->D + 1) || p->M > 16)
+            return WAST3D_ERR_INVALID_ARGUMENT;
+    }
+    if (p->raw_params) {
+        if (!p->shs || !has_sr || p->colors_precomp || p->cov3D_precomp || (p->M > 1 && !p->shs_rest))
             return WAST3D_ERR_INVALID_ARGUMENT;
     }
     return WAST3D_OK;
@@ -463,9 +556,10 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
     W3D_CUDA_TRY(cudaMemsetAsync(g.totals, 0, 32 * sizeof(uint32_t), s));
     {
     ProfScope ps(PS_PREPROCESS, s);
-    preprocess_kernel<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(
+    auto pre = prm->raw_params ? preprocess_kernel<true> : preprocess_kernel<false>;
+    pre<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, prm->scales, prm->scale_modifier, prm->rotations,
-        prm->opacities, prm->shs, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
+        prm->opacities, prm->shs, prm->shs_rest, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
         prm->projmatrix, prm->campos, W, H, prm->tan_fovx, prm->tan_fovy, focal_x, focal_y, grid,
         prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.totals + 1);
     W3D_AFTER_LAUNCH(s, debug);
@@ -504,12 +598,24 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
     if (!bin_chunk) return WAST3D_ERR_ALLOC;
     BinningState bn = BinningState::carve(bin_chunk, R, nullptr);
 
-    W3D_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, num_tiles * sizeof(uint2), s));
     if (R > 0) {
+        W3D_CUDA_TRY(cudaMemsetAsync(im.tile_count, 0, num_tiles * sizeof(uint32_t), s));
         {
         ProfScope ps(PS_EMIT, s);
-        emit_instances_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.order_a, g.offsets, g.tiles_touched,
-                                                               radii, g.rec, bn.keys_a, bn.vals_a, grid);
+        const bool smem_hist = num_tiles <= (uint32_t)EMIT_MAX_SMEM_TILES;
+        const size_t smem = smem_hist ? num_tiles * sizeof(uint32_t) : 0;
+        static bool attr_set = false;
+        if (!attr_set) {
+            W3D_CUDA_TRY(cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              EMIT_MAX_SMEM_TILES * (int)sizeof(uint32_t)));
+            attr_set = true;
+        }
+        const int n_chunks = (P + 31) / 32;
+        int blocks = 148 * 4;
+        if (blocks > (n_chunks + 7) / 8) blocks = (n_chunks + 7) / 8;
+        emit_instances_kernel<<<blocks, EMIT_THREADS, smem, s>>>(P, g.order_a, g.offsets, g.tiles_touched, radii,
+                                                               g.rec, bn.keys_a, bn.vals_a, im.tile_count, grid,
+                                                               (int)num_tiles, smem_hist);
         W3D_AFTER_LAUNCH(s, debug);
         }
         ProfScope* pts = new ProfScope(PS_TILE_SORT, s);
@@ -517,7 +623,9 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         const int passes = tile_sort_passes(num_tiles, &bpp);
         uint32_t *kin = bn.keys_a, *vin = bn.vals_a, *kout = bn.keys_b, *vout = bn.vals_b;
         for (int p = 0; p < passes; ++p) {
-            st = radix_pass_u32(kin, vin, kout, vout, R, p * bpp, bpp, bn.rs_hist, bn.scan_scratch, s, debug);
+            // the last pass does not need to write the sorted tile ids: ranges come from the counts
+            st = radix_pass_u32(kin, vin, p + 1 < passes ? kout : nullptr, vout, R, p * bpp, bpp, bn.rs_hist,
+                                bn.scan_scratch, s, debug);
             if (st) { delete pts; return st; }
             uint32_t* t;
             t = kin; kin = kout; kout = t;
@@ -525,8 +633,10 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         }
         delete pts;
         ProfScope ps(PS_RANGES, s);
-        tile_ranges_kernel<<<(R + 255) / 256, 256, 0, s>>>(R, sorted_tiles_ptr(bn, num_tiles), im.ranges);
+        tile_ranges_from_counts_kernel<<<1, 1024, 0, s>>>((int)num_tiles, im.tile_count, im.ranges);
         W3D_AFTER_LAUNCH(s, debug);
+    } else {
+        W3D_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, num_tiles * sizeof(uint2), s));
     }
 
     ProfScope ps_render(PS_RENDER_FWD, s);

@@ -219,4 +219,54 @@ __device__ __forceinline__ void unstage_rows(float* __restrict__ g_rows, int row
     }
 }
 
+// ---- model-space activations (raw_params mode; scene/gaussian_model.py:26-41) ----------------
+// Same expressions as the torch kernels the reference runs for the GaussianModel getters:
+// sigmoid = 1 / (1 + exp(-x)), exp, F.normalize = x / max(||x||_2, 1e-12).
+__device__ __forceinline__ float act_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float3 act_exp3(float3 v) { return make_float3(expf(v.x), expf(v.y), expf(v.z)); }
+__device__ __forceinline__ float quat_denom(float4 q) {
+    return fmaxf(sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w), 1e-12f);
+}
+__device__ __forceinline__ float4 act_normalize4(float4 q, float denom) {
+    return make_float4(q.x / denom, q.y / denom, q.z / denom, q.w / denom);
+}
+
+// Linear staging for the model-space path: _features_rest rows are 3*(M-1) floats (45 at degree 3,
+// odd => one-thread-per-row reads of a LINEAR copy are already bank-conflict free), so the
+// warp's block of rows_valid rows is copied 1:1 into shared memory with 16-byte cp.async
+// (float4 that may straddle two rows).  float4s that only cover rows outside `need`, or only
+// elements >= used (inactive SH degrees), are skipped.  Ends with the data visible to the warp.
+__device__ __forceinline__ void stage_rows_linear(const float* __restrict__ g_rows, int row_floats,
+                                                  int used, int rows_valid, unsigned need,
+                                                  float* s_rows, int lane) {
+    const int total = rows_valid * row_floats;
+    const int total4 = (((size_t)g_rows & 15) == 0 && row_floats >= 4) ? (total >> 2) : 0;
+    int g = (4 * lane) / row_floats, e = 4 * lane - g * row_floats;
+    for (int q = lane; q < total4; q += 32) {
+        const bool spill = e + 3 >= row_floats;  // the float4 reaches into row g + 1
+        const bool want = (((need >> g) & 1u) && e < used) || (spill && ((need >> (g + 1)) & 1u));
+        if (want) cp_async16(s_rows + 4 * q, g_rows + 4 * q);
+        e += 128;
+        while (e >= row_floats) { e -= row_floats; ++g; }
+    }
+    cp_async_commit();
+    for (int i = (total4 << 2) + lane; i < total; i += 32) {  // unaligned base or tail
+        const int gg = i / row_floats, ee = i - gg * row_floats;
+        if (((need >> gg) & 1u) && ee < used) s_rows[i] = __ldg(g_rows + i);
+    }
+    cp_async_wait<0>();
+    __syncwarp();
+}
+
+// Inverse: the linear shared-memory block (every element of rows_valid rows valid) to global.
+__device__ __forceinline__ void unstage_rows_linear(float* __restrict__ g_rows, int row_floats,
+                                                    int rows_valid, const float* s_rows, int lane) {
+    const int total = rows_valid * row_floats;
+    const int total4 = ((size_t)g_rows & 15) == 0 ? (total >> 2) : 0;
+    float4* g4 = reinterpret_cast<float4*>(g_rows);
+    const float4* s4 = reinterpret_cast<const float4*>(s_rows);
+    for (int q = lane; q < total4; q += 32) g4[q] = s4[q];
+    for (int i = (total4 << 2) + lane; i < total; i += 32) g_rows[i] = s_rows[i];
+}
+
 }  // namespace w3d

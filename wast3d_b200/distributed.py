@@ -28,55 +28,102 @@ def shard_bounds(n: int, rank: int, world: int) -> tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
-def allreduce_gradients(params: Iterable[torch.Tensor], group=None, average: bool = False,
-                        bucket_bytes: int = 256 << 20, async_op: bool = False):
-    """Sum (or average) `.grad` of every parameter across ranks, in flat fp32 buckets.
+def _avg_supported(group) -> bool:
+    try:
+        return dist.get_backend(group) == "nccl"
+    except Exception:  # noqa: BLE001
+        return False
 
-    Buckets are filled in the given order (pass parameters in reverse-autograd order to start
-    the first collective as early as possible) and sized for launch latency, not link count:
-    on NVSwitch every peer is at full bandwidth.  Returns the list of work handles when
-    async_op=True (call `finish_allreduce` to wait and scatter back)."""
-    params = [p for p in params if p.grad is not None]
+
+def _grad_chunks(params, chunk_bytes: int, small_bytes: int):
+    """Work list for the gradient all-reduce.  Every entry is (flat_view, [(param, start, end)], packed):
+    large gradients are reduced IN PLACE as contiguous slices of at most chunk_bytes (no pack /
+    unpack copies); gradients smaller than small_bytes are packed together into one buffer so
+    that tiny tensors do not each pay a collective launch."""
+    work, small, small_n = [], [], 0
+    for p in params:
+        g = p.grad
+        if g is None:
+            continue
+        nbytes = g.numel() * g.element_size()
+        if nbytes < small_bytes or not g.is_contiguous():
+            small.append(p)
+            small_n += nbytes
+            continue
+        flat = g.view(-1)
+        per = max(1, chunk_bytes // g.element_size())
+        for s0 in range(0, flat.numel(), per):
+            e0 = min(flat.numel(), s0 + per)
+            work.append((flat[s0:e0], [(p, s0, e0)], False))
+    if small:
+        work.insert(0, (torch.cat([p.grad.reshape(-1) for p in small]), [(p, 0, p.grad.numel()) for p in small], True))
+    return work
+
+
+def allreduce_gradients(params: Iterable[torch.Tensor], group=None, average: bool = False,
+                        bucket_bytes: int = 128 << 20, async_op: bool = False, small_bytes: int = 1 << 20):
+    """Sum (or average) `.grad` of every parameter across ranks.
+
+    Gradients are reduced in place in contiguous chunks of at most `bucket_bytes` (sized for launch
+    latency and for overlap with the optimizer, not for link count: on NVSwitch every peer is at
+    full bandwidth); gradients below `small_bytes` share one packed buffer.  With NCCL the average
+    is taken inside the collective (ReduceOp.AVG).  Returns the list of pending chunks when
+    async_op=True (pass it to `finish_allreduce`, or use `allreduce_and_step`)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
+    params = [p for p in params if p.grad is not None]
     if world == 1 or not params:
         return []
-    buckets, cur, cur_bytes = [], [], 0
-    for p in params:
-        nbytes = p.grad.numel() * p.grad.element_size()
-        if cur and cur_bytes + nbytes > bucket_bytes:
-            buckets.append(cur)
-            cur, cur_bytes = [], 0
-        cur.append(p)
-        cur_bytes += nbytes
-    if cur:
-        buckets.append(cur)
+    use_avg = average and _avg_supported(group)
+    op = dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM
     pending = []
-    for bucket in buckets:
-        if len(bucket) == 1 and bucket[0].grad.is_contiguous():
-            flat = bucket[0].grad.view(-1)  # in place, no pack/unpack copy
-            packed = False
-        else:
-            flat = torch.cat([p.grad.reshape(-1) for p in bucket])
-            packed = True
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True)
-        pending.append((work, flat, bucket, packed))
+    for flat, owners, packed in _grad_chunks(params, bucket_bytes, small_bytes):
+        h = dist.all_reduce(flat, op=op, group=group, async_op=True)
+        pending.append((h, flat, owners, packed, average and not use_avg, world))
     if async_op:
-        return [(w, f, b, k, average, world) for (w, f, b, k) in pending]
-    finish_allreduce([(w, f, b, k, average, world) for (w, f, b, k) in pending])
+        return pending
+    finish_allreduce(pending)
     return []
 
 
+def _finish_one(entry):
+    work, flat, owners, packed, divide, world = entry
+    work.wait()
+    if divide:
+        flat.div_(world)
+    if packed:
+        off = 0
+        for p, s0, e0 in owners:
+            n = e0 - s0
+            p.grad.view(-1)[s0:e0].copy_(flat[off:off + n])
+            off += n
+
+
 def finish_allreduce(handles):
-    for work, flat, bucket, packed, average, world in handles:
-        work.wait()
-        if average:
-            flat.div_(world)
-        if packed:
-            off = 0
-            for p in bucket:
-                n = p.grad.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+    for entry in handles:
+        _finish_one(entry)
+
+
+def allreduce_and_step(optimizer, params: Iterable[torch.Tensor] = None, group=None, average: bool = True,
+                       chunk_bytes: int = 128 << 20):
+    """View-parallel optimizer step: all-reduce the gradients chunk by chunk and apply the Adam
+    update of each chunk as soon as ITS collective has finished, so the update of chunk i (HBM
+    bound, compute stream) overlaps the all-reduce of chunk i+1 (NVLink, NCCL stream).
+
+    `optimizer` must offer begin_step() and step_range(param, start, end) (optim.FusedAdam); with a
+    single rank this is optimizer.step().  Every rank applies the identical update, so parameters
+    stay replicated without a broadcast."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        optimizer.step()
+        return
+    if params is None:
+        params = [p for g in optimizer.param_groups for p in g["params"]]
+    pending = allreduce_gradients(params, group=group, average=average, bucket_bytes=chunk_bytes, async_op=True)
+    optimizer.begin_step()
+    for entry in pending:
+        _finish_one(entry)
+        for p, s0, e0 in entry[2]:
+            optimizer.step_range(p, s0, e0)
 
 
 def sharded_match(match_fn: Callable[..., Sequence[torch.Tensor]], row_tensors: Sequence[torch.Tensor],

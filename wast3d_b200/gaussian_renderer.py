@@ -14,6 +14,7 @@ import math
 import torch
 
 from .diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+from .model_render import model_supports_fusion, rasterize_model
 from .sh import eval_sh
 
 
@@ -23,6 +24,11 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
 
     `sampling_offsets` (extension) lets a caller pin the per-pixel jitter; by default it is
     drawn like the reference does: -rand(H, W, 2) in (-1, 0] (gaussian_renderer/__init__.py:31).
+
+    When `pc` is a GaussianModel with the reference's activations and neither Python-side SH nor
+    covariance is requested, the getters' sigmoid / exp / normalize / cat are folded into the
+    kernels (model_render.py); `pipe.fused_activations = False` forces the reference's op-by-op
+    call chain.  Both produce the same dict.
     """
     xyz = pc.get_xyz
     dev = xyz.device
@@ -48,6 +54,14 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         projmatrix=viewpoint_camera.full_proj_transform,
         sh_degree=pc.active_sh_degree, campos=viewpoint_camera.camera_center,
         prefiltered=False, debug=pipe.debug)
+    if (override_color is None and not pipe.convert_SHs_python and not pipe.compute_cov3D_python
+            and getattr(pipe, "fused_activations", True) and model_supports_fusion(pc)):
+        image, depth, radii = rasterize_model(
+            xyz, screenspace_points, pc._features_dc, pc._features_rest, pc._opacity, pc._scaling,
+            pc._rotation, settings, sampling_offsets)
+        return {"render": image, "depth": depth, "viewspace_points": screenspace_points,
+                "visibility_filter": radii > 0, "radii": radii}
+
     rasterizer = GaussianRasterizer(raster_settings=settings)
 
     scales = rotations = cov3D_precomp = None

@@ -1,0 +1,126 @@
+"""Fused "model-space" rasterisation: the autograd op takes the six LEAF
+parameters of GaussianModel (scene/gaussian_model.py:149-167) instead of their activated
+versions, so the four activation kernels of the reference's render()
+(gaussian_renderer/__init__.py:61-90: sigmoid / exp / normalize / cat through the getters of
+scene/gaussian_model.py:95-120), the 576 MB `get_features` concatenation and their autograd
+backward never run as separate torch kernels: K1 applies the activations while it reads the
+parameters, K8+K9 writes the gradients of the raw parameters directly
+(`wast3d_raster_params::raw_params`, `wast3d_raster_backward_raw`).
+
+Results equal the unfused path up to the rounding of the activations (tests/test_raster_gpu.py::
+test_model_render_matches_unfused).  There is no fallback: without the library it raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .diff_gaussian_rasterization import GaussianRasterizationSettings
+from .diff_gaussian_rasterization import _C as dgr_C
+
+
+def _prm(keep, rs: GaussianRasterizationSettings, xyz, f_dc, f_rest, opacity, scaling, rotation, offsets):
+    P = int(xyz.size(0))
+    M = 1 + (int(f_rest.size(1)) if f_rest.numel() else 0)
+    return dgr_C._params(
+        keep, P=P, D=rs.sh_degree, M=M, W=rs.image_width, H=rs.image_height, tan_fovx=rs.tanfovx,
+        tan_fovy=rs.tanfovy, scale_modifier=rs.scale_modifier, prefiltered=rs.prefiltered, debug=rs.debug,
+        bg=rs.bg, means3D=xyz, sh=f_dc, colors=None, opacity=opacity, scales=scaling, rotations=rotation,
+        cov3D_precomp=None, viewmatrix=rs.viewmatrix, projmatrix=rs.projmatrix, campos=rs.campos,
+        sampling_offsets=offsets, raw_params=True, sh_rest=f_rest)
+
+
+class _RasterizeModel(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz, means2D, f_dc, f_rest, opacity, scaling, rotation, raster_settings,
+                sampling_offsets):
+        rs = raster_settings
+        _lib.require_device(xyz)
+        if xyz.dim() != 2 or xyz.size(1) != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        lib = _lib.load()
+        dev = xyz.device
+        P, H, W = int(xyz.size(0)), int(rs.image_height), int(rs.image_width)
+        color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom, binning, img = _lib.GrowBuffer(dev), _lib.GrowBuffer(dev), _lib.GrowBuffer(dev)
+        keep: list = []
+        prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation, sampling_offsets)
+        rendered = C.c_int(0)
+        with torch.cuda.device(dev):
+            st = lib.wast3d_raster_forward(
+                C.byref(prm), geom.cb, None, binning.cb, None, img.cb, None, color.data_ptr(),
+                depth.data_ptr(), radii.data_ptr() if P else None, C.byref(rendered), _lib.stream_ptr())
+        for b in (geom, binning, img):
+            if b.error is not None:
+                raise b.error
+        _lib.check(st, "rasterize_model")
+        ctx.raster_settings = rs
+        ctx.num_rendered = rendered.value
+        ctx.save_for_backward(xyz, f_dc, f_rest, opacity, scaling, rotation, radii, geom.tensor,
+                              binning.tensor, img.tensor,
+                              sampling_offsets if sampling_offsets is not None else torch.empty(0))
+        ctx.mark_non_differentiable(radii)
+        return color, depth, radii
+
+    @staticmethod
+    def backward(ctx, g_color, g_depth, _g_radii):
+        rs = ctx.raster_settings
+        (xyz, f_dc, f_rest, opacity, scaling, rotation, radii, geom, binning, img, offsets) = ctx.saved_tensors
+        lib = _lib.load()
+        dev = xyz.device
+        P, H, W = int(xyz.size(0)), int(rs.image_height), int(rs.image_width)
+        if g_color is None:
+            g_color = torch.zeros((3, H, W), dtype=torch.float32, device=dev)
+        if g_depth is None:
+            g_depth = torch.zeros((H, W), dtype=torch.float32, device=dev)
+        opt = dict(dtype=torch.float32, device=dev)
+        d_xyz = torch.empty_like(xyz)
+        d_dc = torch.empty_like(f_dc)
+        d_rest = torch.empty_like(f_rest)
+        d_op = torch.empty_like(opacity)
+        d_sc = torch.empty_like(scaling)
+        d_rot = torch.empty_like(rotation)
+        d_m2d = torch.empty((P, 3), **opt) if ctx.needs_input_grad[1] else None
+        if P:
+            keep: list = []
+            prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation,
+                       offsets if offsets.numel() else None)
+            p = lambda t: None if t is None or t.numel() == 0 else t.data_ptr()
+            with torch.cuda.device(dev):
+                st = lib.wast3d_raster_backward_raw(
+                    C.byref(prm), int(ctx.num_rendered), _lib.fptr(radii, keep, torch.int32),
+                    _lib.fptr(geom, keep, torch.uint8), _lib.fptr(binning, keep, torch.uint8),
+                    _lib.fptr(img, keep, torch.uint8), _lib.fptr(g_color, keep), _lib.fptr(g_depth, keep),
+                    p(d_xyz), p(d_dc), p(d_rest), p(d_op), p(d_sc), p(d_rot), p(d_m2d), _lib.stream_ptr())
+            _lib.check(st, "rasterize_model_backward")
+        return d_xyz, d_m2d, d_dc, d_rest, d_op, d_sc, d_rot, None, None
+
+
+def rasterize_model(xyz, means2D, features_dc, features_rest, opacity_logits, log_scales, rotations,
+                    raster_settings: GaussianRasterizationSettings, sampling_offsets=None):
+    """(color[3,H,W], depth[H,W], radii[P]) from the RAW GaussianModel parameters."""
+    for name, t in (("features_dc", features_dc), ("features_rest", features_rest),
+                    ("opacity", opacity_logits), ("scaling", log_scales), ("rotation", rotations)):
+        if not t.is_contiguous() or t.dtype != torch.float32:
+            raise RuntimeError(f"rasterize_model: {name} must be contiguous float32")
+    return _RasterizeModel.apply(xyz, means2D, features_dc, features_rest, opacity_logits, log_scales,
+                                 rotations, raster_settings, sampling_offsets)
+
+
+def model_supports_fusion(pc) -> bool:
+    """True when `pc` exposes the six raw parameter tensors and uses the reference's activations
+    (scene/gaussian_model.py:26-41), so folding them into the kernels does not change results."""
+    names = ("_xyz", "_features_dc", "_features_rest", "_opacity", "_scaling", "_rotation")
+    if not all(isinstance(getattr(pc, n, None), torch.Tensor) for n in names):
+        return False
+    if getattr(pc, "scaling_activation", torch.exp) is not torch.exp:
+        return False
+    if getattr(pc, "opacity_activation", torch.sigmoid) is not torch.sigmoid:
+        return False
+    if getattr(pc, "rotation_activation", torch.nn.functional.normalize) is not torch.nn.functional.normalize:
+        return False
+    return all(getattr(pc, n).is_contiguous() and getattr(pc, n).dtype == torch.float32 for n in names)

@@ -174,10 +174,13 @@ def scene_cameras(spec: SceneSpec, n: int = 8, device="cuda"):
 class PipelineParams:
     """arguments/__init__.py PipelineParams: the three switches render() reads."""
 
-    def __init__(self, convert_SHs_python=False, compute_cov3D_python=False, debug=False):
+    def __init__(self, convert_SHs_python=False, compute_cov3D_python=False, debug=False,
+                 fused_activations=True):
         self.convert_SHs_python = convert_SHs_python
         self.compute_cov3D_python = compute_cov3D_python
         self.debug = debug
+        # extension: fold the GaussianModel activations into the kernels (model_render.py)
+        self.fused_activations = fused_activations
 
 
 @dataclass
