@@ -189,6 +189,19 @@ int wast3d_adam_step(size_t n, float* param, const float* grad, float* exp_avg,
                      float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int step,
                      void* stream);
 
+/* Test / measurement hooks for the binning primitives that replace the reference's CUB calls
+ * (cub::DeviceScan::InclusiveSum rasterizer_impl.cu:279, cub::DeviceRadixSort::SortPairs :305-310).
+ * wast3d_test_sort_pairs: stable LSD radix sort of n (u32 key, u32 value) pairs on key bits
+ * [begin_bit, end_bit); vals_in == NULL means values 0..n-1.  mode 0 = multi-kernel passes
+ * (histogram / table scan / scatter), 1 = single-kernel passes with decoupled look-back (what the
+ * rasteriser uses).  wast3d_test_scan: out[i] = sum_{k<i} in[perm ? perm[k] : k], *total = full sum
+ * (mode 0 = three kernels, 1 = one look-back kernel). */
+int wast3d_test_sort_pairs(size_t n, const uint32_t* keys_in, const uint32_t* vals_in,
+                           uint32_t* keys_out, uint32_t* vals_out, int begin_bit, int end_bit,
+                           int mode, void* stream);
+int wast3d_test_scan(size_t n, const uint32_t* in, const uint32_t* perm, uint32_t* out,
+                     uint32_t* total, int mode, void* stream);
+
 /* Measurement hooks (bench.py): per-stage CUDA-event timing on the launching stream and a count
  * of kernel launches issued by this library.  Slots: wast3d_profile_slots() names via
  * wast3d_profile_slot_name(); enable a subset with a bit mask (0 = off, the default).

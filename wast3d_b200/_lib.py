@@ -54,6 +54,8 @@ SIGNATURES = {
     "wast3d_nn_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_w2_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_w2_match_debug": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_test_sort_pairs": (_i, [_sz, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "wast3d_test_scan": (_i, [_sz, _vp, _vp, _vp, _vp, _i, _vp]),
     "wast3d_profile_set": (_i, [C.c_uint]),
     "wast3d_profile_slots": (_i, []),
     "wast3d_profile_slot_name": (C.c_char_p, [_i]),

@@ -78,6 +78,10 @@ constexpr int RS_RADIX = 256;
 inline size_t rs_num_blocks(size_t n) { return (n + RS_TILE - 1) / RS_TILE; }
 inline size_t rs_hist_words(size_t n) { return rs_num_blocks(n) * RS_RADIX; }
 
+size_t onesweep_workspace_words(size_t n, int passes);
+size_t scan_lookback_workspace_words(size_t n);
+constexpr int TILE_SORT_MAX_PASSES = 3;  // tile ids of up to 24 bits
+
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
@@ -101,8 +105,8 @@ struct GeomState {
     uint32_t* order_a;       // [P]  Gaussian indices, final depth order lands here
     uint32_t* order_b;       // [P]
     uint32_t* offsets;       // [P]  exclusive scan of tiles_touched in depth order
-    uint32_t* rs_hist;       // [rs_hist_words(P)]
-    uint32_t* scan_scratch;  // [scan_scratch_words(max(P, rs_hist_words(P)))]
+    uint32_t* sort_ws;       // [onesweep_workspace_words(P, 4)]  depth sort workspace
+    uint32_t* scan_ws;       // [scan_lookback_workspace_words(P)]
     uint32_t* totals;        // [4]  {num_rendered, num_visible, ...}
     float4* grad_rec;        // [3P] backward accumulators (see raster_backward.cu)
 
@@ -118,9 +122,8 @@ struct GeomState {
         g.order_a = c.take<uint32_t>(P);
         g.order_b = c.take<uint32_t>(P);
         g.offsets = c.take<uint32_t>(P);
-        g.rs_hist = c.take<uint32_t>(rs_hist_words(P));
-        size_t m = rs_hist_words(P) > P ? rs_hist_words(P) : P;
-        g.scan_scratch = c.take<uint32_t>(scan_scratch_words(m));
+        g.sort_ws = c.take<uint32_t>(onesweep_workspace_words(P, 4));
+        g.scan_ws = c.take<uint32_t>(scan_lookback_workspace_words(P) + scan_scratch_words(P));
         g.totals = c.take<uint32_t>(32);
         g.grad_rec = c.take<float4>(3 * P);
         if (bytes) *bytes = c.bytes();
@@ -150,8 +153,7 @@ struct BinningState {
     uint32_t* vals_a;  // [R] Gaussian ids; after the sort: the point list
     uint32_t* keys_b;  // [R]
     uint32_t* vals_b;  // [R]
-    uint32_t* rs_hist;       // [rs_hist_words(R)]
-    uint32_t* scan_scratch;  // [scan_scratch_words(rs_hist_words(R))]
+    uint32_t* sort_ws;       // [onesweep_workspace_words(R, TILE_SORT_MAX_PASSES)]
     static BinningState carve(void* chunk, size_t R, size_t* bytes) {
         Carver c(chunk);
         BinningState b;
@@ -159,8 +161,7 @@ struct BinningState {
         b.vals_a = c.take<uint32_t>(R);
         b.keys_b = c.take<uint32_t>(R);
         b.vals_b = c.take<uint32_t>(R);
-        b.rs_hist = c.take<uint32_t>(rs_hist_words(R));
-        b.scan_scratch = c.take<uint32_t>(scan_scratch_words(rs_hist_words(R)));
+        b.sort_ws = c.take<uint32_t>(onesweep_workspace_words(R, TILE_SORT_MAX_PASSES));
         if (bytes) *bytes = c.bytes();
         return b;
     }
@@ -182,6 +183,22 @@ int scan_exclusive_u32(const uint32_t* in, const uint32_t* perm, uint32_t* out, 
 int radix_pass_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                    uint32_t* vals_out, size_t n, int shift, int bits, uint32_t* hist,
                    uint32_t* scan_scratch, cudaStream_t s, bool debug);
+
+// Single-pass (decoupled look-back) variants — see scan_sort.cu.  The workspace `ws` of
+// onesweep_workspace_words(n, passes) words is zeroed by onesweep_prepare() once per sort;
+// onesweep_hist() fills the per-pass global digit histograms from the keys (or the caller fills
+// onesweep_digit_hist(...) itself), then onesweep_pass() is called once per pass.
+size_t onesweep_workspace_words(size_t n, int passes);
+int onesweep_prepare(uint32_t* ws, size_t n, int passes, cudaStream_t s);
+int onesweep_hist(const uint32_t* keys, size_t n, int passes, const int* shifts, const int* bits,
+                  uint32_t* ws, cudaStream_t s, bool debug);
+int onesweep_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                  size_t n, int shift, int bits, uint32_t* ws, int passes, int pass, cudaStream_t s, bool debug);
+uint32_t* onesweep_digit_hist(uint32_t* ws, size_t n, int passes, int pass);
+uint32_t* onesweep_error_word(uint32_t* ws, size_t n, int passes);
+size_t scan_lookback_workspace_words(size_t n);
+int scan_exclusive_lookback_u32(const uint32_t* in, const uint32_t* perm, uint32_t* out, size_t n,
+                                uint32_t* ws, uint32_t* total, cudaStream_t s, bool debug);
 
 // ---- small device helpers -------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {

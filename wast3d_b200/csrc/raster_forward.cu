@@ -20,6 +20,7 @@
 //    only visits survivors; warps retire independently (ballot) and the block leaves when all
 //    have (one __syncthreads_and per batch).
 #include "raster_math.cuh"
+#include <cstdlib>
 
 namespace w3d {
 
@@ -339,6 +340,22 @@ tile_ranges_from_counts_kernel(int num_tiles, const uint32_t* __restrict__ tile_
     }
 }
 
+// Global digit histograms of the tile-id radix passes from the per-tile instance counts.
+__global__ void __launch_bounds__(256)
+tile_digit_hist_kernel(int num_tiles, const uint32_t* __restrict__ tile_count, int passes, int bpp,
+                       uint32_t* __restrict__ digit_hist /*[passes][RS_RADIX]*/) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= num_tiles) return;
+    const uint32_t c = tile_count[t];
+    if (c == 0) return;
+    const uint32_t mask = (1u << bpp) - 1u;
+    for (int p = 0; p < passes; ++p) atomicAdd(digit_hist + p * RS_RADIX + (((uint32_t)t >> (p * bpp)) & mask), c);
+}
+
+__global__ void tile_copy_flags_kernel(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+    if (threadIdx.x == 0) *out = (a ? *a : 0u) | (b ? *b : 0u);
+}
+
 // ------------------------------------------------------------------ K6 -------------------
 constexpr int RENDER_BATCH = 256;
 
@@ -480,6 +497,18 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 }
 
 // ------------------------------------------------------------------ host -----------------
+// Which flavour of the sort / scan primitives each binning stage uses: 0 = multi-kernel (histogram,
+// table scan, scatter), 1 = single-kernel passes with decoupled look-back.  Measured on B200
+// (profiles/r01_sort_modes.md): the depth sort of P keys is launch-bound and wins with look-back
+// (5 launches instead of 20), the tile partition of R pairs and the offsets scan are a few percent
+// faster multi-kernel.  WAST3D_SORT_MODE=0|1 forces one flavour everywhere (experiments, tests).
+enum SortStage { STAGE_DEPTH = 0, STAGE_SCAN = 1, STAGE_TILE = 2 };
+static int sort_mode(SortStage stage) {
+    static const int forced = getenv("WAST3D_SORT_MODE") ? atoi(getenv("WAST3D_SORT_MODE")) : -1;
+    if (forced == 0 || forced == 1) return forced;
+    return stage == STAGE_DEPTH ? 1 : 0;
+}
+
 static int tile_sort_passes(uint32_t num_tiles, int* bits_per_pass) {
     const int bits = bits_for(num_tiles);
     const int passes = (bits + 7) / 8;
@@ -565,29 +594,54 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
     W3D_AFTER_LAUNCH(s, debug);
     }
 
-    // depth order: 4 stable 8-bit passes on the float bits (positive floats order like uints)
+    // depth order: 4 stable 8-bit passes on the float bits (positive floats order like uints),
+    // each ONE look-back kernel; the four global digit histograms come from one read of the keys
     {
     ProfScope ps(PS_DEPTH_SORT, s);
-    st = radix_pass_u32(g.depth_key, nullptr, g.key_tmp, g.order_b, P, 0, 8, g.rs_hist, g.scan_scratch, s, debug);
-    if (st) return st;
-    st = radix_pass_u32(g.key_tmp, g.order_b, g.depth_key, g.order_a, P, 8, 8, g.rs_hist, g.scan_scratch, s, debug);
-    if (st) return st;
-    st = radix_pass_u32(g.depth_key, g.order_a, g.key_tmp, g.order_b, P, 16, 8, g.rs_hist, g.scan_scratch, s, debug);
-    if (st) return st;
-    st = radix_pass_u32(g.key_tmp, g.order_b, nullptr, g.order_a, P, 24, 8, g.rs_hist, g.scan_scratch, s, debug);
-    if (st) return st;
+    const int shifts[4] = {0, 8, 16, 24}, bits[4] = {8, 8, 8, 8};
+    uint32_t* const kin[4] = {g.depth_key, g.key_tmp, g.depth_key, g.key_tmp};
+    uint32_t* const kout[4] = {g.key_tmp, g.depth_key, g.key_tmp, nullptr};
+    uint32_t* const vin[4] = {nullptr, g.order_b, g.order_a, g.order_b};
+    uint32_t* const vout[4] = {g.order_b, g.order_a, g.order_b, g.order_a};
+    if (sort_mode(STAGE_DEPTH) == 1) {
+        st = onesweep_prepare(g.sort_ws, P, 4, s);
+        if (st) return st;
+        st = onesweep_hist(g.depth_key, P, 4, shifts, bits, g.sort_ws, s, debug);
+        if (st) return st;
+    }
+    for (int p = 0; p < 4; ++p) {
+        if (sort_mode(STAGE_DEPTH) == 1)
+            st = onesweep_pass(kin[p], vin[p], kout[p], vout[p], P, shifts[p], bits[p], g.sort_ws, 4, p, s, debug);
+        else
+            st = radix_pass_u32(kin[p], vin[p], kout[p], vout[p], P, shifts[p], bits[p], g.sort_ws,
+                                g.sort_ws + rs_hist_words(P), s, debug);
+        if (st) return st;
+    }
     }
     {
     ProfScope ps(PS_SCAN, s);
-    st = scan_exclusive_u32(g.tiles_touched, g.order_a, g.offsets, P, g.scan_scratch, g.totals, s, debug);
+    if (sort_mode(STAGE_SCAN) == 1)
+        st = scan_exclusive_lookback_u32(g.tiles_touched, g.order_a, g.offsets, P, g.scan_ws, g.totals, s, debug);
+    else
+        st = scan_exclusive_u32(g.tiles_touched, g.order_a, g.offsets, P, g.scan_ws, g.totals, s, debug);
     if (st) return st;
+    // look-back time-outs (never expected) of the depth sort and the scan, read with num_rendered
+    if (sort_mode(STAGE_DEPTH) == 1 || sort_mode(STAGE_SCAN) == 1) {
+        tile_copy_flags_kernel<<<1, 32, 0, s>>>(sort_mode(STAGE_DEPTH) == 1 ? onesweep_error_word(g.sort_ws, P, 4) : nullptr,
+                                               sort_mode(STAGE_SCAN) == 1 ? g.scan_ws + 1 : nullptr, g.totals + 2);
+        W3D_AFTER_LAUNCH(s, debug);
+    }
     }
 
     // the one blocking read the reference also has (rasterizer_impl.cu:283)
-    uint32_t host_totals[2] = {0, 0};
+    uint32_t host_totals[3] = {0, 0, 0};
     W3D_CUDA_TRY(cudaMemcpyAsync(host_totals, g.totals, sizeof(host_totals), cudaMemcpyDeviceToHost, s));
     W3D_CUDA_TRY(cudaStreamSynchronize(s));
     if (host_totals[1] & 1u) return WAST3D_ERR_INVALID_ARGUMENT;  // prefiltered violated
+    if (host_totals[2]) {
+        set_last_cuda_error(cudaErrorLaunchTimeout, __FILE__, __LINE__);
+        return WAST3D_ERR_CUDA;
+    }
     if (host_totals[0] > 0x7FFFFFFFu) return WAST3D_ERR_OVERFLOW;
     const uint32_t R = host_totals[0];
     *num_rendered_host = (int)R;
@@ -621,11 +675,24 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         ProfScope* pts = new ProfScope(PS_TILE_SORT, s);
         int bpp;
         const int passes = tile_sort_passes(num_tiles, &bpp);
+        if (passes > TILE_SORT_MAX_PASSES) { delete pts; return WAST3D_ERR_OVERFLOW; }
+        if (sort_mode(STAGE_TILE) == 1) {
+            st = onesweep_prepare(bn.sort_ws, R, passes, s);
+            if (st) { delete pts; return st; }
+            // the per-pass global digit histograms follow from the per-tile counts: no read of the keys
+            tile_digit_hist_kernel<<<(num_tiles + 255) / 256, 256, 0, s>>>(
+                (int)num_tiles, im.tile_count, passes, bpp, onesweep_digit_hist(bn.sort_ws, R, passes, 0));
+            W3D_AFTER_LAUNCH(s, debug);
+        }
         uint32_t *kin = bn.keys_a, *vin = bn.vals_a, *kout = bn.keys_b, *vout = bn.vals_b;
         for (int p = 0; p < passes; ++p) {
             // the last pass does not need to write the sorted tile ids: ranges come from the counts
-            st = radix_pass_u32(kin, vin, p + 1 < passes ? kout : nullptr, vout, R, p * bpp, bpp, bn.rs_hist,
-                                bn.scan_scratch, s, debug);
+            if (sort_mode(STAGE_TILE) == 1)
+                st = onesweep_pass(kin, vin, p + 1 < passes ? kout : nullptr, vout, R, p * bpp, bpp, bn.sort_ws,
+                                   passes, p, s, debug);
+            else
+                st = radix_pass_u32(kin, vin, p + 1 < passes ? kout : nullptr, vout, R, p * bpp, bpp, bn.sort_ws,
+                                    bn.sort_ws + rs_hist_words(R), s, debug);
             if (st) { delete pts; return st; }
             uint32_t* t;
             t = kin; kin = kout; kout = t;
