@@ -165,6 +165,23 @@ int wast3d_cluster_stats(int n, int K, const float* points, const int32_t* label
 int wast3d_nn_match(int Na, int Nb, const float* a, const float* b, int32_t* out_idx,
                     float* out_dist, void* stream);
 
+/* wast3d_cdist_topk: the k smallest entries of every row of torch.cdist(a, b) ([Na,3] x [Nb,3])
+ * without materialising the matrix: out_dist [Na,k] ascending, out_idx [Na,k] int32, rows ordered by
+ * (distance, index) like a stable sort.  Replaces `torch.sort(torch.cdist(x, y), 1)[:, :k]` /
+ * `torch.topk(torch.cdist(x, x), k, largest=False)` and, through out_dist[:, k-1], the kNN mask
+ * `D <= sorted[:, k-1:k]` (aux_optimize_cluster_D_W_distance.py:73-82, ...distance2.py:269-273,
+ * notebooks/25.4.Optimize_with_SAM_masks_clean.ipynb cell 73).  1 <= k <= min(128, Nb). */
+int wast3d_cdist_topk(int Na, int Nb, const float* a, const float* b, int k, float* out_dist,
+                      int32_t* out_idx, void* stream);
+
+/* wast3d_emd2_uniform: exact optimal-transport cost between two samples xa, xb ([n,3] each) with
+ * uniform weights 1/n and POT's default squared-Euclidean ground cost, i.e. what
+ * `ot.emd2(w, w, ot.dist(xa, xb))` returns (aux_optimize_cluster_D_W_distance.py:260-270; POT is an
+ * un-vendored dependency).  With equal uniform weights the optimal plan is a permutation; out_perm[i]
+ * (optional) is the column matched to row i, the plan is P/n.  1 <= n <= 1023. */
+int wast3d_emd2_uniform(int n, const float* xa, const float* xb, float* out_cost, int32_t* out_perm,
+                        void* stream);
+
 /* wast3d_w2_match: content clusters (mean_c [Kc,3], cov_c [Kc,6]) against style clusters
  * (mean_s [Ks,3], cov_s [Ks,6]): out_idx[i] = argmin_j W2^2(N(mc_i,Sc_i), N(ms_j,Ss_j)),
  *   W2^2 = |m1-m2|^2 + tr(S1) + tr(S2) - 2 tr((S1^1/2 S2 S1^1/2)^1/2)      

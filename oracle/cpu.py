@@ -201,6 +201,25 @@ def nn_match(a, b):
     return idx, dist
 
 
+def cdist_topk(a, b, k):
+    a, b = _f32(a), _f32(b)
+    dist = np.zeros((a.shape[0], k), np.float32)
+    idx = np.zeros((a.shape[0], k), np.int32)
+    lib().oracle_cdist_topk(a.shape[0], b.shape[0], _p(a), _p(b), int(k), _p(dist), _p(idx))
+    return dist, idx
+
+
+def emd2_uniform(xa, xb, want_matrix=False):
+    xa, xb = _f32(xa), _f32(xb)
+    n = xa.shape[0]
+    perm = np.zeros(n, np.int32)
+    M = np.zeros((n, n), np.float32) if want_matrix else None
+    f = lib().oracle_emd2_uniform
+    f.restype = C.c_float
+    cost = float(f(n, _p(xa), _p(xb), _p(perm), _p(M)))
+    return (cost, perm, M) if want_matrix else (cost, perm)
+
+
 def w2_match(mean_c, cov_c, mean_s, cov_s, want_matrix=False):
     mean_c, cov_c, mean_s, cov_s = _f32(mean_c), _f32(cov_c), _f32(mean_s), _f32(cov_s)
     Kc, Ks = mean_c.shape[0], mean_s.shape[0]

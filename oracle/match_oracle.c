@@ -73,6 +73,101 @@ void oracle_nn_match(int Na, int Nb, const float* a, const float* b, int32_t* ou
     }
 }
 
+/* ---- M2: k smallest per row of cdist, ordered by (distance, index) == stable sort of the row
+ * (torch.sort / torch.topk call sites: aux_optimize_cluster_D_W_distance.py:79-82,
+ * aux_optimize_cluster_D_W_distance2.py:269-273, notebooks/25.4 cell 73).  PINNED against
+ * torch.sort(torch.cdist(...), stable=True) on the squared-distance values in tests/test_match_oracle.py
+ * (same 1-ulp sqrt caveat as oracle_nn_match). */
+void oracle_cdist_topk(int Na, int Nb, const float* a, const float* b, int k, float* out_dist, int32_t* out_idx) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int i = 0; i < Na; ++i) {
+        float* bd = out_dist + (size_t)i * k;
+        int32_t* bi = out_idx + (size_t)i * k;
+        int filled = 0;
+        for (int j = 0; j < Nb; ++j) {
+            const float d = sqrtf(oracle_cdist_sq(a + 3 * i, b + 3 * j));
+            if (filled == k && !(d < bd[k - 1])) continue; /* later index never displaces an equal distance */
+            int pos = filled < k ? filled : k - 1;
+            while (pos > 0 && d < bd[pos - 1]) {
+                bd[pos] = bd[pos - 1];
+                bi[pos] = bi[pos - 1];
+                --pos;
+            }
+            bd[pos] = d;
+            bi[pos] = j;
+            if (filled < k) ++filled;
+        }
+    }
+}
+
+/* ---- M4: ot.emd2 with uniform weights (aux_optimize_cluster_D_W_distance.py:260-270) ------------
+ * POT (`import ot`) is an un-vendored, un-pinned dependency of the reference and is not installed
+ * here, so PARITY IS UNPINNED against POT itself.  Restated from its published definition:
+ * emd2(a, b, M) = min_{G >= 0, G 1 = a, G^T 1 = b} <G, M>, M = ot.dist(xa, xb) = squared Euclidean
+ * (a2 + b2 - 2 a.b^T clamped at 0, ot/utils.py euclidean_distances).  For a = b = 1/n the vertices of
+ * the feasible polytope are permutation matrices / n, so the optimum is a linear assignment:
+ * solved by the Jonker-Volgenant shortest augmenting path method in double precision.  The optimal
+ * VALUE is unique; tests cross-check it against scipy.optimize.linear_sum_assignment. */
+static void emd_cost_matrix(int n, const float* xa, const float* xb, float* M) {
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) {
+            const float* a = xa + 3 * i;
+            const float* b = xb + 3 * j;
+            const float a2 = (a[0] * a[0] + a[1] * a[1]) + a[2] * a[2];
+            const float b2 = (b[0] * b[0] + b[1] * b[1]) + b[2] * b[2];
+            const float dot = (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2];
+            float c = -2.f * dot;
+            c = c + a2;
+            c = c + b2;
+            M[(size_t)i * n + j] = fmaxf(c, 0.f);
+        }
+}
+
+float oracle_emd2_uniform(int n, const float* xa, const float* xb, int32_t* perm, float* M_out) {
+    float* M = (float*)malloc(sizeof(float) * (size_t)n * n);
+    emd_cost_matrix(n, xa, xb, M);
+    double* u = (double*)calloc((size_t)n + 1, sizeof(double));
+    double* v = (double*)calloc((size_t)n + 1, sizeof(double));
+    double* minv = (double*)malloc(sizeof(double) * ((size_t)n + 1));
+    int* p = (int*)calloc((size_t)n + 1, sizeof(int));
+    int* way = (int*)calloc((size_t)n + 1, sizeof(int));
+    char* used = (char*)malloc((size_t)n + 1);
+    for (int i = 1; i <= n; ++i) {
+        p[0] = i;
+        int j0 = 0;
+        for (int j = 0; j <= n; ++j) { minv[j] = DBL_MAX; used[j] = 0; }
+        do {
+            used[j0] = 1;
+            const int i0 = p[j0];
+            double delta = DBL_MAX;
+            int j1 = 0;
+            for (int j = 1; j <= n; ++j)
+                if (!used[j]) {
+                    const double cur = (double)M[(size_t)(i0 - 1) * n + (j - 1)] - u[i0] - v[j];
+                    if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
+                    if (minv[j] < delta) { delta = minv[j]; j1 = j; }
+                }
+            for (int j = 0; j <= n; ++j)
+                if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
+                else minv[j] -= delta;
+            j0 = j1;
+        } while (p[j0] != 0);
+        do {
+            const int j1 = way[j0];
+            p[j0] = p[j1];
+            j0 = j1;
+        } while (j0);
+    }
+    double tot = 0.0;
+    for (int j = 1; j <= n; ++j) {
+        tot += (double)M[(size_t)(p[j] - 1) * n + (j - 1)];
+        if (perm) perm[p[j] - 1] = j - 1;
+    }
+    if (M_out) memcpy(M_out, M, sizeof(float) * (size_t)n * n);
+    free(M); free(u); free(v); free(minv); free(p); free(way); free(used);
+    return (float)(tot / (double)n);
+}
+
 /* ---- M5: closed-form Gaussian W2^2, fixed fp32 operation order --------------------------
  * cov6 = (xx, xy, xz, yy, yz, zz).  Per cluster "descriptor" (derived once):
  *   tr = (xx + yy) + zz

@@ -109,6 +109,93 @@ def test_nn_match_equals_oracle_and_torch(built, Na, Nb):
     assert mism <= max(2, Na // 10000)  # only cuBLAS/sqrt rounding near-ties may differ
 
 
+@pytest.mark.parametrize("Na,Nb,k,kind", [(1, 1, 1, "rand"), (7, 300, 10, "rand"), (33, 128, 128, "rand"),
+                                            (500, 2000, 50, "ties"), (4893, 4893, 10, "self"),
+                                            (4893, 4893, 100, "self"), (50000, 10000, 20, "rand")])
+def test_cdist_topk_equals_oracle(built, Na, Nb, k, kind):
+    """M2: fused cdist + k smallest per row, bit-exact (indices and distances) against the oracle."""
+    from oracle import cpu
+    from wast3d_b200 import matching
+    rng = np.random.default_rng(Na + Nb + k)
+    b = rng.normal(size=(Nb, 3)).astype(np.float32)
+    a = b.copy() if kind == "self" else rng.normal(size=(Na, 3)).astype(np.float32)
+    if kind == "ties":
+        b[::3] = b[1::3][: b[::3].shape[0]]      # many exactly equal distances
+        b = np.round(b * 4) / 4                  # and a coarse lattice
+    T = lambda x: torch.from_numpy(x).cuda()
+    vals, idx = matching.cdist_topk(T(a), T(b), k)
+    rows = np.arange(Na) if Na <= 5000 else rng.choice(Na, 3000, replace=False)
+    od, oi = cpu.cdist_topk(a[rows], b, k)
+    assert (idx.cpu().numpy()[rows] == oi).all()
+    assert (vals.cpu().numpy()[rows] == od).all()
+    assert (vals[:, 1:] >= vals[:, :-1]).all()
+    if kind == "self":  # every point is (one of) its own nearest neighbours, at distance ~0: the
+        # matmul-path formula |a|^2 + |b|^2 - 2 a.b cancels to a few ulp of |a|^2, not to exactly 0
+        assert (vals[:, 0] <= 4e-3).all()
+    thr, idx2 = matching.knn_mask_threshold(T(a), T(b), k)
+    assert torch.equal(thr, vals[:, k - 1]) and torch.equal(idx2, idx)
+    if Na * Nb <= 30_000_000:  # the reference's dense mask (aux_optimize_cluster_D_W_distance.py:79-82)
+        # evaluated with torch on the CPU, whose cdist the oracle's operation order is pinned to
+        D = torch.cdist(torch.from_numpy(a), torch.from_numpy(b))
+        srt = torch.sort(D, dim=1).values
+        ref_mask = D <= srt[:, k - 1:k]
+        our_mask = D <= thr.cpu()[:, None]
+        # torch's vectorised CPU sqrt can be 1 ulp off the IEEE sqrt (oracle header): compare the
+        # rows whose k-th distance is separated from its neighbours by more than that
+        kth = srt[:, k - 1]
+        sep = 4e-7 * kth.clamp_min(1e-12)
+        gap = (srt[:, min(k, Nb - 1)] - kth > sep) if k < Nb else torch.ones_like(kth, dtype=torch.bool)
+        if k > 1:
+            gap &= (kth - srt[:, k - 2]) > sep
+        if gap.any():
+            assert torch.equal(ref_mask[gap], our_mask[gap])
+        assert gap.float().mean().item() > 0.5 or kind == "ties"
+
+
+def test_cdist_topk_rejects_bad_k(built):
+    from wast3d_b200 import matching
+    a = torch.zeros(4, 3, device="cuda")
+    with pytest.raises(RuntimeError):
+        matching.cdist_topk(a, a, 5)      # k > Nb, torch.topk raises too
+    with pytest.raises(RuntimeError):
+        matching.cdist_topk(a, a, 0)
+    v, i = matching.cdist_topk(torch.zeros(0, 3, device="cuda"), a, 2)
+    assert v.shape == (0, 2) and i.shape == (0, 2)
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (31, 2), (100, 3), (100, 4), (333, 5), (1023, 6)])
+def test_emd2_uniform_equals_oracle(built, n, seed):
+    """M4: exact OT cost for uniform weights (ot.emd2 call site aux_optimize_cluster_D_W_distance.py:260-270)."""
+    from oracle import cpu
+    from wast3d_b200 import matching
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(n, 3)).astype(np.float32)
+    b = (rng.normal(size=(n, 3)) * 1.5 + 0.3).astype(np.float32)
+    if n > 2:
+        b[1] = b[0]
+    oc, operm = cpu.emd2_uniform(a, b)
+    ta = torch.from_numpy(a).cuda().requires_grad_(True)
+    tb = torch.from_numpy(b).cuda().requires_grad_(True)
+    cost, perm = matching.emd2_uniform(ta, tb, return_plan=True)
+    assert cost.item() == np.float32(oc)                       # same operations in the same order
+    assert (perm.cpu().numpy() == operm).all()
+    # gradient through the optimal plan == autograd of the cost evaluated on the fixed permutation
+    (3.0 * cost).backward()
+    ra = torch.from_numpy(a).cuda().requires_grad_(True)
+    rb = torch.from_numpy(b).cuda().requires_grad_(True)
+    (3.0 * ((ra - rb[perm]) ** 2).sum() / n).backward()
+    assert torch.allclose(ta.grad, ra.grad, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(tb.grad, rb.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_emd2_uniform_rejects_bad_input(built):
+    from wast3d_b200 import matching
+    with pytest.raises(RuntimeError):
+        matching.emd2_uniform(torch.zeros(4, 3, device="cuda"), torch.zeros(5, 3, device="cuda"))
+    with pytest.raises(RuntimeError):
+        matching.emd2_uniform(torch.zeros(2000, 3, device="cuda"), torch.zeros(2000, 3, device="cuda"))
+
+
 def test_cluster_stats_and_c1_pipeline(built):
     """BASELINE.json configs[0]: 50k content + 10k style points, 512 clusters each."""
     from oracle import cpu

@@ -119,3 +119,55 @@ def test_knn_oracle_small_cases(built):
     pts = np.array([[0, 0, 0], [1, 0, 0], [0, 2, 0], [0, 0, 3], [0, 0, 0]], np.float32)
     d, idx = cpu.knn(pts)
     assert d[0] == np.float32((0 + 1 + 4) / 3.0) and idx[0].tolist() == [4, 1, 2]
+
+
+@pytest.mark.parametrize("n,m,k,seed", [(50, 50, 10, 0), (300, 1000, 20, 1), (64, 4893, 100, 2), (10, 128, 128, 3)])
+def test_cdist_topk_equals_torch_stable_sort(built, n, m, k, seed):
+    """M2 oracle pinned on torch: k smallest of torch.cdist rows in stable-sort order
+    (aux_optimize_cluster_D_W_distance.py:79-82 uses sort, notebooks/25.4 cell 73 uses topk)."""
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(n, 3)).astype(np.float32)
+    b = rng.normal(size=(m, 3)).astype(np.float32)
+    b[m // 2] = b[m // 3]  # an exact tie in every row
+    d, i = cpu.cdist_topk(a, b, k)
+    D = torch.cdist(torch.from_numpy(a), torch.from_numpy(b))
+    v, ix = torch.sort(D, dim=1, stable=True)
+    # torch's vectorised CPU sqrt is not correctly rounded (see oracle header): compare indices on
+    # rows whose k+1 smallest squared distances are well separated, values to 1 ulp everywhere
+    np.testing.assert_allclose(d, v[:, :k].numpy(), rtol=2e-7, atol=0)
+    same = (i == ix[:, :k].numpy()).all(axis=1)
+    assert same.mean() > 0.95
+    for r in np.nonzero(~same)[0]:  # any disagreement must be between distances equal to 1 ulp
+        bad = i[r] != ix[r, :k].numpy()
+        assert np.abs(d[r][bad] - v[r, :k].numpy()[bad]).max() <= 2e-7 * d[r][bad].max()
+    # the reference's mask D <= kth value == membership in our top-k, plus ties at the k-th value
+    mask = (D <= v[:, k - 1:k]).numpy()
+    ours = np.zeros_like(mask)
+    np.put_along_axis(ours, i.astype(np.int64), True, axis=1)
+    assert (mask | ours == mask).all() and (mask.sum(1) >= k).all()
+
+
+@pytest.mark.parametrize("n,seed", [(1, 0), (2, 1), (7, 2), (100, 3), (100, 4), (300, 5)])
+def test_emd2_uniform_oracle_is_optimal(built, n, seed):
+    """M4: the restated ot.emd2 (uniform weights => assignment problem) against an independent exact
+    solver (scipy.optimize.linear_sum_assignment) on the same ground-cost matrix, and against brute
+    force for tiny n.  POT itself is not available: parity unpinned, optimality is what is checked."""
+    from itertools import permutations
+    from scipy.optimize import linear_sum_assignment
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(n, 3)).astype(np.float32)
+    b = (rng.normal(size=(n, 3)) * 1.5 + 0.3).astype(np.float32)
+    if n >= 7:
+        b[1] = b[0]  # duplicate target points: several optimal plans, one optimal value
+    cost, perm, M = cpu.emd2_uniform(a, b, want_matrix=True)
+    assert sorted(perm.tolist()) == list(range(n))
+    # ground cost == squared Euclidean distances (ot.dist default metric)
+    D2 = ((a[:, None, :].astype(np.float64) - b[None, :, :]) ** 2).sum(-1)
+    np.testing.assert_allclose(M, D2, rtol=1e-5, atol=1e-5)
+    r, c = linear_sum_assignment(M.astype(np.float64))
+    ref = M.astype(np.float64)[r, c].sum() / n
+    assert abs(cost - ref) <= 1e-6 * max(ref, 1e-12)
+    assert abs(M.astype(np.float64)[np.arange(n), perm].sum() / n - ref) <= 1e-9 * max(ref, 1e-12)
+    if n <= 7:
+        best = min(sum(M[i, s[i]] for i in range(n)) for s in permutations(range(n))) / n
+        assert abs(cost - best) <= 1e-6 * max(best, 1e-12)

@@ -52,6 +52,8 @@ SIGNATURES = {
     "wast3d_knn_dist2": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wast3d_cluster_stats": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_nn_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_cdist_topk": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "wast3d_emd2_uniform": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_w2_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_w2_match_debug": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_test_sort_pairs": (_i, [_sz, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

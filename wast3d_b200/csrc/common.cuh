@@ -205,11 +205,36 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gmem_src));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
+// ---- mbarrier helpers (shared::cta) ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbarrier_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// The executing thread's arrival on `bar` is triggered when all of ITS prior cp.async copies have
+// landed; .noinc: the arrival was accounted for in the barrier's initial count.
+__device__ __forceinline__ void cp_async_mbarrier_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));

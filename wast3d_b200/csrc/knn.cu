@@ -224,8 +224,11 @@ knn_query_kernel(int P, const float4* __restrict__ sorted, const uint32_t* __res
                     for (uint32_t t = s; t < e; ++t) {
                         const float4 p = sorted[t];
                         const uint32_t pid = __float_as_uint(p.w);
-                        if (pid == self) continue;
-                        best3_insert(b, knn_dist2(p.x, p.y, p.z, q.x, q.y, q.z), pid);
+                        const float dist = knn_dist2(p.x, p.y, p.z, q.x, q.y, q.z);
+                        // cheap reject: strictly farther than the current third best can never enter
+                        // (equal distances still go through the index tie-break)
+                        if (dist > b.d[2] || pid == self) continue;
+                        best3_insert(b, dist, pid);
                     }
                 }
             }

@@ -190,6 +190,10 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                     hit = pos < warp_max_last &&
                           !((a.x + a.w < bx0) || (a.x - a.w > bx1) || (a.y + hy < by0) ||
                             (a.y - hy > by1));
+                    if (hit) {  // the box overlaps: decide exactly on the ellipse
+                        const float4 co = r1[jj];
+                        hit = !ellipse_misses_rect(a.x, a.y, co.x, co.y, co.z, co.w, bx0, bx1, by0, by1);
+                    }
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
                 while (m) {
@@ -391,6 +395,10 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
                     hit = pos < warp_max_last &&
                           !((a.x + a.w < bx0) || (a.x - a.w > bx1) || (a.y + hy < by0) ||
                             (a.y - hy > by1));
+                    if (hit) {  // the box overlaps: decide exactly on the ellipse
+                        const float4 co = r1[jj];
+                        hit = !ellipse_misses_rect(a.x, a.y, co.x, co.y, co.z, co.w, bx0, bx1, by0, by1);
+                    }
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
                 while (m) {

@@ -166,6 +166,37 @@ __device__ __forceinline__ float3 cov2d(const float3& mean, float focal_x, float
     return make_float3(cov.c[0][0] + 0.3f, cov.c[0][1], cov.c[1][1] + 0.3f);
 }
 
+// ---- exact (warp pixel block, Gaussian) culling ------------------------------------------------
+// A pixel receives a contribution only if alpha = o * exp(-q(d)) >= 1/255, q(d) = 0.5 (A dx^2 + C dy^2)
+// + B dx dy (forward.cu:343-356), i.e. only if q(d) <= ln(255 o).  q is convex, so its minimum over
+// the warp's sample rectangle [bx0,bx1] x [by0,by1] is 0 if the centre lies inside and otherwise
+// sits on one of the four edges, where it is a clamped 1-D quadratic minimum.  Returns true when
+// that minimum exceeds the (padded, see cutoff_extent) threshold: no pixel of the block can pass the
+// reference's per-pixel test, so the pair is skipped exactly.  Conservative on any doubt (NaN,
+// non-positive-definite conic): returns false.
+__device__ __forceinline__ float edge_min_q(float e, float lo, float hi, float Pe, float Po, float B) {
+    // min over t in [lo, hi] of 0.5 Pe e^2 + B e t + 0.5 Po t^2   (Po > 0)
+    const float t = fminf(fmaxf(__fdividef(-B * e, Po), lo), hi);
+    return 0.5f * Pe * e * e + t * (B * e + 0.5f * Po * t);
+}
+__device__ __forceinline__ bool ellipse_misses_rect(float cx, float cy, float A, float B, float C, float o,
+                                                    float bx0, float bx1, float by0, float by1) {
+    if (!(A > 0.f) || !(C > 0.f)) return false;
+    const float det = A * C - B * B;
+    if (!(det > 0.f)) return false;
+    const float lx = bx0 - cx, hx = bx1 - cx, ly = by0 - cy, hy = by1 - cy;
+    if (lx <= 0.f && hx >= 0.f && ly <= 0.f && hy >= 0.f) return false;  // centre inside
+    float m = edge_min_q(lx, ly, hy, A, C, B);
+    m = fminf(m, edge_min_q(hx, ly, hy, A, C, B));
+    m = fminf(m, edge_min_q(ly, lx, hx, C, A, B));
+    m = fminf(m, edge_min_q(hy, lx, hx, C, A, B));
+    const float tau0 = __logf(255.0f * o);
+    const float kappa = __fdividef(A * C, det);
+    // padding: fp32 error of q (grows with the conditioning kappa), of __logf / __fdividef, and of m
+    const float tau = tau0 + 2e-3f + fabsf(tau0) * (2e-3f + 8e-6f * kappa);
+    return m * (1.0f - 1e-3f) - 1e-3f > tau;   // NaN -> false
+}
+
 // ---- per-warp SH staging -----------------------------------------------------------------
 // A warp owns 32 consecutive Gaussians; their SH blocks are contiguous in memory
 // (32 * M*3 floats).  Lanes stream that range with coalesced 16-byte (or 4-byte) loads into

@@ -62,6 +62,81 @@ def nn_match(a: torch.Tensor, b: torch.Tensor):
     return idx.long(), dist
 
 
+def cdist_topk(a: torch.Tensor, b: torch.Tensor, k: int):
+    """(values [Na,k], indices [Na,k] int64) = the k smallest entries of each row of torch.cdist(a, b),
+    ascending, equal distances ordered by index (what `torch.sort(D, 1, stable=True)` gives) — the
+    N x M matrix is never written.  Call sites in the reference: the kNN masks
+    `D <= torch.sort(D, 1)[0][:, k-1:k]` (aux_optimize_cluster_D_W_distance.py:79-82) and the
+    descriptor neighbourhoods `torch.topk(cdist, k, largest=False)` (notebooks/25.4 cell 73)."""
+    _check3(a, "a", 3)
+    _check3(b, "b", 3)
+    _lib.require_device(a)
+    lib = _lib.load()
+    Na, Nb, k = int(a.size(0)), int(b.size(0)), int(k)
+    if k < 1 or k > Nb:
+        raise RuntimeError("cdist_topk: selected index k out of range")  # torch.topk's message
+    if k > 128:
+        raise RuntimeError("cdist_topk: k > 128 is not supported")
+    vals = torch.empty((Na, k), dtype=torch.float32, device=a.device)
+    idx = torch.empty((Na, k), dtype=torch.int32, device=a.device)
+    keep: list = []
+    with torch.cuda.device(a.device):
+        st = lib.wast3d_cdist_topk(Na, Nb, _lib.fptr(a, keep), _lib.fptr(b, keep), k,
+                                   vals.data_ptr() if Na else None, idx.data_ptr() if Na else None,
+                                   _lib.stream_ptr())
+    _lib.check(st, "cdist_topk")
+    return vals, idx.long()
+
+
+def knn_mask_threshold(a: torch.Tensor, b: torch.Tensor, k: int):
+    """Per-row threshold t_i with `torch.cdist(a, b)[i] <= t_i` == the reference's kNN mask row
+    (aux_optimize_cluster_D_W_distance.py:79-82), plus the k nearest indices.  The dense mask is
+    `dist_row <= t_i`; ties at the k-th distance are all inside it, as in the reference."""
+    vals, idx = cdist_topk(a, b, k)
+    return vals[:, k - 1].contiguous(), idx
+
+
+class _Emd2Uniform(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xa, xb):
+        lib = _lib.load()
+        n = int(xa.size(0))
+        cost = torch.empty((), dtype=torch.float32, device=xa.device)
+        perm = torch.empty((n,), dtype=torch.int32, device=xa.device)
+        keep: list = []
+        with torch.cuda.device(xa.device):
+            st = lib.wast3d_emd2_uniform(n, _lib.fptr(xa.detach(), keep), _lib.fptr(xb.detach(), keep),
+                                         cost.data_ptr(), perm.data_ptr(), _lib.stream_ptr())
+        _lib.check(st, "emd2_uniform")
+        ctx.save_for_backward(xa, xb, perm)
+        ctx.mark_non_differentiable(perm)
+        return cost, perm
+
+    @staticmethod
+    def backward(ctx, g_cost, _g_perm):
+        # d cost / d M = plan = P_sigma / n (what POT's emd2 back-propagates); M_ij = |a_i - b_j|^2
+        xa, xb, perm = ctx.saved_tensors
+        n = xa.size(0)
+        diff = (xa - xb[perm.long()]) * (2.0 / n) * g_cost
+        gb = torch.zeros_like(xb)
+        gb.index_add_(0, perm.long(), -diff)
+        return diff, gb
+
+
+def emd2_uniform(xa: torch.Tensor, xb: torch.Tensor, return_plan: bool = False):
+    """`ot.emd2(w, w, ot.dist(xa, xb))` for uniform w = 1/n (aux_optimize_cluster_D_W_distance.py:260-270):
+    exact optimal-transport cost between two equally sized samples, differentiable with respect to
+    both point sets through the optimal plan.  `return_plan` also returns the permutation
+    sigma (plan = P_sigma / n)."""
+    _check3(xa, "xa", 3)
+    _check3(xb, "xb", 3)
+    if xa.size(0) != xb.size(0):
+        raise RuntimeError("emd2_uniform: both samples must have the same number of points")
+    _lib.require_device(xa)
+    cost, perm = _Emd2Uniform.apply(xa, xb)
+    return (cost, perm.long()) if return_plan else cost
+
+
 def w2_match(mean_c, cov_c, mean_s, cov_s, return_stats: bool = False, _lb_dump: bool = False):
     """Nearest style cluster per content cluster under squared Gaussian W2.
 
