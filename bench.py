@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--config", default="c3", choices=["c2", "c3", "c5"])
     ap.add_argument("--no-extra", action="store_true", help="skip the kNN / matching side metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync", default="peer", choices=["peer", "nccl"],
+                    help="optimizer step: 'peer' = one fused reduce+Adam+broadcast kernel over NVLink peer memory "
+                         "(peer.PeerShardedAdam), 'nccl' = chunked NCCL all-reduce overlapped with the dense fused Adam")
     return ap.parse_args()
 
 
@@ -207,11 +210,11 @@ def run_reference(args, spec):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(spec, n):
+def workload_config(spec, n, sync="peer"):
     return {"workload": f"{spec.name}: synthetic garden-scale scene, {spec.P} Gaussians, {spec.width}x{spec.height}, "
                         f"SH degree 3, render fwd (colour+depth) + loss + bwd + Adam",
             "gaussians": spec.P, "width": spec.width, "height": spec.height, "views_per_step": n,
-            "parallelism": f"view-parallel x{n}" if n > 1 else "single GPU",
+            "parallelism": f"view-parallel x{n}" if n > 1 else "single GPU", "grad_sync": sync,
             "l2_policy": "inputs_larger_than_L2 (parameters+state ~2.8 GB per step vs 126 MB L2)"}
 
 
@@ -257,7 +260,7 @@ def main():
     arrs = synthetic_gaussians(spec.P, seed=0, garden=spec.garden, log_scale_mu=spec.log_scale_mu)
     pc = GaussianModel.from_arrays(arrs, sh_degree=3, device=dev)
     pc.spatial_lr_scale = 5.0
-    opt = pc.training_setup(fused=True)
+    opt = pc.training_setup(peer=True, average=True) if args.sync == "peer" else pc.training_setup(fused=True)
     cams = scene_cameras(spec, 8, device=dev)
     pipe = PipelineParams()
     bg = torch.zeros(3, device=dev)
@@ -288,8 +291,13 @@ def main():
         out = render(cam, pc, pipe, bg)
         loss = style_loss(out, tgt, dtgt)
         loss.backward()
-        # N > 1: chunked in-place NCCL all-reduce (AVG) overlapped with the per-chunk Adam update
-        wd.allreduce_and_step(opt, average=True)
+        if args.sync == "peer":
+            # one kernel: sum the N gradient replicas of this rank's shard over NVLink, Adam, store the new
+            # parameters into every replica (gradients were written into the peer arena by the backward)
+            opt.step()
+        else:
+            # N > 1: chunked in-place NCCL all-reduce (AVG) overlapped with the per-chunk Adam update
+            wd.allreduce_and_step(opt, average=True)
         opt.zero_grad(set_to_none=True)
         if host_io:
             return loss.item()  # device -> host read of the step's result
@@ -323,12 +331,20 @@ def main():
         step(i, False)
 
     def settle(host_io, first):
-        """Untimed rounds (one step per camera) until two consecutive rounds agree within 3%."""
+        """Untimed rounds (one step per camera) until two consecutive rounds agree within 3% AND the
+        caching allocator did not cudaMalloc during the last round (a fresh process keeps growing its
+        pools for a few dozen steps: tools/diag_phases.py)."""
         prev, done = None, 0
         for _ in range(20):
+            a0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
             t = timed(len(cams), host_io, first + done)
             done += len(cams)
-            if prev is not None and abs(t - prev) <= 0.03 * prev:
+            quiet = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) == a0
+            if world > 1:
+                q = torch.tensor([1 if quiet else 0], device=dev)
+                dist.all_reduce(q, op=dist.ReduceOp.MIN)
+                quiet = bool(q.item())
+            if quiet and prev is not None and abs(t - prev) <= 0.03 * prev:
                 break
             prev = t
         return done
@@ -458,13 +474,16 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": workload_config(spec, world), "impl": "ours",
+                "config": workload_config(spec, world, args.sync), "impl": "ours",
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "stages_ms": stages,
                 "scene": {"visible_gaussians": vis, "tile_instances_R": R, "pixels": N}, "extra": extra}
         print(json.dumps(line), flush=True)
+    if args.sync == "peer":
+        opt.check_peers()
+        opt.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define WAST3D_ABI_VERSION 2
+#define WAST3D_ABI_VERSION 3
 
 enum wast3d_status {
     WAST3D_OK = 0,
@@ -205,6 +205,48 @@ int wast3d_w2_match_debug(int Kc, int Ks, const float* mean_c, const float* cov_
 int wast3d_adam_step(size_t n, float* param, const float* grad, float* exp_avg,
                      float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int step,
                      void* stream);
+
+/* ---- view-parallel optimizer step over NVLink peer memory (ABI v3) ------------------
+ * The reference is single-GPU: torch.optim.Adam over six groups (scene/gaussian_model.py:149-167).
+ * With N GPUs rendering N views, every rank keeps a replica of one flat "arena" (all parameter tensors
+ * back to back, each padded to 16 bytes, then the gradients in the same layout).  Rank r owns the
+ * float4 range [shard_begin4, shard_end4) of the arena: wast3d_peer_adam_step sums the N gradient
+ * replicas of that range through peer loads (fixed rank order), applies Adam with shard-local moments
+ * and stores the new parameters into all N replicas — reduce-scatter + Adam + all-gather in one kernel,
+ * including the flag exchange that orders it against the peers' gradient kernels.  world == 1 is a
+ * single-launch multi-tensor Adam (no flags needed).
+ *
+ * grad_ptrs / param_ptrs / flag_ptrs: HOST arrays of `world` DEVICE pointers (entry q = rank q's
+ * replica as mapped into THIS process; 16-byte aligned).  flag_ptrs[q] points at
+ * wast3d_peer_flag_bytes() zero-initialised bytes of rank q.  exp_avg / exp_avg_sq: this rank's
+ * moments, 4*(shard_end4-shard_begin4) floats.  segs: parameter groups as float4 ranges of the arena,
+ * ascending and disjoint, `step` = 1-based step count.  grad_scale multiplies the summed gradient
+ * (1/world = average).  epoch: 1, 2, 3, ... identical on all ranks and increasing per call.
+ * A rank that waits longer than timeout_s (<= 0: 20 s) for a peer sets a sticky error
+ * (wast3d_peer_error) instead of hanging the GPU. */
+#define WAST3D_PEER_MAX_WORLD 8
+#define WAST3D_PEER_MAX_SEGMENTS 8
+#define WAST3D_PEER_HANDLE_BYTES 64
+typedef struct wast3d_adam_segment {
+    unsigned long long begin4, end4; /* float4 units within the arena */
+    float lr, beta1, beta2, eps;
+    int step;
+    int reserved;
+} wast3d_adam_segment;
+size_t wast3d_peer_flag_bytes(void);
+int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs, void* const* param_ptrs,
+                          void* const* flag_ptrs, float* exp_avg, float* exp_avg_sq,
+                          size_t shard_begin4, size_t shard_end4, const wast3d_adam_segment* segs,
+                          int nsegs, float grad_scale, unsigned epoch, double timeout_s, void* stream);
+/* 0 = no error; k > 0 = timed out waiting for rank k-1.  reset != 0 clears it. */
+int wast3d_peer_error(int reset);
+/* Peer-visible device memory for the arena: cudaMalloc'ed (zero-filled) and shared between the
+ * processes of one node through CUDA IPC handles (WAST3D_PEER_HANDLE_BYTES opaque bytes, exchanged by
+ * the host layer over torch.distributed).  release: imported != 0 closes a mapping, 0 frees. */
+int wast3d_peer_alloc(size_t bytes, void** out_ptr);
+int wast3d_peer_export(void* ptr, unsigned char* handle64);
+int wast3d_peer_import(const unsigned char* handle64, void** out_ptr);
+int wast3d_peer_release(void* ptr, int imported);
 
 /* Test / measurement hooks for the binning primitives that replace the reference's CUB calls
  * (cub::DeviceScan::InclusiveSum rasterizer_impl.cu:279, cub::DeviceRadixSort::SortPairs :305-310).

@@ -33,6 +33,13 @@ class RasterParams(C.Structure):
     ]
 
 
+class AdamSegment(C.Structure):
+    """struct wast3d_adam_segment (include/wast3d_b200.h)."""
+
+    _fields_ = [("begin4", C.c_ulonglong), ("end4", C.c_ulonglong), ("lr", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int), ("reserved", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol of include/wast3d_b200.h
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -64,6 +71,14 @@ SIGNATURES = {
     "wast3d_profile_read": (_i, [_vp, _vp]),
     "wast3d_launch_count": (C.c_ulonglong, [_i]),
     "wast3d_adam_step": (_i, [_sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
+    "wast3d_peer_flag_bytes": (_sz, []),
+    "wast3d_peer_adam_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _i, _f, C.c_uint,
+                                   C.c_double, _vp]),
+    "wast3d_peer_error": (_i, [_i]),
+    "wast3d_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
+    "wast3d_peer_export": (_i, [_vp, _vp]),
+    "wast3d_peer_import": (_i, [_vp, C.POINTER(_vp)]),
+    "wast3d_peer_release": (_i, [_vp, _i]),
 }
 
 _lib = None
@@ -137,17 +152,31 @@ def bucket_bytes(n: int) -> int:
     return (n + g - 1) // g * g
 
 
+# (device index, kind) -> largest size handed out so far.  The binning buffer scales with the per-view
+# instance count; asking torch's caching allocator for a slightly different size per camera makes it
+# cudaMalloc a fresh ~0.4 GB segment for every new size (tens to hundreds of milliseconds each, reserved
+# memory growing to 2-3x the live set over the first ~60 steps: tools/diag_phases.py).  Requesting the
+# high-water size every time makes every call after the first hit the allocator's cache.
+_HIGH_WATER: dict = {}
+
+
 class GrowBuffer:
     """One of the three opaque byte buffers; plays resizeFunctional (rasterize_points.cu:27-33)."""
 
-    def __init__(self, device):
+    def __init__(self, device, kind: str = "scratch"):
         self.device = device
         self.tensor = torch.empty(0, dtype=torch.uint8, device=device)
         self.error = None
+        key = (torch.device(device).index, kind)
 
         def _alloc(nbytes, _user):
             try:
-                self.tensor = torch.empty(bucket_bytes(nbytes), dtype=torch.uint8, device=self.device)
+                want = bucket_bytes(nbytes)
+                have = _HIGH_WATER.get(key, 0)
+                if want > have:
+                    # a new maximum: leave 1/8 headroom so the next slightly larger view fits as well
+                    _HIGH_WATER[key] = have = bucket_bytes(want + want // 8) if have else want
+                self.tensor = torch.empty(have, dtype=torch.uint8, device=self.device)
                 return self.tensor.data_ptr()
             except Exception as e:  # never let an exception cross the C boundary
                 self.error = e

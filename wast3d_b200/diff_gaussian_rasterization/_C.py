@@ -52,7 +52,7 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
     out_color = torch.empty((NUM_CHANNELS, H, W), dtype=torch.float32, device=dev)
     out_depth = torch.empty((H, W), dtype=torch.float32, device=dev)
     radii = torch.empty((P,), dtype=torch.int32, device=dev)
-    geom, binning, img = _lib.GrowBuffer(dev), _lib.GrowBuffer(dev), _lib.GrowBuffer(dev)
+    geom, binning, img = _lib.GrowBuffer(dev, "geom"), _lib.GrowBuffer(dev, "binning"), _lib.GrowBuffer(dev, "img")
     keep: list = []
     prm = _params(keep, P=P, D=degree, M=_sh_coeffs(sh), W=W, H=H, tan_fovx=tan_fovx,
                   tan_fovy=tan_fovy, scale_modifier=scale_modifier, prefiltered=prefiltered,

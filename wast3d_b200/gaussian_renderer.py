@@ -58,7 +58,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
             and getattr(pipe, "fused_activations", True) and model_supports_fusion(pc)):
         image, depth, radii = rasterize_model(
             xyz, screenspace_points, pc._features_dc, pc._features_rest, pc._opacity, pc._scaling,
-            pc._rotation, settings, sampling_offsets)
+            pc._rotation, settings, sampling_offsets, getattr(pc, "grad_sink", None))
         return {"render": image, "depth": depth, "viewspace_points": screenspace_points,
                 "visibility_filter": radii > 0, "radii": radii}
 

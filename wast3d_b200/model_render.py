@@ -35,8 +35,11 @@ def _prm(keep, rs: GaussianRasterizationSettings, xyz, f_dc, f_rest, opacity, sc
 class _RasterizeModel(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, means2D, f_dc, f_rest, opacity, scaling, rotation, raster_settings,
-                sampling_offsets):
+                sampling_offsets, grad_sink=None):
         rs = raster_settings
+        # peer.GradSink: the leaf gradients go straight into the optimizer's peer-visible arena
+        ctx.grad_sink = grad_sink
+        ctx.sink_params = (xyz, f_dc, f_rest, opacity, scaling, rotation) if grad_sink is not None else None
         _lib.require_device(xyz)
         if xyz.dim() != 2 or xyz.size(1) != 3:
             raise RuntimeError("means3D must have dimensions (num_points, 3)")
@@ -46,7 +49,7 @@ class _RasterizeModel(torch.autograd.Function):
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         depth = torch.empty((H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom, binning, img = _lib.GrowBuffer(dev), _lib.GrowBuffer(dev), _lib.GrowBuffer(dev)
+        geom, binning, img = _lib.GrowBuffer(dev, "geom"), _lib.GrowBuffer(dev, "binning"), _lib.GrowBuffer(dev, "img")
         keep: list = []
         prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation, sampling_offsets)
         rendered = C.c_int(0)
@@ -78,12 +81,22 @@ class _RasterizeModel(torch.autograd.Function):
         if g_depth is None:
             g_depth = torch.zeros((H, W), dtype=torch.float32, device=dev)
         opt = dict(dtype=torch.float32, device=dev)
-        d_xyz = torch.empty_like(xyz)
-        d_dc = torch.empty_like(f_dc)
-        d_rest = torch.empty_like(f_rest)
-        d_op = torch.empty_like(opacity)
-        d_sc = torch.empty_like(scaling)
-        d_rot = torch.empty_like(rotation)
+        sink, sunk = ctx.grad_sink, None
+        if sink is not None and sink.fresh:
+            sunk = [sink.view_for(p) for p in ctx.sink_params]
+            if any(v is None for v in sunk):
+                sunk = None
+        if sunk is not None:
+            # first backward since zero_grad(): K8+K9 writes every element of the arena's gradient
+            # views; autograd gets None for these leaves and .grad is pointed at the views
+            d_xyz, d_dc, d_rest, d_op, d_sc, d_rot = sunk
+        else:
+            d_xyz = torch.empty_like(xyz)
+            d_dc = torch.empty_like(f_dc)
+            d_rest = torch.empty_like(f_rest)
+            d_op = torch.empty_like(opacity)
+            d_sc = torch.empty_like(scaling)
+            d_rot = torch.empty_like(rotation)
         d_m2d = torch.empty((P, 3), **opt) if ctx.needs_input_grad[1] else None
         if P:
             keep: list = []
@@ -97,18 +110,27 @@ class _RasterizeModel(torch.autograd.Function):
                     _lib.fptr(img, keep, torch.uint8), _lib.fptr(g_color, keep), _lib.fptr(g_depth, keep),
                     p(d_xyz), p(d_dc), p(d_rest), p(d_op), p(d_sc), p(d_rot), p(d_m2d), _lib.stream_ptr())
             _lib.check(st, "rasterize_model_backward")
-        return d_xyz, d_m2d, d_dc, d_rest, d_op, d_sc, d_rot, None, None
+        elif sunk is not None:
+            for v in sunk:
+                v.zero_()
+        if sunk is not None:
+            for p_, v in zip(ctx.sink_params, sunk):
+                p_.grad = v
+            sink.fresh = False
+            return None, d_m2d, None, None, None, None, None, None, None, None
+        return d_xyz, d_m2d, d_dc, d_rest, d_op, d_sc, d_rot, None, None, None
 
 
 def rasterize_model(xyz, means2D, features_dc, features_rest, opacity_logits, log_scales, rotations,
-                    raster_settings: GaussianRasterizationSettings, sampling_offsets=None):
-    """(color[3,H,W], depth[H,W], radii[P]) from the RAW GaussianModel parameters."""
+                    raster_settings: GaussianRasterizationSettings, sampling_offsets=None, grad_sink=None):
+    """(color[3,H,W], depth[H,W], radii[P]) from the RAW GaussianModel parameters.
+    `grad_sink` (peer.GradSink, optional): destination of the leaf gradients (see peer.py)."""
     for name, t in (("features_dc", features_dc), ("features_rest", features_rest),
                     ("opacity", opacity_logits), ("scaling", log_scales), ("rotation", rotations)):
         if not t.is_contiguous() or t.dtype != torch.float32:
             raise RuntimeError(f"rasterize_model: {name} must be contiguous float32")
     return _RasterizeModel.apply(xyz, means2D, features_dc, features_rest, opacity_logits, log_scales,
-                                 rotations, raster_settings, sampling_offsets)
+                                 rotations, raster_settings, sampling_offsets, grad_sink)
 
 
 def model_supports_fusion(pc) -> bool:

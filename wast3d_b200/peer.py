@@ -1,0 +1,298 @@
+"""View-parallel optimizer over NVLink peer memory (csrc/peer_adam.cu).
+
+The reference trains on one GPU with torch.optim.Adam over six parameter groups
+(scene/gaussian_model.py:149-167).  With N GPUs rendering N views per step the textbook scheme is
+"all-reduce the gradients, then every rank runs the full Adam" (distributed.allreduce_and_step, kept as
+the NCCL baseline).  `PeerShardedAdam` instead keeps parameters AND gradients of all groups in one flat
+peer-visible arena per rank and runs ONE kernel per step: each rank sums the N gradient replicas of its
+1/N shard through peer loads, applies Adam with shard-local moments, and stores the new parameters into
+all N replicas.  Same NVLink bytes as an all-reduce; optimizer HBM traffic and state divided by N; no
+NCCL call on the step's critical path.
+
+Host-side pieces that do not touch CUDA (`ArenaLayout`: padding, shard bounds, segment table) are
+plain Python so the world_size-2 gloo tests can check them against an unsharded Adam.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+# --------------------------------------------------------------------------------- layout (host logic)
+@dataclass(frozen=True)
+class ArenaSlot:
+    begin4: int  # float4 units from the start of the parameter (or gradient) region
+    end4: int    # begin4 + ceil(numel / 4)
+    numel: int
+
+
+class ArenaLayout:
+    """Flat layout of several fp32 tensors, each padded to a multiple of 4 floats (16-byte accesses,
+    segment boundaries on float4 units), plus the balanced contiguous shard of every rank."""
+
+    def __init__(self, numels: Sequence[int]):
+        self.slots: list[ArenaSlot] = []
+        off = 0
+        for n in numels:
+            n = int(n)
+            if n < 0:
+                raise ValueError("negative size")
+            n4 = (n + 3) // 4
+            self.slots.append(ArenaSlot(off, off + n4, n))
+            off += n4
+        self.total4 = off
+
+    def shard4(self, rank: int, world: int) -> tuple[int, int]:
+        """[begin4, end4) owned by `rank`: contiguous and balanced over the whole arena (a shard may
+        span several parameter groups; the kernel intersects it with the segment table)."""
+        from .distributed import shard_bounds
+        return shard_bounds(self.total4, rank, world)
+
+    def segments(self, hyper: Sequence[dict], steps: Sequence[int]) -> list[dict]:
+        """One Adam segment per non-empty slot: float4 range + that group's hyper-parameters."""
+        out = []
+        for slot, h, t in zip(self.slots, hyper, steps):
+            if slot.end4 == slot.begin4:
+                continue
+            b1, b2 = h["betas"]
+            out.append(dict(begin4=slot.begin4, end4=slot.end4, lr=float(h["lr"]), beta1=float(b1),
+                            beta2=float(b2), eps=float(h["eps"]), step=int(t)))
+        return out
+
+
+# --------------------------------------------------------------------------------- peer-visible memory
+class _RawCuda:
+    """__cuda_array_interface__ holder so torch can view a raw device pointer as a uint8 tensor."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def _wrap(ptr: int, nbytes: int, device) -> torch.Tensor:
+    return torch.as_tensor(_RawCuda(ptr, nbytes), device=device)
+
+
+class PeerBuffer:
+    """`nbytes` of zero-filled device memory on every rank of `group`, each rank's block mapped into
+    every other rank's address space.  .local is this rank's block as a uint8 tensor, .ptrs[q] the
+    address of rank q's block in THIS process.
+
+    Backends: "ipc" = cudaMalloc + CUDA IPC handles through the library's own C ABI
+    (wast3d_peer_alloc/export/import); "symm" = torch.distributed._symmetric_memory.  "auto" tries
+    ipc, then symm; all ranks take the same decision."""
+
+    def __init__(self, nbytes: int, device, group=None, backend: str | None = None):
+        _lib.require_device()
+        self.device = torch.device(device)
+        self.nbytes = int(nbytes)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._imported: list[int] = []
+        self._own_ptr = None
+        self._symm = None
+        backend = backend or os.environ.get("WAST3D_PEER_BACKEND", "auto")
+        if self.world == 1:
+            self.backend = "local"
+            self.local = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
+            self.ptrs = [self.local.data_ptr()]
+            return
+        errors = []
+        for b in (("ipc", "symm") if backend == "auto" else (backend,)):
+            ok, err = True, None
+            try:
+                getattr(self, "_open_" + b)()
+            except Exception as e:  # noqa: BLE001 - any failure moves every rank to the next backend
+                ok, err = False, f"{b}: {e!r}"
+            flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 1:
+                self.backend = b
+                break
+            errors.append(err or f"{b}: failed on another rank")
+            self._close()
+        else:
+            raise RuntimeError("PeerBuffer: no peer-memory backend works on this node: " + "; ".join(errors))
+        dist.barrier(group=group)
+
+    # -- backends
+    def _open_ipc(self):
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            p = C.c_void_p()
+            _lib.check(lib.wast3d_peer_alloc(self.nbytes, C.byref(p)), "peer_alloc")
+            self._own_ptr = int(p.value)
+            h = (C.c_ubyte * 64)()
+            _lib.check(lib.wast3d_peer_export(self._own_ptr, h), "peer_export")
+            mine = torch.tensor(list(h), dtype=torch.uint8, device=self.device)
+            allh = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allh, mine, group=self.group)
+            allh = allh.cpu().view(self.world, 64)
+            self.ptrs = []
+            for q in range(self.world):
+                if q == self.rank:
+                    self.ptrs.append(self._own_ptr)
+                    continue
+                hq = (C.c_ubyte * 64)(*allh[q].tolist())
+                pq = C.c_void_p()
+                _lib.check(lib.wast3d_peer_import(hq, C.byref(pq)), f"peer_import(rank {q})")
+                self._imported.append(int(pq.value))
+                self.ptrs.append(int(pq.value))
+            self.local = _wrap(self._own_ptr, self.nbytes, self.device)
+
+    def _open_symm(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        with torch.cuda.device(self.device):
+            t = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+            hdl = symm_mem.rendezvous(t, grp.group_name)
+            t.zero_()
+            torch.cuda.synchronize()
+        self._symm = (t, hdl)
+        self.local = t
+        self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+
+    def _close(self):
+        lib = _lib.load()
+        for p in self._imported:
+            lib.wast3d_peer_release(p, 1)
+        self._imported = []
+        if self._own_ptr is not None:
+            self.local = None
+            lib.wast3d_peer_release(self._own_ptr, 0)
+            self._own_ptr = None
+        self._symm = None
+
+    def close(self):
+        """Unmap the peers and free the block.  Call after all ranks stopped using it."""
+        if self.world > 1:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+        self._close()
+
+
+# --------------------------------------------------------------------------------- the optimizer
+class GradSink:
+    """Where the rasteriser's backward writes the leaf gradients (model_render.py): views of the
+    arena's gradient region, one per parameter.  `fresh` is True until the first backward after
+    zero_grad(); later backwards of the same step accumulate through autograd as usual."""
+
+    def __init__(self, views: dict):
+        self.views = views  # id(param) -> gradient view with the parameter's shape
+        self.fresh = True
+
+    def view_for(self, p):
+        return self.views.get(id(p))
+
+
+class PeerShardedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam's interface (param_groups with per-group lr / betas / eps) over the peer arena.
+
+    Construction moves every parameter's storage into the arena (`p.data` becomes a view; the
+    nn.Parameter objects stay the same) and creates `grad_sink`.  step() launches the fused
+    reduce + Adam + broadcast kernel once.  Gradients are averaged over ranks when average=True
+    (mean of the per-view losses), summed otherwise.  Replicas stay bit-identical: each element is
+    computed by exactly one rank.  Moments are sharded: state_dict-style access goes through
+    `exp_avg` / `exp_avg_sq` (this rank's shard, flat)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, group=None, average=True,
+                 backend: str | None = None, timeout_s: float = 20.0):
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.group = group
+        self.average = average
+        self.timeout_s = timeout_s
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if self.world > 8:
+            raise RuntimeError("PeerShardedAdam: at most 8 ranks (one NVSwitch node)")
+        self._params = [p for g in self.param_groups for p in g["params"]]
+        self._hyper_of = [g for g in self.param_groups for _ in g["params"]]
+        if not self._params:
+            raise ValueError("no parameters")
+        dev = self._params[0].device
+        for p in self._params:
+            _lib.require_device(p)
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev:
+                raise RuntimeError("PeerShardedAdam: parameters must be contiguous float32 on one CUDA device")
+        self.device = dev
+        self.layout = ArenaLayout([p.numel() for p in self._params])
+        lib = _lib.load()
+        self._flag_bytes = (int(lib.wast3d_peer_flag_bytes()) + 255) // 256 * 256
+        region = self.layout.total4 * 16
+        self.buffer = PeerBuffer(self._flag_bytes + 2 * region, dev, group=group, backend=backend)
+        base = self.buffer.local
+        self._param_flat = base[self._flag_bytes:self._flag_bytes + region].view(torch.float32)
+        self._grad_flat = base[self._flag_bytes + region:self._flag_bytes + 2 * region].view(torch.float32)
+        views = {}
+        with torch.no_grad():
+            for p, slot in zip(self._params, self.layout.slots):
+                pv = self._param_flat[4 * slot.begin4:4 * slot.begin4 + slot.numel].view(p.shape)
+                pv.copy_(p.data)
+                p.data = pv
+                views[id(p)] = self._grad_flat[4 * slot.begin4:4 * slot.begin4 + slot.numel].view(p.shape)
+        self.grad_sink = GradSink(views)
+        self.shard = self.layout.shard4(self.rank, self.world)
+        n = 4 * (self.shard[1] - self.shard[0])
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._steps = [0] * len(self._params)
+        self._epoch = 0
+        W = self.world
+        self._grad_ptrs = (C.c_void_p * W)(*[q + self._flag_bytes + region for q in self.buffer.ptrs])
+        self._param_ptrs = (C.c_void_p * W)(*[q + self._flag_bytes for q in self.buffer.ptrs])
+        self._flag_ptrs = (C.c_void_p * W)(*self.buffer.ptrs)
+        if W > 1:  # replicas start identical: rank 0's values win (the reference has one copy)
+            dist.broadcast(self._param_flat, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                           group=group)
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        # gradients that were produced outside the sink (plain autograd) are copied into the arena
+        for p in self._params:
+            gv = self.grad_sink.view_for(p)
+            if p.grad is None:
+                gv.zero_()  # torch.optim.Adam skips such parameters; peers may still have gradients
+            elif p.grad.data_ptr() != gv.data_ptr():
+                gv.copy_(p.grad)
+        for k in range(len(self._params)):
+            self._steps[k] += 1
+        segs = self.layout.segments(self._hyper_of, self._steps)
+        arr = (_lib.AdamSegment * max(1, len(segs)))()
+        for k, s in enumerate(segs):
+            arr[k] = _lib.AdamSegment(s["begin4"], s["end4"], s["lr"], s["beta1"], s["beta2"], s["eps"], s["step"], 0)
+        self._epoch += 1
+        scale = 1.0 / self.world if self.average else 1.0
+        with torch.cuda.device(self.device):
+            rc = _lib.load().wast3d_peer_adam_step(
+                self.world, self.rank, self._grad_ptrs, self._param_ptrs, self._flag_ptrs,
+                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard[0], self.shard[1], arr, len(segs),
+                scale, self._epoch, float(self.timeout_s), _lib.stream_ptr())
+        _lib.check(rc, "peer_adam_step")
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=True)  # the arena views are overwritten by the next backward
+        self.grad_sink.fresh = True
+
+    def check_peers(self):
+        """Raise if a step timed out waiting for a peer (sticky flag set by the kernel)."""
+        e = int(_lib.load().wast3d_peer_error(0))
+        if e:
+            raise RuntimeError(f"PeerShardedAdam: timed out waiting for rank {e - 1}; replicas have diverged")
+
+    def close(self):
+        self.buffer.close()

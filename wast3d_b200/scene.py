@@ -292,9 +292,12 @@ class GaussianModel:
         self._rotation = nn.Parameter(rots.requires_grad_(True))
         self._opacity = nn.Parameter(opacities.requires_grad_(True))
 
-    def training_setup(self, training_args: OptimizationParams = OptimizationParams(), fused: bool = False):
+    def training_setup(self, training_args: OptimizationParams = OptimizationParams(), fused: bool = False,
+                       peer: bool = False, group=None, average: bool = True):
         """Adam with the reference's six groups (scene/gaussian_model.py:154-163).
-        `fused=True` swaps torch.optim.Adam for the library's fused Adam kernel (same maths)."""
+        `fused=True` swaps torch.optim.Adam for the library's fused Adam kernel (same maths);
+        `peer=True` for the view-parallel single-kernel optimizer over NVLink peer memory
+        (peer.PeerShardedAdam; parameters move into its arena, render() writes gradients there)."""
         a = training_args
         groups = [
             {"params": [self._xyz], "lr": a.position_lr_init * self.spatial_lr_scale, "name": "xyz"},
@@ -304,7 +307,12 @@ class GaussianModel:
             {"params": [self._scaling], "lr": a.scaling_lr, "name": "scaling"},
             {"params": [self._rotation], "lr": a.rotation_lr, "name": "rotation"},
         ]
-        if fused:
+        self.grad_sink = None
+        if peer:
+            from .peer import PeerShardedAdam
+            self.optimizer = PeerShardedAdam(groups, lr=0.0, eps=1e-15, group=group, average=average)
+            self.grad_sink = self.optimizer.grad_sink
+        elif fused:
             from .optim import FusedAdam
             self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
         else:
