@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--config", default="c3", choices=["c2", "c3", "c5"])
     ap.add_argument("--no-extra", action="store_true", help="skip the kNN / matching side metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
+                    help="pixel losses (L1 + TV + depth L2) through the fused kernels of csrc/loss.cu or as torch expressions")
     ap.add_argument("--sync", default="peer", choices=["peer", "nccl"],
                     help="optimizer step: 'peer' = one fused reduce+Adam+broadcast kernel over NVLink peer memory "
                          "(peer.PeerShardedAdam), 'nccl' = chunked NCCL all-reduce overlapped with the dense fused Adam")
@@ -64,11 +66,17 @@ def peaks():
 
 
 def tv_loss(img):
-    return (img[:, :, 1:] - img[:, :, :-1]).abs().mean() + (img[:, 1:, :] - img[:, :-1, :]).abs().mean()
+    """utils/loss_utils.py:213-215"""
+    return 0.5 * ((img[..., 1:, :] - img[..., :-1, :]).abs().mean() + (img[..., :, 1:] - img[..., :, :-1]).abs().mean())
 
 
-def style_loss(out, tgt, dtgt):
+def style_loss(out, tgt, dtgt, fused=False):
+    """l1_loss + tv_loss (utils/loss_utils.py:18-19,213-215; train_st_normals.py:127,145) + 0.1 * depth L2.
+    fused=True: the same expression through wast3d_b200.losses.pixel_loss (csrc/loss.cu, two kernels)."""
     img, depth = out["render"], out["depth"]
+    if fused:
+        from wast3d_b200.losses import pixel_loss
+        return pixel_loss(img, tgt, depth, dtgt, w_l1=1.0, w_tv=1.0, w_depth=0.1)
     return (img - tgt).abs().mean() + 0.1 * ((depth - dtgt) ** 2).mean() + tv_loss(img)
 
 
@@ -210,11 +218,16 @@ def run_reference(args, spec):
     print(json.dumps(line), flush=True)
 
 
+LOSS_KIND = ["fused"]
+PEER_BACKEND = [None]  # "local" | "ipc" | "symm": how the peer arena is shared (set once the optimizer exists)
+
+
 def workload_config(spec, n, sync="peer"):
     return {"workload": f"{spec.name}: synthetic garden-scale scene, {spec.P} Gaussians, {spec.width}x{spec.height}, "
                         f"SH degree 3, render fwd (colour+depth) + loss + bwd + Adam",
             "gaussians": spec.P, "width": spec.width, "height": spec.height, "views_per_step": n,
             "parallelism": f"view-parallel x{n}" if n > 1 else "single GPU", "grad_sync": sync,
+            "peer_backend": PEER_BACKEND[0] if sync == "peer" else None, "loss": LOSS_KIND[0],
             "l2_policy": "inputs_larger_than_L2 (parameters+state ~2.8 GB per step vs 126 MB L2)"}
 
 
@@ -235,6 +248,7 @@ def main():
     args = parse()
     from wast3d_b200.scene import CONFIGS
     spec = CONFIGS[args.config]
+    LOSS_KIND[0] = args.loss
     if args.impl == "reference":
         run_reference(args, spec)
         return
@@ -261,6 +275,8 @@ def main():
     pc = GaussianModel.from_arrays(arrs, sh_degree=3, device=dev)
     pc.spatial_lr_scale = 5.0
     opt = pc.training_setup(peer=True, average=True) if args.sync == "peer" else pc.training_setup(fused=True)
+    if args.sync == "peer":
+        PEER_BACKEND[0] = opt.buffer.backend + ("+multicast" if opt.multicast else "")
     cams = scene_cameras(spec, 8, device=dev)
     pipe = PipelineParams()
     bg = torch.zeros(3, device=dev)
@@ -275,22 +291,55 @@ def main():
     params = pc.parameters()
     last_R = [0]
 
+    # ---- host I/O of the end-to-end arm: this step's target image + depth come from pinned host memory
+    # over a copy stream into a double-buffered device staging area (the 17 MB transfer overlaps the
+    # forward pass; the loss waits for it), the camera matrices are copied on the compute stream (K1 needs
+    # them first), and the step's loss is copied to pinned host memory and read by the host one step later
+    # (every step's loss is read inside the timed region; the last one before the closing synchronize).
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_tgt = [torch.empty(3, H, W, device=dev) for _ in range(2)]
+    stage_dtgt = [torch.empty(H, W, device=dev) for _ in range(2)]
+    stage_free = [torch.cuda.Event() for _ in range(2)]   # compute stream is done reading stage k
+    stage_full = [torch.cuda.Event() for _ in range(2)]   # copy stream has filled stage k
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    pending = []   # slots whose loss has been enqueued but not read yet
+    losses_read = [0, 0.0]
+
+    def read_loss(slot):
+        loss_ready[slot].synchronize()
+        losses_read[0] += 1
+        losses_read[1] += float(loss_host[slot])
+
+    def drain():
+        while pending:
+            read_loss(pending.pop(0))
+
     def step(i, host_io):
         cam = wd.view_for_rank(cams, i, rank, world)
         k = i % 2
         if host_io:  # this step's inputs come from pinned host memory
+            main = torch.cuda.current_stream(dev)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(stage_free[k])
+                stage_tgt[k].copy_(tgt_host[k], non_blocking=True)
+                stage_dtgt[k].copy_(dtgt_host[k], non_blocking=True)
+                stage_full[k].record(copy_stream)
             ci = cams.index(cam)
             cam = cam.to(dev)  # shallow copy
             cam.world_view_transform = cam_host[ci][0].to(dev, non_blocking=True)
             cam.full_proj_transform = cam_host[ci][1].to(dev, non_blocking=True)
             cam.camera_center = cam_host[ci][2].to(dev, non_blocking=True)
-            tgt = tgt_host[k].to(dev, non_blocking=True)
-            dtgt = dtgt_host[k].to(dev, non_blocking=True)
+            tgt, dtgt = stage_tgt[k], stage_dtgt[k]
         else:
             tgt, dtgt = tgt_dev[k], dtgt_dev[k]
         out = render(cam, pc, pipe, bg)
-        loss = style_loss(out, tgt, dtgt)
+        if host_io:
+            main.wait_event(stage_full[k])
+        loss = style_loss(out, tgt, dtgt, fused=args.loss == "fused")
         loss.backward()
+        if host_io:
+            stage_free[k].record(main)
         if args.sync == "peer":
             # one kernel: sum the N gradient replicas of this rank's shard over NVLink, Adam, store the new
             # parameters into every replica (gradients were written into the peer arena by the backward)
@@ -300,7 +349,14 @@ def main():
             wd.allreduce_and_step(opt, average=True)
         opt.zero_grad(set_to_none=True)
         if host_io:
-            return loss.item()  # device -> host read of the step's result
+            # device -> host read of the step's result: enqueue now, the host reads it during the next step
+            if len(pending) == 2:
+                read_loss(pending.pop(0))
+            loss_host[k].copy_(loss.detach(), non_blocking=True)
+            loss_ready[k].record(main)
+            pending.append(k)
+            if len(pending) == 2:
+                read_loss(pending.pop(0))
         return None
 
     def barrier():
@@ -308,14 +364,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    issue_ms = [[]]  # host-side issue time of each step of the last timed() call (sorted)
+
     def timed(n, host_io, first):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        marks = [time.perf_counter()]
         for i in range(n):
             step(first + i, host_io)
+            marks.append(time.perf_counter())
+        drain()  # the last step's loss is read before the region closes
         b.record()
         barrier()
+        issue_ms[0] = sorted((y - x) * 1e3 for x, y in zip(marks, marks[1:]))
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -361,6 +423,8 @@ def main():
     ms_total = timed(args.steps, False, it0)
     if sampler:
         sampler.end()
+    iss = issue_ms[0]
+    host_issue = {"min": round(iss[0], 3), "median": round(iss[len(iss) // 2], 3), "max": round(iss[-1], 3)}
     launches = _lib.launch_count(reset=True)
     clocks = sampler.stop() if sampler else None
     prof = _lib.profile_read()
@@ -476,8 +540,10 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(spec, world, args.sync), "impl": "ours",
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "h2d": "pinned -> device on a copy stream, overlapped with the forward pass",
+                        "d2h": "loss copied to pinned memory every step, read by the host one step later",
                         "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+                "gpu_launches": launches, "host_issue_ms_per_step": host_issue, "clocks": clocks, "roofline": roofline,
                 "cpu_baseline": cpu_baseline, "stages_ms": stages,
                 "scene": {"visible_gaussians": vis, "tile_instances_R": R, "pixels": N}, "extra": extra}
         print(json.dumps(line), flush=True)

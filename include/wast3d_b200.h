@@ -206,6 +206,24 @@ int wast3d_adam_step(size_t n, float* param, const float* grad, float* exp_avg,
                      float* exp_avg_sq, float lr, float beta1, float beta2, float eps, int step,
                      void* stream);
 
+/* Fused pixel losses of the style-optimisation loop (replaces the torch expressions of
+ * utils/loss_utils.py:18-19 l1_loss and :213-215 tv_loss as called at train_st_normals.py:127,145, plus
+ * a depth L2 term):
+ *   loss = w_l1 * mean|img - gt| + w_tv * 0.5 * (mean|img[y+1]-img[y]| + mean|img[x+1]-img[x]|)
+ *        + w_depth * mean((depth - depth_gt)^2)
+ * img, gt [C,H,W] (gt NULL = no L1 term); depth, depth_gt [H,W] or both NULL.  scratch:
+ * wast3d_pixel_loss_scratch_bytes() bytes, zero-filled once by the caller and then reusable for calls
+ * on the same stream.  out_loss: one float.  The reduction order is fixed (deterministic result).
+ * backward: d_img [C,H,W] and d_depth [H,W] (d_depth NULL allowed) = grad_out[0] * dloss/d(.), grad_out
+ * a DEVICE scalar (NULL = 1); sign(0) = 0 like torch. */
+size_t wast3d_pixel_loss_scratch_bytes(void);
+int wast3d_pixel_loss_forward(int C, int H, int W, const float* img, const float* gt, const float* depth,
+                              const float* depth_gt, float w_l1, float w_tv, float w_depth, void* scratch,
+                              float* out_loss, void* stream);
+int wast3d_pixel_loss_backward(int C, int H, int W, const float* img, const float* gt, const float* depth,
+                               const float* depth_gt, float w_l1, float w_tv, float w_depth,
+                               const float* grad_out, float* d_img, float* d_depth, void* stream);
+
 /* ---- view-parallel optimizer step over NVLink peer memory (ABI v3) ------------------
  * The reference is single-GPU: torch.optim.Adam over six groups (scene/gaussian_model.py:149-167).
  * With N GPUs rendering N views, every rank keeps a replica of one flat "arena" (all parameter tensors
@@ -222,6 +240,10 @@ int wast3d_adam_step(size_t n, float* param, const float* grad, float* exp_avg,
  * moments, 4*(shard_end4-shard_begin4) floats.  segs: parameter groups as float4 ranges of the arena,
  * ascending and disjoint, `step` = 1-based step count.  grad_scale multiplies the summed gradient
  * (1/world = average).  epoch: 1, 2, 3, ... identical on all ranks and increasing per call.
+ * mc_grads / mc_params: NVLS multicast addresses of the gradient / parameter regions (an NVSwitch
+ * multicast object bound to every rank's arena), or NULL.  When both are given the switch sums the
+ * gradients (multimem.ld_reduce) and broadcasts the parameters (multimem.st): ~1x the arena crosses
+ * each NVLink direction per step instead of 2 (N-1)/N x with per-peer loads and stores.
  * A rank that waits longer than timeout_s (<= 0: 20 s) for a peer sets a sticky error
  * (wast3d_peer_error) instead of hanging the GPU. */
 #define WAST3D_PEER_MAX_WORLD 8
@@ -235,7 +257,8 @@ typedef struct wast3d_adam_segment {
 } wast3d_adam_segment;
 size_t wast3d_peer_flag_bytes(void);
 int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs, void* const* param_ptrs,
-                          void* const* flag_ptrs, float* exp_avg, float* exp_avg_sq,
+                          void* const* flag_ptrs, void* mc_grads, void* mc_params,
+                          float* exp_avg, float* exp_avg_sq,
                           size_t shard_begin4, size_t shard_end4, const wast3d_adam_segment* segs,
                           int nsegs, float grad_scale, unsigned epoch, double timeout_s, void* stream);
 /* 0 = no error; k > 0 = timed out waiting for rank k-1.  reset != 0 clears it. */

@@ -71,8 +71,11 @@ SIGNATURES = {
     "wast3d_profile_read": (_i, [_vp, _vp]),
     "wast3d_launch_count": (C.c_ulonglong, [_i]),
     "wast3d_adam_step": (_i, [_sz, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i, _vp]),
+    "wast3d_pixel_loss_scratch_bytes": (_sz, []),
+    "wast3d_pixel_loss_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp]),
+    "wast3d_pixel_loss_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp]),
     "wast3d_peer_flag_bytes": (_sz, []),
-    "wast3d_peer_adam_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _i, _f, C.c_uint,
+    "wast3d_peer_adam_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _i, _f, C.c_uint,
                                    C.c_double, _vp]),
     "wast3d_peer_error": (_i, [_i]),
     "wast3d_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),

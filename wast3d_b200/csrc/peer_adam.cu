@@ -38,6 +38,8 @@ struct PeerArgs {
     const float4* grads[PEER_MAX_WORLD];
     float4* params[PEER_MAX_WORLD];
     uint32_t* flags[PEER_MAX_WORLD];  // per rank: [2][PEER_MAX_WORLD] words (arrive, done), written by peers
+    const float4* mc_grads;           // NVLS multicast mapping of the gradient / parameter regions of ALL
+    float4* mc_params;                // ranks (NULL: use the per-rank pointers above)
     float4* m;                        // moments of MY shard, index (i - shard_begin4)
     float4* v;
     unsigned long long shard_begin4, shard_end4;
@@ -64,8 +66,25 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 // streaming 16-byte accesses: nothing here is re-read by this kernel
-__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+// (volatile asm: the loads of one tile are all issued, in program order, before the first use)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 __device__ __forceinline__ void st_stream(float4* p, const float4& v) { __stcs(p, v); }
+// NVLS (NVSwitch multicast): one load returns the switch-side sum of the addressed float4 over every
+// GPU bound to the multicast object; one store lands in every GPU's replica.
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float4* p) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float4* p, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 // Wait until every peer wrote `epoch` (or a later one) into my flag row.  Returns false on time-out.
 __device__ bool wait_flags(const uint32_t* row, int world, uint32_t epoch, unsigned long long timeout_ns,
@@ -96,7 +115,10 @@ __device__ __forceinline__ void adam4(float4& p, const float4& g, float4& m, flo
 #undef W3D_ADAM1
 }
 
-template <int WORLD>
+// MC = true: gradients are summed by the switch (multimem.ld_reduce) and parameters broadcast by it
+// (multimem.st): per GPU and direction ~1x the arena crosses NVLink instead of 2 (N-1)/N x with the
+// per-peer loads and stores of MC = false.
+template <int WORLD, bool MC>
 __global__ void __launch_bounds__(PEER_THREADS)
 peer_adam_kernel(const __grid_constant__ PeerArgs a) {
     __shared__ int ok_s;
@@ -113,32 +135,59 @@ peer_adam_kernel(const __grid_constant__ PeerArgs a) {
         if (!ok_s) return;
     }
 
-    // ---- phase 1: reduce + Adam + broadcast over my shard, one segment (= parameter group) at a time
-    const unsigned long long tid = (unsigned long long)blockIdx.x * PEER_THREADS + threadIdx.x;
-    const unsigned long long stride = (unsigned long long)gridDim.x * PEER_THREADS;
+    // ---- phase 1: reduce + Adam + broadcast over my shard, one segment (= parameter group) at a time.
+    // NVLink latency (~2 us) x bandwidth (~0.9 TB/s per direction) needs ~2 MB of peer loads in flight per
+    // GPU: every thread issues all loads of U float4 columns (U * (WORLD + 3) 16-byte loads) before it
+    // touches any of them.
+    constexpr int U = MC ? 4 : (WORLD <= 2 ? 4 : (WORLD <= 5 ? 2 : 1));
+    constexpr int NG = MC ? 1 : WORLD;  // gradient loads per column
+    const unsigned long long tile = (unsigned long long)PEER_THREADS * U;
     for (int sidx = 0; sidx < a.nsegs; ++sidx) {
         const PeerSeg seg = a.segs[sidx];
         const unsigned long long lo = seg.begin4 > a.shard_begin4 ? seg.begin4 : a.shard_begin4;
         const unsigned long long hi = seg.end4 < a.shard_end4 ? seg.end4 : a.shard_end4;
-        for (unsigned long long i = lo + tid; i < hi; i += stride) {
-            float4 g[WORLD];
+        for (unsigned long long base = lo + (unsigned long long)blockIdx.x * tile; base < hi;
+             base += (unsigned long long)gridDim.x * tile) {
+            float4 g[U][NG], p[U], m[U], v[U];
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int q = 0; q < WORLD; ++q) g[q] = ld_stream(a.grads[q] + i);
-            const unsigned long long j = i - a.shard_begin4;
-            float4 p = ld_stream(a.params[rank] + i), m = ld_stream(a.m + j), v = ld_stream(a.v + j);
-            float4 gs = g[0];
+            for (int u = 0; u < U; ++u) {
+                const unsigned long long i = base + (unsigned long long)u * PEER_THREADS + threadIdx.x;
+                const bool in = i < hi;
+                const unsigned long long j = i - a.shard_begin4;
+                if (MC) {
+                    g[u][0] = in ? mc_ld_reduce_add(a.mc_grads + i) : z;
+                } else {
 #pragma unroll
-            for (int q = 1; q < WORLD; ++q) {
-                gs.x += g[q].x; gs.y += g[q].y; gs.z += g[q].z; gs.w += g[q].w;
+                    for (int q = 0; q < NG; ++q) g[u][q] = in ? ld_stream(a.grads[q] + i) : z;
+                }
+                p[u] = in ? ld_stream(a.params[rank] + i) : z;
+                m[u] = in ? ld_stream(a.m + j) : z;
+                v[u] = in ? ld_stream(a.v + j) : z;
             }
-            if (WORLD > 1) {
-                gs.x *= a.grad_scale; gs.y *= a.grad_scale; gs.z *= a.grad_scale; gs.w *= a.grad_scale;
-            }
-            adam4(p, gs, m, v, seg);
-            st_stream(a.m + j, m);
-            st_stream(a.v + j, v);
 #pragma unroll
-            for (int q = 0; q < WORLD; ++q) st_stream(a.params[q] + i, p);
+            for (int u = 0; u < U; ++u) {
+                const unsigned long long i = base + (unsigned long long)u * PEER_THREADS + threadIdx.x;
+                if (i >= hi) continue;
+                const unsigned long long j = i - a.shard_begin4;
+                float4 gs = g[u][0];
+#pragma unroll
+                for (int q = 1; q < NG; ++q) {
+                    gs.x += g[u][q].x; gs.y += g[u][q].y; gs.z += g[u][q].z; gs.w += g[u][q].w;
+                }
+                if (WORLD > 1) {
+                    gs.x *= a.grad_scale; gs.y *= a.grad_scale; gs.z *= a.grad_scale; gs.w *= a.grad_scale;
+                }
+                adam4(p[u], gs, m[u], v[u], seg);
+                st_stream(a.m + j, m[u]);
+                st_stream(a.v + j, v[u]);
+                if (MC) {
+                    mc_st(a.mc_params + i, p[u]);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < WORLD; ++q) st_stream(a.params[q] + i, p[u]);
+                }
+            }
         }
     }
 
@@ -182,7 +231,8 @@ using namespace w3d;
 extern "C" size_t wast3d_peer_flag_bytes(void) { return 2 * PEER_MAX_WORLD * sizeof(uint32_t) + 64; }
 
 extern "C" int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs, void* const* param_ptrs,
-                                     void* const* flag_ptrs, float* exp_avg, float* exp_avg_sq,
+                                     void* const* flag_ptrs, void* mc_grads, void* mc_params,
+                                     float* exp_avg, float* exp_avg_sq,
                                      size_t shard_begin4, size_t shard_end4,
                                      const wast3d_adam_segment* segs, int nsegs, float grad_scale,
                                      unsigned epoch, double timeout_s, void* stream_v) {
@@ -206,7 +256,11 @@ extern "C" int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs
         a.params[q] = (float4*)param_ptrs[q];
         a.flags[q] = world > 1 ? (uint32_t*)flag_ptrs[q] : nullptr;
     }
-    if (((size_t)exp_avg | (size_t)exp_avg_sq) & 15) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (((size_t)exp_avg | (size_t)exp_avg_sq | (size_t)mc_grads | (size_t)mc_params) & 15)
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    const bool mc = world > 1 && mc_grads != nullptr && mc_params != nullptr;
+    a.mc_grads = mc ? (const float4*)mc_grads : nullptr;
+    a.mc_params = mc ? (float4*)mc_params : nullptr;
     a.m = (float4*)exp_avg;
     a.v = (float4*)exp_avg_sq;
     a.shard_begin4 = shard_begin4;
@@ -240,14 +294,29 @@ extern "C" int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs
 
     const size_t n4 = shard_end4 - shard_begin4;
     size_t blocks = (n4 + PEER_THREADS - 1) / PEER_THREADS;
-    if (blocks > 148 * 4) blocks = 148 * 4;   // persistent: 4 CTAs of 512 threads per SM
     if (blocks < 1) blocks = 1;
     ProfScope ps(PS_ADAM, s);
     switch (world) {
-#define W3D_PEER_CASE(N) case N: peer_adam_kernel<N><<<(unsigned)blocks, PEER_THREADS, 0, s>>>(a); break;
+        // persistent grid: as many CTAs as are resident at once (register-limited, differs per WORLD)
+#define W3D_PEER_LAUNCH(N, MCFLAG)                                                                        \
+    {                                                                                                     \
+        static int per_sm = 0;                                                                            \
+        if (!per_sm) {                                                                                    \
+            W3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(                                   \
+                &per_sm, peer_adam_kernel<N, MCFLAG>, PEER_THREADS, 0));                                  \
+            if (per_sm < 1) per_sm = 1;                                                                   \
+        }                                                                                                 \
+        if (blocks > (size_t)148 * per_sm) blocks = (size_t)148 * per_sm;                                 \
+        peer_adam_kernel<N, MCFLAG><<<(unsigned)blocks, PEER_THREADS, 0, s>>>(a);                         \
+    }
+#define W3D_PEER_CASE(N)                                                                                  \
+    case N:                                                                                               \
+        if (mc) W3D_PEER_LAUNCH(N, true) else W3D_PEER_LAUNCH(N, false)                                   \
+        break;
         W3D_PEER_CASE(1) W3D_PEER_CASE(2) W3D_PEER_CASE(3) W3D_PEER_CASE(4)
         W3D_PEER_CASE(5) W3D_PEER_CASE(6) W3D_PEER_CASE(7) W3D_PEER_CASE(8)
 #undef W3D_PEER_CASE
+#undef W3D_PEER_LAUNCH
         default: return WAST3D_ERR_INVALID_ARGUMENT;
     }
     W3D_AFTER_LAUNCH(s, false);

@@ -86,8 +86,9 @@ class PeerBuffer:
     address of rank q's block in THIS process.
 
     Backends: "ipc" = cudaMalloc + CUDA IPC handles through the library's own C ABI
-    (wast3d_peer_alloc/export/import); "symm" = torch.distributed._symmetric_memory.  "auto" tries
-    ipc, then symm; all ranks take the same decision."""
+    (wast3d_peer_alloc/export/import); "symm" = torch.distributed._symmetric_memory, which also binds
+    the blocks to an NVSwitch multicast object where the node supports it (.mc_ptr).  "auto" tries symm
+    then ipc with more than two ranks, ipc then symm with two; all ranks take the same decision."""
 
     def __init__(self, nbytes: int, device, group=None, backend: str | None = None):
         _lib.require_device()
@@ -99,14 +100,18 @@ class PeerBuffer:
         self._imported: list[int] = []
         self._own_ptr = None
         self._symm = None
+        self.mc_ptr = 0  # NVLS multicast address of the block (symm backend on NVSwitch), 0 = none
         backend = backend or os.environ.get("WAST3D_PEER_BACKEND", "auto")
+        # auto: with more than two ranks the switch-side reduction (multicast, symm backend) halves the
+        # NVLink bytes, so it is tried first; with two ranks plain peer loads/stores move the same bytes
+        order = ("symm", "ipc") if self.world > 2 else ("ipc", "symm")
         if self.world == 1:
             self.backend = "local"
             self.local = torch.zeros(self.nbytes, dtype=torch.uint8, device=self.device)
             self.ptrs = [self.local.data_ptr()]
             return
         errors = []
-        for b in (("ipc", "symm") if backend == "auto" else (backend,)):
+        for b in (order if backend == "auto" else (backend,)):
             ok, err = True, None
             try:
                 getattr(self, "_open_" + b)()
@@ -159,6 +164,8 @@ class PeerBuffer:
         self._symm = (t, hdl)
         self.local = t
         self.ptrs = [int(p) for p in hdl.buffer_ptrs]
+        mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+        self.mc_ptr = 0 if os.environ.get("WAST3D_PEER_MULTICAST", "1") == "0" else mc
 
     def _close(self):
         lib = _lib.load()
@@ -170,6 +177,7 @@ class PeerBuffer:
             lib.wast3d_peer_release(self._own_ptr, 0)
             self._own_ptr = None
         self._symm = None
+        self.mc_ptr = 0
 
     def close(self):
         """Unmap the peers and free the block.  Call after all ranks stopped using it."""
@@ -249,6 +257,10 @@ class PeerShardedAdam(torch.optim.Optimizer):
         self._grad_ptrs = (C.c_void_p * W)(*[q + self._flag_bytes + region for q in self.buffer.ptrs])
         self._param_ptrs = (C.c_void_p * W)(*[q + self._flag_bytes for q in self.buffer.ptrs])
         self._flag_ptrs = (C.c_void_p * W)(*self.buffer.ptrs)
+        mc = self.buffer.mc_ptr if W > 1 else 0
+        self._mc_params = (mc + self._flag_bytes) if mc else None
+        self._mc_grads = (mc + self._flag_bytes + region) if mc else None
+        self.multicast = bool(mc)
         if W > 1:  # replicas start identical: rank 0's values win (the reference has one copy)
             dist.broadcast(self._param_flat, src=dist.get_global_rank(group, 0) if group is not None else 0,
                            group=group)
@@ -279,7 +291,7 @@ class PeerShardedAdam(torch.optim.Optimizer):
         with torch.cuda.device(self.device):
             rc = _lib.load().wast3d_peer_adam_step(
                 self.world, self.rank, self._grad_ptrs, self._param_ptrs, self._flag_ptrs,
-                self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard[0], self.shard[1], arr, len(segs),
+                self._mc_grads, self._mc_params, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard[0], self.shard[1], arr, len(segs),
                 scale, self._epoch, float(self.timeout_s), _lib.stream_ptr())
         _lib.check(rc, "peer_adam_step")
         return loss
