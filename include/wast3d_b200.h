@@ -124,6 +124,30 @@ int wast3d_raster_backward_raw(const wast3d_raster_params* prm, int num_rendered
                                float* dL_dopacity_logit, float* dL_dlog_scale, float* dL_drotation,
                                float* dL_dmean2D, void* stream);
 
+/* wast3d_raster_backward_raw with the optimizer folded in ("the Adam update into
+ * K9's epilogue"): instead of writing the six leaf gradients and running torch.optim.Adam over them
+ * (scene/gaussian_model.py:149-167, GaussianModel.optimizer.step() at train_st.py:317), the per-Gaussian
+ * kernel applies the Adam update to every parameter element in place as soon as its gradient is known —
+ * same arithmetic as wast3d_adam_step, dense semantics (culled Gaussians take the zero-gradient update).
+ * groups[6] = xyz, features_dc, features_rest, opacity, scaling, rotation, in that order; groups[k].param
+ * must be the pointer the forward read (prm->means3D, shs, shs_rest, opacities, scales, rotations) and
+ * groups[k].step the 1-based count of THIS update.  Only valid when this backward carries the whole
+ * gradient of the step (single GPU, one rasteriser call per optimizer step).
+ * grads_out: NULL, or 6 pointers (each may be NULL) that additionally receive the leaf gradients (tests). */
+typedef struct wast3d_adam_group {
+    float* param;
+    float* exp_avg;
+    float* exp_avg_sq;
+    float lr, beta1, beta2, eps;
+    int step;
+    int reserved;
+} wast3d_adam_group;
+int wast3d_raster_backward_raw_adam(const wast3d_raster_params* prm, int num_rendered, const int* radii,
+                                    void* geom_buffer, void* binning_buffer, void* img_buffer,
+                                    const float* dL_dpix, const float* dL_ddepth,
+                                    const wast3d_adam_group* groups, float* const* grads_out,
+                                    float* dL_dmean2D, void* stream);
+
 /* Test/inspection hook (no reference equivalent is Python-visible; mirrors the state
  * structs of rasterizer_impl.h:29-65).  Any output may be NULL.
  * depths[P], means2D[P,2], conic_opacity[P,4], rgb[P,3], tiles_touched[P] (uint32),
@@ -134,6 +158,13 @@ int wast3d_raster_export_state(const wast3d_raster_params* prm, int num_rendered
                                float* conic_opacity, float* rgb, uint32_t* tiles_touched,
                                unsigned char* clamped, uint32_t* point_list, uint32_t* ranges,
                                void* stream);
+
+/* Tile instancing policy of wast3d_raster_forward (process-wide; returns the previous mode, any other
+ * `mode` value only queries).  1 (default; env WAST3D_TILE_CUT) = a Gaussian is instantiated only in
+ * the tiles whose sample positions can reach alpha >= 1/255 (forward.cu:355) — same image, same
+ * gradients, fewer instances than duplicateWithKeys (rasterizer_impl.cu:70-113); 0 = the reference's
+ * radius rectangles (auxiliary.h:46-56), which reproduces its num_rendered and point list exactly. */
+int wast3d_set_tile_cut(int mode);
 
 /* Replaces markVisible -> checkFrustum (rasterize_points.cu:208-227,
  * rasterizer_impl.cu:54-66,141-153).  present is bool[P] (1 byte each). */

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.util import call_backward, call_forward, export, raster_case, rel_l2, to_cuda
+from tests.util import CutMapping, call_backward, call_forward, export, raster_case, rel_l2, to_cuda
 
 pytestmark = pytest.mark.gpu
 GOLD = Path(__file__).resolve().parent / "golden"
@@ -35,6 +35,16 @@ def _np(t):
     return t.detach().cpu().numpy()
 
 
+@pytest.fixture(params=[1, 0], ids=["tile_cut", "ref_rects"])
+def cut(request, built):
+    """Both tile instancing policies (include/wast3d_b200.h wast3d_set_tile_cut): 0 reproduces the
+    reference's instance lists bit for bit, 1 (the default) drops instances that cannot contribute."""
+    from wast3d_b200 import _lib
+    prev = _lib.set_tile_cut(request.param)
+    yield request.param
+    _lib.set_tile_cut(prev)
+
+
 def _run_all(case, seed=0):
     from oracle import cpu
     tc = to_cuda(case)
@@ -48,7 +58,7 @@ def _run_all(case, seed=0):
 
 
 @pytest.mark.parametrize("name", list(CASES))
-def test_stages_against_oracle(built, name):
+def test_stages_against_oracle(built, cut, name):
     case = raster_case(**CASES[name])
     tc, fwd, st, dpix, ddep, grads, cpu = _run_all(case)
     R, color, depth, radii = fwd[0], fwd[1], fwd[2], fwd[3]
@@ -67,11 +77,27 @@ def test_stages_against_oracle(built, name):
         assert np.abs(pre["rgb"][vis] - _np(st["rgb"])[vis]).max() <= 5e-6
     # ---- binning: exact, given OUR K1 outputs
     b = cpu.bin_instances(W, H, r, _np(st["means2D"]), _np(st["depths"]))
-    assert b["R"] == R == int(_np(st["tiles_touched"]).astype(np.int64).sum())
-    assert (b["point_list"] == _np(st["point_list"]).astype(np.uint32)).all()
-    assert (b["ranges"] == _np(st["ranges"]).astype(np.uint32)).all()
-    # ---- K6 on identical inputs
+    assert R == int(_np(st["tiles_touched"]).astype(np.int64).sum())
     colors = case["colors_precomp"] if "colors_precomp" in case else _np(st["rgb"])
+    if cut == 0:
+        assert b["R"] == R
+        assert (b["point_list"] == _np(st["point_list"]).astype(np.uint32)).all()
+        assert (b["ranges"] == _np(st["ranges"]).astype(np.uint32)).all()
+    else:
+        # our lists = the reference's with non-contributing instances removed, order preserved ...
+        ours = dict(ranges=_np(st["ranges"]).astype(np.uint32), point_list=_np(st["point_list"]).astype(np.uint32))
+        cm = CutMapping(b["ranges"], b["point_list"], ours["ranges"], ours["point_list"], P)
+        assert R < b["R"]
+        # ... and the oracle renders bit-identical images from both lists
+        img_ref = cpu.render_forward(W, H, case["bg"], case.get("sampling_offsets"), b["ranges"], b["point_list"],
+                                     _np(st["means2D"]), colors, _np(st["depths"]), _np(st["conic_opacity"]))
+        img_cut = cpu.render_forward(W, H, case["bg"], case.get("sampling_offsets"), ours["ranges"], ours["point_list"],
+                                     _np(st["means2D"]), colors, _np(st["depths"]), _np(st["conic_opacity"]))
+        for k in ("color", "depth", "final_T"):
+            assert np.array_equal(img_ref[k], img_cut[k]), k
+        assert np.array_equal(cm.map_n_contrib(img_ref["n_contrib"], W, H), img_cut["n_contrib"].astype(np.int64))
+        b = dict(b, **ours)
+    # ---- K6 on identical inputs
     img = cpu.render_forward(W, H, case["bg"], case.get("sampling_offsets"), b["ranges"], b["point_list"],
                              _np(st["means2D"]), colors, _np(st["depths"]), _np(st["conic_opacity"]))
     ok = img["fragile"] == 0
@@ -108,7 +134,7 @@ def test_stages_against_oracle(built, name):
 
 
 @pytest.mark.parametrize("name", ["raster_sh_jitter", "raster_precomp"])
-def test_against_golden(built, name):
+def test_against_golden(built, cut, name):
     z = np.load(GOLD / f"{name}.npz")
     case = {k[3:]: z[k] for k in z.files if k.startswith("in_")}
     for k in ("W", "H", "D"):
@@ -118,13 +144,24 @@ def test_against_golden(built, name):
     tc = to_cuda(case)
     fwd = call_forward(tc)
     st = export(tc, fwd)
-    assert fwd[0] == int(z["R"])
     assert (_np(fwd[3]) == z["radii"]).all()
-    assert (_np(st["point_list"]) == z["st_point_list"]).all()
+    if cut == 0:
+        assert fwd[0] == int(z["R"])
+        assert (_np(st["point_list"]) == z["st_point_list"]).all()
+        assert (_np(st["n_contrib"]) == z["st_n_contrib"]).all()
+    else:
+        # tile ranges of the reference's list: the (golden-pinned) CPU binning on the reference's K1 outputs
+        from oracle import cpu
+        b = cpu.bin_instances(case["W"], case["H"], z["radii"], z["st_means2D"], z["st_depths"])
+        assert (b["point_list"] == z["st_point_list"].astype(np.uint32)).all()
+        cm = CutMapping(b["ranges"], b["point_list"], _np(st["ranges"]).astype(np.uint32),
+                        _np(st["point_list"]).astype(np.uint32), case["means3D"].shape[0])
+        assert fwd[0] <= int(z["R"])
+        assert np.array_equal(cm.map_n_contrib(z["st_n_contrib"], case["W"], case["H"]),
+                              _np(st["n_contrib"]).astype(np.int64))
     assert np.abs(_np(fwd[1]) - z["color"]).max() <= 1e-4
     assert np.abs(_np(fwd[2]) - z["depth"]).max() <= 1e-4
     assert np.abs(_np(st["final_T"]) - z["st_final_T"]).max() <= 1e-4
-    assert (_np(st["n_contrib"]) == z["st_n_contrib"]).all()
     g = dict(zip(GRAD_NAMES, call_backward(tc, fwd, torch.from_numpy(z["dL_dpix"]).cuda(),
                                           torch.from_numpy(z["dL_ddepth"]).cuda())))
     for k in ("dL_dmean2D", "dL_dcolor", "dL_dopacity", "dL_dmean3D", "dL_dcov3D", "dL_dsh", "dL_dscale", "dL_drot"):
@@ -134,7 +171,7 @@ def test_against_golden(built, name):
 
 
 @pytest.mark.parametrize("name", ["sh3_jitter", "odd_size_bg", "precomp", "garden_culling"])
-def test_against_reference_library(built, name):
+def test_against_reference_library(built, cut, name):
     from oracle import ref
     if not ref.available():
         pytest.skip("oracle/_ref not built on this box")
@@ -145,13 +182,23 @@ def test_against_reference_library(built, name):
             "colors_precomp", "scales", "rotations", "cov3D_precomp", "sampling_offsets", "D", "scale_modifier")
     rf = rr.forward(**{k: tc.get(k) for k in keys})
     rs = rr.state()
-    assert rf["R"] == fwd[0]
     assert torch.equal(rf["radii"], fwd[3])
-    assert torch.equal(rs["point_list"], st["point_list"])
+    if cut == 0:
+        assert rf["R"] == fwd[0]
+        assert torch.equal(rs["point_list"], st["point_list"])
+        assert torch.equal(rs["n_contrib"], st["n_contrib"])
+    else:
+        from oracle import cpu
+        b = cpu.bin_instances(case["W"], case["H"], _np(rf["radii"]), _np(rs["means2D"]), _np(rs["depths"]))
+        assert (b["point_list"] == _np(rs["point_list"]).astype(np.uint32)).all()
+        cm = CutMapping(b["ranges"], b["point_list"], _np(st["ranges"]).astype(np.uint32),
+                        _np(st["point_list"]).astype(np.uint32), case["means3D"].shape[0])
+        assert fwd[0] < rf["R"]
+        assert np.array_equal(cm.map_n_contrib(_np(rs["n_contrib"]), case["W"], case["H"]),
+                              _np(st["n_contrib"]).astype(np.int64))
     assert (rf["color"] - fwd[1]).abs().max().item() <= 1e-4
     assert (rf["depth"] - fwd[2]).abs().max().item() <= 1e-4
     assert (rs["final_T"] - st["final_T"]).abs().max().item() <= 1e-4
-    assert torch.equal(rs["n_contrib"], st["n_contrib"])
     rg = rr.backward(dpix, ddep)
     for k in GRAD_NAMES:
         want = rg[k]
@@ -260,6 +307,70 @@ def test_model_render_matches_unfused(built, P, sh_degree, active, W, H):
         for a in pf.parameters():
             if a.numel():
                 assert a.grad.reshape(a.shape[0], -1)[culled].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("P,sh_degree,active,W,H", [(5000, 3, 3, 160, 120), (4999, 3, 1, 97, 61), (777, 0, 0, 64, 48),
+                                                     (31, 1, 1, 33, 17)])
+def test_adam_in_backward_equals_backward_then_adam(built, P, sh_degree, active, W, H):
+    """optim.BackwardFusedAdam (wast3d_raster_backward_raw_adam: the Adam update applied by K8+K9 in place)
+    against "backward, then Adam over the gradients" — exact comparison: the fused kernel also dumps the
+    gradients it consumed (capture_grads), and torch.optim.Adam's update of the SAME gradients from the
+    SAME state must give the same parameters and moments (a few ulp: FMA contraction may differ)."""
+    from wast3d_b200.gaussian_renderer import render
+    from wast3d_b200.scene import GaussianModel, PipelineParams, orbit_cameras, synthetic_gaussians
+    arrs = synthetic_gaussians(P, seed=4, log_scale_mu=-3.3, sh_degree=sh_degree)
+    cams = orbit_cameras(4, 4.03, 0.0, 0.6911, W, H, device="cuda", sphere=True)
+    bg = torch.tensor([0.1, 0.3, 0.2], device="cuda")
+    torch.manual_seed(0)
+    tgt = torch.rand(3, H, W, device="cuda")
+    pc = GaussianModel.from_arrays(arrs, sh_degree=sh_degree, device="cuda")
+    pc.active_sh_degree = active
+    pc.spatial_lr_scale = 2.0
+    opt = pc.training_setup(in_backward=True)
+    opt.capture_grads = True
+    # the reference optimizer runs on clones, fed with the captured gradients
+    shadow = [p.detach().clone().requires_grad_(True) for p in pc.parameters()]
+    ref = torch.optim.Adam([dict(params=[q], lr=g["lr"]) for q, g in zip(shadow, opt.param_groups)], lr=0.0, eps=1e-15)
+    for it in range(3):
+        offs = -torch.rand(H, W, 2, device="cuda")
+        before = [p.detach().clone() for p in pc.parameters()]
+        out = render(cams[it], pc, PipelineParams(), bg, sampling_offsets=offs)
+        loss = ((out["render"] - tgt) ** 2).sum() + 0.1 * (out["depth"] ** 2).sum()
+        loss.backward()
+        assert all(p.grad is None for p in pc.parameters())          # no gradient tensors
+        with pytest.raises(RuntimeError):                             # a second backward is refused
+            out2 = render(cams[it], pc, PipelineParams(), bg, sampling_offsets=offs)
+            out2["render"].sum().backward()
+        opt.step()
+        opt.zero_grad()
+        for q, g in zip(shadow, opt.last_grads):
+            q.grad = g.clone()
+        ref.step()
+        culled = out["radii"] == 0
+        for name, p, q, b, g in zip(("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation"), pc.parameters(), shadow,
+                                    before, opt.last_grads):
+            if p.numel() == 0:
+                continue
+            assert torch.isfinite(p).all(), name
+            torch.testing.assert_close(p.detach(), q.detach(), rtol=2e-6, atol=1e-7, msg=lambda m: f"{name} it={it}: {m}")
+            st, rst = opt.state[p], ref.state[q]
+            torch.testing.assert_close(st["exp_avg"], rst["exp_avg"], rtol=1e-5, atol=1e-12)
+            torch.testing.assert_close(st["exp_avg_sq"], rst["exp_avg_sq"], rtol=1e-5, atol=1e-20)
+            if it == 0 and culled.any():   # zero gradient, zero moments: culled Gaussians do not move
+                assert torch.equal(p.detach().reshape(p.shape[0], -1)[culled], b.reshape(b.shape[0], -1)[culled]), name
+                assert g.reshape(g.shape[0], -1)[culled].abs().max().item() == 0, name
+        assert any(not torch.equal(p.detach(), b) for p, b in zip(pc.parameters(), before))
+    # the captured gradients are the plain backward's gradients
+    pc2 = GaussianModel.from_arrays(arrs, sh_degree=sh_degree, device="cuda")
+    pc2.active_sh_degree = active
+    with torch.no_grad():
+        for a, b in zip(pc2.parameters(), before):
+            a.copy_(b)
+    out = render(cams[2], pc2, PipelineParams(), bg, sampling_offsets=offs)
+    (((out["render"] - tgt) ** 2).sum() + 0.1 * (out["depth"] ** 2).sum()).backward()
+    for a, g in zip(pc2.parameters(), opt.last_grads):
+        if a.numel() and a.grad.norm().item() > 1e-12:
+            assert rel_l2(g, a.grad) <= 1e-3
 
 
 def test_model_render_rejects_bad_inputs(built):

@@ -86,3 +86,46 @@ def export(tc: dict, fwd):
 def rel_l2(a, b):
     a, b = a.double().flatten(), b.double().flatten()
     return float((a - b).norm() / max(b.norm().item(), 1e-30))
+
+
+class CutMapping:
+    """Relation between the reference's per-tile blend lists (every tile of the radius rectangle,
+    rasterizer_impl.cu:70-113) and ours under the tile cut (wast3d_set_tile_cut(1)): ours must be the
+    reference's lists with some instances removed and the order of the rest preserved.  Raises
+    AssertionError otherwise.  All arrays are numpy; ranges are [T,2]."""
+
+    def __init__(self, ref_ranges, ref_pl, our_ranges, our_pl, P):
+        T = ref_ranges.shape[0]
+        assert our_ranges.shape[0] == T
+        rsz = (ref_ranges[:, 1].astype(np.int64) - ref_ranges[:, 0].astype(np.int64))
+        osz = (our_ranges[:, 1].astype(np.int64) - our_ranges[:, 0].astype(np.int64))
+        assert (rsz >= 0).all() and (osz >= 0).all() and (osz <= rsz).all()
+        assert rsz.sum() == len(ref_pl) and osz.sum() == len(our_pl)
+
+        def tile_major(ranges, sizes, pl):
+            tile = np.repeat(np.arange(T, dtype=np.int64), sizes)
+            first = np.cumsum(sizes) - sizes
+            pos = np.arange(len(pl), dtype=np.int64) - np.repeat(first, sizes) + np.repeat(ranges[:, 0].astype(np.int64), sizes)
+            return tile, pl.astype(np.int64)[pos], first
+
+        rt, rp, self.ref_first = tile_major(ref_ranges, rsz, ref_pl)
+        ot, op, _ = tile_major(our_ranges, osz, our_pl)
+        rk, ok = rt * int(P) + rp, ot * int(P) + op
+        assert len(np.unique(rk)) == len(rk)
+        self.kept = np.isin(rk, ok)
+        assert int(self.kept.sum()) == len(ok), "ours holds instances the reference does not"
+        assert np.array_equal(rk[self.kept], ok), "order of the kept instances differs from the reference's"
+        self.kept_prefix = np.concatenate([[0], np.cumsum(self.kept)]).astype(np.int64)
+        self.ref_sizes, self.our_sizes = rsz, osz
+
+    def map_n_contrib(self, n_ref, W, H):
+        """The reference's last-contributor positions (1-based, in ITS tile list) expressed in our lists.
+        Asserts that every last contributor survived the cut."""
+        n_ref = np.asarray(n_ref).astype(np.int64).reshape(H, W)
+        tx = (W + 15) // 16
+        yy, xx = np.mgrid[0:H, 0:W]
+        first = self.ref_first[(yy // 16) * tx + (xx // 16)]
+        has = n_ref > 0
+        assert self.kept[(first + n_ref - 1)[has]].all(), "a contributing instance was cut"
+        out = self.kept_prefix[first + n_ref] - self.kept_prefix[first]
+        return np.where(has, out, 0)

@@ -40,6 +40,14 @@ class AdamSegment(C.Structure):
                 ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int), ("reserved", C.c_int)]
 
 
+class AdamGroup(C.Structure):
+    """struct wast3d_adam_group (include/wast3d_b200.h)."""
+
+    _fields_ = [("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("lr", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int),
+                ("reserved", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol of include/wast3d_b200.h
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -52,9 +60,12 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_raster_backward_raw": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_raster_backward_raw_adam": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                             C.POINTER(AdamGroup), C.POINTER(_vp), _vp, _vp]),
     "wast3d_raster_export_state": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp]),
     "wast3d_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_set_tile_cut": (_i, [_i]),
     "wast3d_knn_scratch_bytes": (_sz, [_i]),
     "wast3d_knn_dist2": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wast3d_cluster_stats": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -186,6 +197,12 @@ class GrowBuffer:
                 return None
 
         self.cb = ALLOC_FN(_alloc)
+
+
+def set_tile_cut(mode: int) -> int:
+    """1 (default) = Gaussians are instantiated only in tiles that can see alpha >= 1/255; 0 = the
+    reference's radius rectangles (reproduces its num_rendered / point list).  Returns the old mode."""
+    return int(load().wast3d_set_tile_cut(int(mode)))
 
 
 def profile_slots() -> list:

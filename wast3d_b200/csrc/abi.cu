@@ -52,7 +52,7 @@ __global__ void export_geom_kernel(int P, const float4* __restrict__ rec,
                                    uint32_t* tiles_touched, unsigned char* clamped) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    const bool vis = tiles_touched_in[i] != 0;
+    const bool vis = (clamped_in[i] & 8u) != 0;  // bit 3: K1 wrote a render record (radius > 0)
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 r0 = vis ? rec[3 * i] : z, r1 = vis ? rec[3 * i + 1] : z, r2 = vis ? rec[3 * i + 2] : z;
     if (depths) depths[i] = r0.z;

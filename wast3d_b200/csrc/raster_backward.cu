@@ -23,6 +23,7 @@
 //  Summation order across pixels differs from the reference's atomics (both are unordered);
 //  gradients agree to fp32 rounding, not bitwise (tests state the tolerance per tensor).
 #include "raster_math.cuh"
+#include <cmath>
 #include <cstdlib>
 
 namespace w3d {
@@ -482,11 +483,80 @@ constexpr int GB_THREADS = 128;
 constexpr int GB_WARPS = GB_THREADS / 32;
 constexpr int GB_SH_STRIDE = 49;
 
+// Fused optimizer epilogue (ADAM = true, RAW only): the gradient of every leaf
+// element is consumed where it is produced — Adam (adam.cu's arithmetic = torch's single-tensor
+// update, scene/gaussian_model.py:154-163) is applied to the parameter in place, so the 236 B/Gaussian
+// of gradients are neither written to nor read back from HBM and the six optimizer launches disappear.
+// Valid because each parameter element is read (as a parameter) only by the warp that also updates it,
+// before the update.  Culled Gaussians take the zero-gradient update (their moments still decay), like
+// the dense torch.optim.Adam of the reference.
+struct AdamSlot {  // one GaussianModel parameter group
+    float* p;
+    float* m;
+    float* v;
+    float step_size, bc2_sqrt, one_minus_b1, b2, one_minus_b2, eps;
+};
+struct AdamFused {
+    AdamSlot g[6];  // xyz, f_dc, f_rest, opacity, scaling, rotation
+};
+__device__ __forceinline__ float adam_elem(float p, float g, float& m, float& v, const AdamSlot& s) {
+    m = m + s.one_minus_b1 * (g - m);
+    v = v * s.b2 + s.one_minus_b2 * g * g;
+    return p - s.step_size * (m / (sqrtf(v) / s.bc2_sqrt + s.eps));
+}
+template <int N>
+__device__ __forceinline__ void adam_small(const AdamSlot& s, size_t base, const float (&g)[N]) {
+    float p[N], m[N], v[N];
+#pragma unroll
+    for (int k = 0; k < N; ++k) { p[k] = s.p[base + k]; m[k] = s.m[base + k]; v[k] = s.v[base + k]; }
+#pragma unroll
+    for (int k = 0; k < N; ++k) p[k] = adam_elem(p[k], g[k], m[k], v[k], s);
+#pragma unroll
+    for (int k = 0; k < N; ++k) { s.p[base + k] = p[k]; s.m[base + k] = m[k]; s.v[base + k] = v[k]; }
+}
+// Adam over a warp's contiguous block of `total` elements whose gradients sit in shared memory
+__device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base, int total,
+                                                 const float* s_grad, float* g_out, int lane) {
+    float* P_ = s.p + base;
+    float* M_ = s.m + base;
+    float* V_ = s.v + base;
+    const bool vec = (total & 3) == 0 && ((((size_t)P_ | (size_t)M_ | (size_t)V_ | (size_t)s_grad) & 15) == 0) &&
+                     (g_out == nullptr || (((size_t)(g_out + base)) & 15) == 0);
+    if (vec) {
+        const int n4 = total >> 2;
+        for (int q = lane; q < n4; q += 32) {
+            const float4 g = *reinterpret_cast<const float4*>(s_grad + 4 * q);
+            float4 p = reinterpret_cast<float4*>(P_)[q];
+            float4 m = reinterpret_cast<float4*>(M_)[q];
+            float4 v = reinterpret_cast<float4*>(V_)[q];
+            p.x = adam_elem(p.x, g.x, m.x, v.x, s);
+            p.y = adam_elem(p.y, g.y, m.y, v.y, s);
+            p.z = adam_elem(p.z, g.z, m.z, v.z, s);
+            p.w = adam_elem(p.w, g.w, m.w, v.w, s);
+            reinterpret_cast<float4*>(P_)[q] = p;
+            reinterpret_cast<float4*>(M_)[q] = m;
+            reinterpret_cast<float4*>(V_)[q] = v;
+            if (g_out) reinterpret_cast<float4*>(g_out + base)[q] = g;
+        }
+    } else {
+        for (int q = lane; q < total; q += 32) {
+            const float g = s_grad[q];
+            float m = M_[q], v = V_[q];
+            P_[q] = adam_elem(P_[q], g, m, v, s);
+            M_[q] = m;
+            V_[q] = v;
+            if (g_out) g_out[base + q] = g;
+        }
+    }
+}
+
 // RAW: model-space inputs (wast3d_raster_params::raw_params): scales/rotations/SH arrive
 // un-activated, and the gradients written are those of the six GaussianModel leaves, i.e. this
 // kernel also does the autograd backward of exp / normalize / sigmoid / cat.  In RAW mode
 // dL_dsh is dL/d_features_dc [P,1,3] and dL_dsh_rest is dL/d_features_rest [P,M-1,3].
-template <bool RAW>
+// ADAM (RAW only): apply the optimizer update in place (AdamFused); the gradient outputs of the six
+// leaves become optional (non-NULL ones are still written: tests).
+template <bool RAW, bool ADAM>
 __global__ void __launch_bounds__(GB_THREADS)
 gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                          const int* __restrict__ radii, const float* __restrict__ shs,
@@ -502,7 +572,7 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                          float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
                          float* __restrict__ dL_dsh_rest,
                          float* __restrict__ dL_dscale, float* __restrict__ dL_drot,
-                         float* __restrict__ dL_dviewdepth_out) {
+                         float* __restrict__ dL_dviewdepth_out, const __grid_constant__ AdamFused af) {
     __shared__ __align__(16) float s_sh[GB_WARPS][32 * GB_SH_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
@@ -773,7 +843,15 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                 for (int e = RAW ? 3 : 0; e < row_floats; ++e) row[e] = 0.f;
             }
             __syncwarp();
-            if (RAW) {
+            if (RAW && ADAM) {
+                if (live) {
+                    adam_small<3>(af.g[1], 3 * (size_t)idx, dc_grad);
+                    if (dL_dsh) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
+                }
+                if (rest_floats > 0)
+                    adam_rows_linear(af.g[2], (size_t)warp_first * rest_floats, rows_valid * rest_floats, s_sh[warp],
+                                     dL_dsh_rest, lane);
+            } else if (RAW) {
                 if (live) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
                 if (rest_floats > 0)
                     unstage_rows_linear(dL_dsh_rest + (size_t)warp_first * rest_floats, rest_floats, rows_valid,
@@ -796,25 +874,39 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         dL_dcolor[3 * idx + 1] = g2.y;
         dL_dcolor[3 * idx + 2] = g2.z;
     }
+    float dopac = g1.y;
     if (RAW) {
         // sigmoid backward: d/dlogit = d/do * o (1 - o); o is the activated opacity of the record
         float o = 0.f;
         if (vis) o = rec[3 * (size_t)idx + 1].w;
-        dL_dopacity[idx] = g1.y * ((1.f - o) * o);
-    } else {
-        dL_dopacity[idx] = g1.y;
+        dopac = g1.y * ((1.f - o) * o);
     }
-    dL_dmean3D[3 * idx + 0] = dmean.x;
-    dL_dmean3D[3 * idx + 1] = dmean.y;
-    dL_dmean3D[3 * idx + 2] = dmean.z;
+    if (RAW && ADAM) {
+        const float gx[3] = {dmean.x, dmean.y, dmean.z};
+        const float go[1] = {dopac};
+        const float gs[3] = {dscale.x, dscale.y, dscale.z};
+        const float gr[4] = {drot.x, drot.y, drot.z, drot.w};
+        adam_small<3>(af.g[0], 3 * (size_t)idx, gx);
+        adam_small<1>(af.g[3], (size_t)idx, go);
+        adam_small<3>(af.g[4], 3 * (size_t)idx, gs);
+        adam_small<4>(af.g[5], 4 * (size_t)idx, gr);
+    }
+    if (!ADAM || dL_dopacity) dL_dopacity[idx] = dopac;
+    if (!ADAM || dL_dmean3D) {
+        dL_dmean3D[3 * idx + 0] = dmean.x;
+        dL_dmean3D[3 * idx + 1] = dmean.y;
+        dL_dmean3D[3 * idx + 2] = dmean.z;
+    }
     if (dL_dcov3D) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = dcov[k];
     }
-    dL_dscale[3 * idx + 0] = dscale.x;
-    dL_dscale[3 * idx + 1] = dscale.y;
-    dL_dscale[3 * idx + 2] = dscale.z;
-    *reinterpret_cast<float4*>(dL_drot + 4 * idx) = drot;
+    if (!ADAM || dL_dscale) {
+        dL_dscale[3 * idx + 0] = dscale.x;
+        dL_dscale[3 * idx + 1] = dscale.y;
+        dL_dscale[3 * idx + 2] = dscale.z;
+    }
+    if (!ADAM || dL_drot) *reinterpret_cast<float4*>(dL_drot + 4 * idx) = drot;
     if (dL_dconic_out) *reinterpret_cast<float4*>(dL_dconic_out + 4 * idx) = make_float4(g0.z, g0.w, 0.f, g1.x);
     if (dL_dviewdepth_out) dL_dviewdepth_out[idx] = g1.z;
 }
@@ -828,7 +920,8 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
                                 const float* dL_dpix, const float* dL_ddepth, float* dL_dmean2D,
                                 float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
                                 float* dL_dcov3D, float* dL_dsh, float* dL_dsh_rest, float* dL_dscale,
-                                float* dL_drot, float* dL_dcamViewDepth, cudaStream_t s) {
+                                float* dL_drot, float* dL_dcamViewDepth, cudaStream_t s,
+                                const AdamFused* adam = nullptr) {
     const int P = prm->P, W = prm->width, H = prm->height;
     const bool debug = prm->debug != 0;
     const size_t N = (size_t)W * H;
@@ -856,13 +949,15 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
         W3D_AFTER_LAUNCH(s, debug);
     }
     ProfScope ps_gb(PS_GAUSS_BWD, s);
-    auto gb = prm->raw_params ? gaussian_backward_kernel<true> : gaussian_backward_kernel<false>;
+    auto gb = prm->raw_params ? (adam ? gaussian_backward_kernel<true, true> : gaussian_backward_kernel<true, false>)
+                              : gaussian_backward_kernel<false, false>;
+    const AdamFused af = adam ? *adam : AdamFused{};
     gb<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, radii, prm->shs, prm->shs_rest, g.rec, g.clamped, prm->scales,
         prm->rotations, prm->scale_modifier, prm->cov3D_precomp, prm->viewmatrix, prm->projmatrix,
         prm->campos, focal_x, focal_y, prm->tan_fovx, prm->tan_fovy, g.grad_rec, dL_dmean2D, dL_dconic,
         dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dsh_rest, dL_dscale, dL_drot,
-        dL_dcamViewDepth);
+        dL_dcamViewDepth, af);
     W3D_AFTER_LAUNCH(s, debug);
     return WAST3D_OK;
 }
@@ -906,4 +1001,45 @@ extern "C" int wast3d_raster_backward_raw(const wast3d_raster_params* prm, int n
                                 dL_ddepth, dL_dmean2D, nullptr, dL_dopacity_logit, nullptr, dL_dxyz, nullptr,
                                 dL_dfeatures_dc, dL_dfeatures_rest, dL_dlog_scale, dL_drotation, nullptr,
                                 (cudaStream_t)stream_v);
+}
+
+extern "C" int wast3d_raster_backward_raw_adam(const wast3d_raster_params* prm, int num_rendered,
+                                               const int* radii, void* geom_buffer, void* binning_buffer,
+                                               void* img_buffer, const float* dL_dpix, const float* dL_ddepth,
+                                               const wast3d_adam_group* groups, float* const* grads_out,
+                                               float* dL_dmean2D, void* stream_v) {
+    int st = validate_params(prm, false);
+    if (st != WAST3D_OK) return st;
+    if (!prm->raw_params || !groups) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (prm->P == 0) return WAST3D_OK;
+    if (num_rendered < 0 || !geom_buffer || !img_buffer || !binning_buffer || !dL_dpix)
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    // the parameters updated are the tensors the forward read (same order as GaussianModel.training_setup)
+    const float* expect[6] = {prm->means3D, prm->shs, prm->shs_rest, prm->opacities, prm->scales, prm->rotations};
+    AdamFused af{};
+    for (int k = 0; k < 6; ++k) {
+        const wast3d_adam_group& h = groups[k];
+        const bool absent = (k == 2 && prm->M <= 1);
+        if (absent) continue;
+        if (!h.param || h.param != expect[k] || !h.exp_avg || !h.exp_avg_sq || h.step < 1)
+            return WAST3D_ERR_INVALID_ARGUMENT;
+        const double bc1 = 1.0 - pow((double)h.beta1, (double)h.step);
+        const double bc2 = 1.0 - pow((double)h.beta2, (double)h.step);
+        AdamSlot& d = af.g[k];
+        d.p = h.param;
+        d.m = h.exp_avg;
+        d.v = h.exp_avg_sq;
+        d.step_size = (float)((double)h.lr / bc1);
+        d.bc2_sqrt = (float)sqrt(bc2);
+        d.one_minus_b1 = 1.0f - h.beta1;
+        d.b2 = h.beta2;
+        d.one_minus_b2 = 1.0f - h.beta2;
+        d.eps = h.eps;
+    }
+    float* go[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (grads_out)
+        for (int k = 0; k < 6; ++k) go[k] = grads_out[k];
+    return raster_backward_impl(prm, num_rendered, radii, geom_buffer, binning_buffer, img_buffer, dL_dpix,
+                                dL_ddepth, dL_dmean2D, nullptr, go[3], nullptr, go[0], nullptr, go[1], go[2],
+                                go[4], go[5], nullptr, (cudaStream_t)stream_v, &af);
 }

@@ -20,6 +20,7 @@
 //    only visits survivors; warps retire independently (ballot) and the block leaves when all
 //    have (one __syncthreads_and per batch).
 #include "raster_math.cuh"
+#include <atomic>
 #include <cstdlib>
 
 namespace w3d {
@@ -108,7 +109,8 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   const float focal_x, const float focal_y, const dim3 grid,
                   const bool prefiltered, int* __restrict__ radii, float4* __restrict__ rec,
                   uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
-                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ flags) {
+                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ flags,
+                  const uint32_t* __restrict__ sample_bound_words, const bool cut_tiles) {
     __shared__ __align__(16) float s_sh[PRE_WARPS][32 * SH_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
@@ -122,6 +124,8 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     float3 p_view = make_float3(0.f, 0.f, 0.f);
     float2 point_image = make_float2(0.f, 0.f);
     float3 conic = make_float3(0.f, 0.f, 0.f);
+    float opac = 0.f;
+    float2 ext = make_float2(0.f, 0.f);
 
     if (live) {
         p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
@@ -165,6 +169,14 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                 if (n_tiles != 0) {
                     visible = true;
                     my_radius_i = (int)my_radius;
+                    opac = RAW ? act_sigmoid(opacities[idx]) : opacities[idx];
+                    ext = cutoff_extent(conic.x, conic.y, conic.z, opac);
+                    if (cut_tiles) {
+                        // only the tiles that hold a sample inside the alpha >= 1/255 box are instantiated
+                        tile_rect_cut(point_image, my_radius_i, ext.x, ext.y, load_sample_bounds(sample_bound_words),
+                                      rect_min, rect_max, grid);
+                        n_tiles = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
+                    }
                 }
             }
         }
@@ -204,14 +216,40 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     if (!live) return;
     radii[idx] = my_radius_i;
     tiles_touched[idx] = visible ? n_tiles : 0u;
-    clamped[idx] = (uint8_t)clamp_bits;
+    clamped[idx] = (uint8_t)(clamp_bits | (visible ? 8u : 0u));  // bit 3: render record written
     depth_key[idx] = visible ? __float_as_uint(p_view.z) : CULLED_KEY;
     if (visible) {
-        const float o = RAW ? act_sigmoid(opacities[idx]) : opacities[idx];
-        const float2 ext = cutoff_extent(conic.x, conic.y, conic.z, o);
         rec[3 * idx + 0] = make_float4(point_image.x, point_image.y, p_view.z, ext.x);
-        rec[3 * idx + 1] = make_float4(conic.x, conic.y, conic.z, o);
+        rec[3 * idx + 1] = make_float4(conic.x, conic.y, conic.z, opac);
         rec[3 * idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, ext.y);
+    }
+}
+
+// Bounds of the per-pixel sampling offsets (forward.cu:287 adds them to the pixel coordinate):
+// words[0..3] = float_order_key of max(ox), max(-ox), max(oy), max(-oy), accumulated with atomicMax
+// into zero-initialised words.  A NaN offset disables the tile cut (bounds become +inf).
+__global__ void __launch_bounds__(256)
+sample_bounds_kernel(size_t n_pix, const float* __restrict__ offs, uint32_t* __restrict__ words) {
+    const float inf = __int_as_float(0x7f800000);
+    float mx = -inf, nx = -inf, my = -inf, ny = -inf;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (size_t)gridDim.x * blockDim.x) {
+        const float2 o = *reinterpret_cast<const float2*>(offs + 2 * i);
+        if (!(o.x == o.x) || !(o.y == o.y)) mx = nx = my = ny = inf;
+        mx = fmaxf(mx, o.x); nx = fmaxf(nx, -o.x);
+        my = fmaxf(my, o.y); ny = fmaxf(ny, -o.y);
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        nx = fmaxf(nx, __shfl_xor_sync(0xffffffffu, nx, d));
+        my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, d));
+        ny = fmaxf(ny, __shfl_xor_sync(0xffffffffu, ny, d));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(words + 0, float_order_key(mx));
+        atomicMax(words + 1, float_order_key(nx));
+        atomicMax(words + 2, float_order_key(my));
+        atomicMax(words + 3, float_order_key(ny));
     }
 }
 
@@ -242,7 +280,8 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
                       const uint32_t* __restrict__ tiles_touched, const int* __restrict__ radii,
                       const float4* __restrict__ rec, uint32_t* __restrict__ keys,
                       uint32_t* __restrict__ vals, uint32_t* __restrict__ tile_count, const dim3 grid,
-                      const int num_tiles, const bool smem_hist) {
+                      const int num_tiles, const bool smem_hist,
+                      const uint32_t* __restrict__ sample_bound_words, const bool cut_tiles) {
     extern __shared__ uint32_t s_count[];
     if (smem_hist) {
         for (int t = threadIdx.x; t < num_tiles; t += EMIT_THREADS) s_count[t] = 0;
@@ -262,7 +301,11 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
             if (n != 0) {
                 const float4 r0 = rec[3 * (size_t)id];
                 uint2 rect_min, rect_max;
-                tile_rect(make_float2(r0.x, r0.y), radii[id], rect_min, rect_max, grid);
+                if (cut_tiles)  // the same rectangle K1 counted (same inputs, same arithmetic)
+                    tile_rect_cut(make_float2(r0.x, r0.y), radii[id], r0.w, rec[3 * (size_t)id + 2].w,
+                                  load_sample_bounds(sample_bound_words), rect_min, rect_max, grid);
+                else
+                    tile_rect(make_float2(r0.x, r0.y), radii[id], rect_min, rect_max, grid);
                 xy0 = rect_min.x | (rect_min.y << 16);
                 w = rect_max.x - rect_min.x;
             }
@@ -513,6 +556,21 @@ static int sort_mode(SortStage stage) {
     return stage == STAGE_DEPTH ? 1 : 0;
 }
 
+// Tile cut (tile_rect_cut, raster_math.cuh): 1 = instantiate a Gaussian only in the tiles that can see
+// alpha >= 1/255 (default), 0 = the reference's full radius rectangles (auxiliary.h:46-56), which
+// reproduces the reference's num_rendered and point list bit for bit.  WAST3D_TILE_CUT=0|1 sets the
+// initial value; wast3d_set_tile_cut() changes it at run time (tests, A/B measurements).
+static std::atomic<int> g_tile_cut{-1};
+static int tile_cut_mode() {
+    int m = g_tile_cut.load();
+    if (m < 0) {
+        const char* e = getenv("WAST3D_TILE_CUT");
+        m = (e && atoi(e) == 0) ? 0 : 1;
+        g_tile_cut.store(m);
+    }
+    return m;
+}
+
 static int tile_sort_passes(uint32_t num_tiles, int* bits_per_pass) {
     const int bits = bits_for(num_tiles);
     const int passes = (bits + 7) / 8;
@@ -587,14 +645,21 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
     const float focal_x = W / (2.0f * prm->tan_fovx);
 
     W3D_CUDA_TRY(cudaMemsetAsync(g.totals, 0, 32 * sizeof(uint32_t), s));
+    const bool cut_tiles = tile_cut_mode() != 0;
+    uint32_t* sample_bound_words = g.totals + 8;  // zero = no offsets
     {
     ProfScope ps(PS_PREPROCESS, s);
+    if (cut_tiles && prm->sampling_offsets != nullptr) {
+        sample_bounds_kernel<<<148 * 2, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
+        W3D_AFTER_LAUNCH(s, debug);
+    }
     auto pre = prm->raw_params ? preprocess_kernel<true> : preprocess_kernel<false>;
     pre<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, prm->scales, prm->scale_modifier, prm->rotations,
         prm->opacities, prm->shs, prm->shs_rest, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
         prm->projmatrix, prm->campos, W, H, prm->tan_fovx, prm->tan_fovy, focal_x, focal_y, grid,
-        prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.totals + 1);
+        prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.totals + 1,
+        sample_bound_words, cut_tiles);
     W3D_AFTER_LAUNCH(s, debug);
     }
 
@@ -673,7 +738,7 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         if (blocks > (n_chunks + 7) / 8) blocks = (n_chunks + 7) / 8;
         emit_instances_kernel<<<blocks, EMIT_THREADS, smem, s>>>(P, g.order_a, g.offsets, g.tiles_touched, radii,
                                                                g.rec, bn.keys_a, bn.vals_a, im.tile_count, grid,
-                                                               (int)num_tiles, smem_hist);
+                                                               (int)num_tiles, smem_hist, sample_bound_words, cut_tiles);
         W3D_AFTER_LAUNCH(s, debug);
         }
         ProfScope* pts = new ProfScope(PS_TILE_SORT, s);
@@ -716,6 +781,12 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
                                                     im.n_contrib, out_color, out_depth);
     W3D_AFTER_LAUNCH(s, debug);
     return WAST3D_OK;
+}
+
+extern "C" int wast3d_set_tile_cut(int mode) {
+    const int prev = tile_cut_mode();
+    if (mode == 0 || mode == 1) g_tile_cut.store(mode);
+    return prev;
 }
 
 extern "C" int wast3d_mark_visible(int P, const float* means3D, const float* viewmatrix,

@@ -71,6 +71,68 @@ __device__ __forceinline__ void tile_rect(const float2 p, int max_radius, uint2&
                 min(grid.y, (unsigned)max((int)0, (int)((p.y + max_radius + TILE_Y - 1) / TILE_Y)))};
 }
 
+// ---- tile rectangle restricted to the alpha >= 1/255 region ------------------------------------
+// The reference instantiates a Gaussian in every tile of the square of side 2*radius around its
+// centre (tile_rect above) although alpha = o*exp(power) can reach 1/255 (forward.cu:355) only inside
+// the ellipse power >= -ln(255 o), whose axis-aligned bounding box [p - ext, p + ext] is stored in the
+// render record (cutoff_extent, raster_forward.cu).  Instances in tiles whose SAMPLE positions
+// (pixel + sampling offset, forward.cu:287) all lie outside that box are skipped by every pixel of
+// the tile in forward and backward alike, so they are never created: the blend order of the
+// remaining instances, the image and the gradients are unchanged; num_rendered shrinks.
+// `sb` = bounds of the sampling offsets over the image: {min ox, max ox, min oy, max oy}.
+struct SampleBounds { float min_x, max_x, min_y, max_y; };
+
+// ordered-uint encoding of a float (monotone; 0 is below every float, used with atomicMax on a
+// zero-initialised word)
+__device__ __forceinline__ uint32_t float_order_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_key(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+// words[0..3] = order keys of max(ox), max(-ox), max(oy), max(-oy); all-zero words (no offsets
+// tensor) decode to zero offsets.
+__device__ __forceinline__ SampleBounds load_sample_bounds(const uint32_t* __restrict__ words) {
+    SampleBounds b;
+    const uint32_t k0 = words[0], k1 = words[1], k2 = words[2], k3 = words[3];
+    b.max_x = k0 ? float_from_order_key(k0) : 0.f;
+    b.min_x = k1 ? -float_from_order_key(k1) : 0.f;
+    b.max_y = k2 ? float_from_order_key(k2) : 0.f;
+    b.min_y = k3 ? -float_from_order_key(k3) : 0.f;
+    return b;
+}
+
+__device__ __forceinline__ void tile_rect_cut(const float2 p, int max_radius, float ext_x, float ext_y,
+                                              const SampleBounds sb, uint2& rect_min, uint2& rect_max,
+                                              const dim3 grid) {
+    tile_rect(p, max_radius, rect_min, rect_max, grid);
+    if (ext_x < 0.f || ext_y < 0.f) {  // opacity < 1/255: alpha never reaches the threshold
+        rect_max = rect_min;
+        return;
+    }
+    // tile column tx holds samples with x in [16 tx + min_ox, 16 tx + 15 + max_ox]; it can be skipped
+    // when that interval misses [p.x - ext_x, p.x + ext_x].  pad: fp32 rounding of the sums below.
+    const float pad_x = 0.01f + 2e-6f * (fabsf(p.x) + ext_x);
+    const float pad_y = 0.01f + 2e-6f * (fabsf(p.y) + ext_y);
+    float lo_x = (p.x - ext_x - pad_x - (float)(TILE_X - 1) - sb.max_x) * (1.0f / TILE_X);
+    float hi_x = (p.x + ext_x + pad_x - sb.min_x) * (1.0f / TILE_X);
+    float lo_y = (p.y - ext_y - pad_y - (float)(TILE_Y - 1) - sb.max_y) * (1.0f / TILE_Y);
+    float hi_y = (p.y + ext_y + pad_y - sb.min_y) * (1.0f / TILE_Y);
+    // clamp in float first (inf extents / NaN centres fall back to the reference rectangle)
+    lo_x = fminf(fmaxf(ceilf(lo_x), (float)rect_min.x), (float)rect_max.x);
+    lo_y = fminf(fmaxf(ceilf(lo_y), (float)rect_min.y), (float)rect_max.y);
+    hi_x = fmaxf(fminf(floorf(hi_x) + 1.0f, (float)rect_max.x), (float)rect_min.x);
+    hi_y = fmaxf(fminf(floorf(hi_y) + 1.0f, (float)rect_max.y), (float)rect_min.y);
+    const uint32_t x0 = (uint32_t)lo_x, x1 = (uint32_t)hi_x, y0 = (uint32_t)lo_y, y1 = (uint32_t)hi_y;
+    if (x1 <= x0 || y1 <= y0) {
+        rect_max = rect_min;
+        return;
+    }
+    rect_min = {x0, y0};
+    rect_max = {x1, y1};
+}
+
 // Rotation matrix from the quaternion AS GIVEN (r,x,y,z) — not normalised (forward.cu:127).
 __device__ __forceinline__ M3 quat_to_R(const float4 q) {
     const float r = q.x, x = q.y, y = q.z, z = q.w;

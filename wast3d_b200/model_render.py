@@ -82,6 +82,32 @@ class _RasterizeModel(torch.autograd.Function):
             g_depth = torch.zeros((H, W), dtype=torch.float32, device=dev)
         opt = dict(dtype=torch.float32, device=dev)
         sink, sunk = ctx.grad_sink, None
+        fused_opt = getattr(sink, "fused_adam", None) if sink is not None else None
+        if fused_opt is not None:
+            # optimizer-in-backward (optim.BackwardFusedAdam): K8+K9 applies the Adam update in place
+            if not sink.fresh:
+                raise RuntimeError("BackwardFusedAdam: a second backward through render() before optimizer.step() / "
+                                   "zero_grad() is not supported (the update was already applied)")
+            d_m2d = torch.empty((P, 3), **opt) if ctx.needs_input_grad[1] else None
+            if P:
+                keep: list = []
+                prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation,
+                           offsets if offsets.numel() else None)
+                groups = fused_opt.adam_groups(list(ctx.sink_params))
+                grads_out = None
+                if fused_opt.capture_grads:  # test hook: also write the leaf gradients
+                    fused_opt.last_grads = [torch.empty_like(t) for t in ctx.sink_params]
+                    grads_out = (C.c_void_p * 6)(*[t.data_ptr() if t.numel() else None for t in fused_opt.last_grads])
+                with torch.cuda.device(dev):
+                    st = lib.wast3d_raster_backward_raw_adam(
+                        C.byref(prm), int(ctx.num_rendered), _lib.fptr(radii, keep, torch.int32),
+                        _lib.fptr(geom, keep, torch.uint8), _lib.fptr(binning, keep, torch.uint8),
+                        _lib.fptr(img, keep, torch.uint8), _lib.fptr(g_color, keep), _lib.fptr(g_depth, keep),
+                        groups, grads_out, d_m2d.data_ptr() if d_m2d is not None else None, _lib.stream_ptr())
+                _lib.check(st, "rasterize_model_backward_adam")
+            fused_opt._applied = True
+            sink.fresh = False
+            return None, d_m2d, None, None, None, None, None, None, None, None
         if sink is not None and sink.fresh:
             sunk = [sink.view_for(p) for p in ctx.sink_params]
             if any(v is None for v in sunk):

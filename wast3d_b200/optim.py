@@ -1,6 +1,10 @@
 """Fused Adam (csrc/adam.cu) with torch.optim.Adam's interface for the reference's six
 parameter groups (scene/gaussian_model.py:154-163).  One kernel per parameter tensor, one pass
-over (param, grad, exp_avg, exp_avg_sq); same update rule as torch's single-tensor Adam."""
+over (param, grad, exp_avg, exp_avg_sq); same update rule as torch's single-tensor Adam.
+
+`BackwardFusedAdam` goes one step further: the rasteriser's per-Gaussian backward
+kernel applies the update itself (wast3d_raster_backward_raw_adam), so the leaf gradients never touch HBM
+and optimizer.step() has nothing left to launch."""
 from __future__ import annotations
 
 import torch
@@ -62,3 +66,73 @@ class FusedAdam(torch.optim.Optimizer):
             for p in group["params"]:
                 self.step_range(p)
         return loss
+
+
+class AdamInBackwardSink:
+    """Handed to model_render.rasterize_model as `grad_sink`: tells the rasteriser's backward to apply
+    the optimizer update in its per-Gaussian kernel.  `fresh` is True until the first backward after
+    zero_grad(); a second backward in the same optimizer step is refused (its gradients would have to be
+    summed with the first one's before the update)."""
+
+    def __init__(self, optimizer):
+        self.fused_adam = optimizer
+        self.fresh = True
+
+    def view_for(self, p):  # peer.GradSink interface: no gradient storage here
+        return None
+
+
+class BackwardFusedAdam(FusedAdam):
+    """FusedAdam whose update is applied inside the rasteriser's backward kernel.
+
+    Requirements: exactly the six GaussianModel leaves, one per group, in training_setup()'s order
+    (xyz, f_dc, f_rest, opacity, scaling, rotation); one render()+backward() per step(); one GPU (the
+    backward must carry the step's whole gradient).  step() only finishes the bookkeeping; if the
+    gradients arrived through plain autograd instead (p.grad set), it falls back to FusedAdam's dense
+    kernels over those gradients — same arithmetic, two more passes over HBM."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, lr=lr, betas=betas, eps=eps)
+        if len(self.param_groups) != 6 or any(len(g["params"]) != 1 for g in self.param_groups):
+            raise ValueError("BackwardFusedAdam: expected the six GaussianModel parameter groups, one tensor each")
+        self.grad_sink = AdamInBackwardSink(self)
+        self._applied = False
+        self.capture_grads = False  # test hook: keep the leaf gradients of the last backward in .last_grads
+        self.last_grads = None
+
+    @torch.no_grad()
+    def adam_groups(self, leaves):
+        """ctypes array of wast3d_adam_group for this update (advances the step counts)."""
+        mine = [g["params"][0] for g in self.param_groups]
+        if len(leaves) != 6 or any(a is not b for a, b in zip(mine, leaves)):
+            raise RuntimeError("BackwardFusedAdam: the rasterised tensors are not this optimizer's parameters "
+                               "(order: xyz, f_dc, f_rest, opacity, scaling, rotation)")
+        arr = (_lib.AdamGroup * 6)()
+        for k, (group, p) in enumerate(zip(self.param_groups, mine)):
+            _lib.require_device(p)
+            if p.dtype != torch.float32 or not p.is_contiguous():
+                raise RuntimeError("BackwardFusedAdam: parameters must be contiguous float32")
+            st = self.state[p]
+            if not st:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+            st["step"] += 1
+            b1, b2 = group["betas"]
+            ptr = lambda t: t.data_ptr() if t.numel() else None
+            arr[k] = _lib.AdamGroup(ptr(p), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), float(group["lr"]), float(b1),
+                                    float(b2), float(group["eps"]), int(st["step"]), 0)
+        return arr
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise RuntimeError("BackwardFusedAdam: closures are not supported")
+        if self._applied:
+            self._applied = False
+            return None
+        return super().step()
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=set_to_none)
+        self.grad_sink.fresh = True

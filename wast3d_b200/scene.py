@@ -293,11 +293,13 @@ class GaussianModel:
         self._opacity = nn.Parameter(opacities.requires_grad_(True))
 
     def training_setup(self, training_args: OptimizationParams = OptimizationParams(), fused: bool = False,
-                       peer: bool = False, group=None, average: bool = True):
+                       peer: bool = False, group=None, average: bool = True, in_backward: bool = False):
         """Adam with the reference's six groups (scene/gaussian_model.py:154-163).
         `fused=True` swaps torch.optim.Adam for the library's fused Adam kernel (same maths);
         `peer=True` for the view-parallel single-kernel optimizer over NVLink peer memory
-        (peer.PeerShardedAdam; parameters move into its arena, render() writes gradients there)."""
+        (peer.PeerShardedAdam; parameters move into its arena, render() writes gradients there);
+        `in_backward=True` (single GPU) applies the update inside the rasteriser's backward kernel
+        (optim.BackwardFusedAdam): no gradient tensors, optimizer.step() launches nothing."""
         a = training_args
         groups = [
             {"params": [self._xyz], "lr": a.position_lr_init * self.spatial_lr_scale, "name": "xyz"},
@@ -311,6 +313,10 @@ class GaussianModel:
         if peer:
             from .peer import PeerShardedAdam
             self.optimizer = PeerShardedAdam(groups, lr=0.0, eps=1e-15, group=group, average=average)
+            self.grad_sink = self.optimizer.grad_sink
+        elif in_backward:
+            from .optim import BackwardFusedAdam
+            self.optimizer = BackwardFusedAdam(groups, lr=0.0, eps=1e-15)
             self.grad_sink = self.optimizer.grad_sink
         elif fused:
             from .optim import FusedAdam
