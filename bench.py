@@ -51,10 +51,12 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="pixel losses (L1 + TV + depth L2) through the fused kernels of csrc/loss.cu or as torch expressions")
-    ap.add_argument("--sync", default="auto", choices=["auto", "peer", "nccl"],
+    ap.add_argument("--sync", default="auto", choices=["auto", "peer", "nccl", "backward"],
                     help="optimizer step: 'peer' = one fused reduce+Adam+broadcast kernel over NVLink peer memory "
                          "(peer.PeerShardedAdam), 'nccl' = chunked NCCL all-reduce overlapped with the dense fused Adam "
-                         "(with one GPU: just the dense fused Adam); 'auto' = peer with N > 1, dense with N = 1")
+                         "(with one GPU: just the dense fused Adam); 'backward' (one GPU only) = the Adam update applied by the "
+                         "rasteriser's per-Gaussian backward kernel, leaf gradients never written (optim.BackwardFusedAdam); "
+                         "'auto' = peer with N > 1, backward with N = 1")
     ap.add_argument("--tile-cut", type=int, default=1, choices=[0, 1],
                     help="1 = instantiate Gaussians only in tiles that can see alpha >= 1/255 (default), "
                          "0 = the reference's radius rectangles")
@@ -275,13 +277,20 @@ def main():
     _lib.load()
     _lib.set_tile_cut(args.tile_cut)
     if args.sync == "auto":
-        args.sync = "peer" if world > 1 else "nccl"
+        args.sync = "peer" if world > 1 else "backward"
+    if args.sync == "backward" and world > 1:
+        raise SystemExit("--sync backward needs the whole gradient in one backward: single GPU only")
 
     torch.manual_seed(0)
     arrs = synthetic_gaussians(spec.P, seed=0, garden=spec.garden, log_scale_mu=spec.log_scale_mu)
     pc = GaussianModel.from_arrays(arrs, sh_degree=3, device=dev)
     pc.spatial_lr_scale = 5.0
-    opt = pc.training_setup(peer=True, average=True) if args.sync == "peer" else pc.training_setup(fused=True)
+    if args.sync == "peer":
+        opt = pc.training_setup(peer=True, average=True)
+    elif args.sync == "backward":
+        opt = pc.training_setup(in_backward=True)
+    else:
+        opt = pc.training_setup(fused=True)
     if args.sync == "peer":
         PEER_BACKEND[0] = opt.buffer.backend + ("+multicast" if opt.multicast else "")
     cams = scene_cameras(spec, 8, device=dev)
@@ -347,9 +356,10 @@ def main():
         loss.backward()
         if host_io:
             stage_free[k].record(main)
-        if args.sync == "peer":
-            # one kernel: sum the N gradient replicas of this rank's shard over NVLink, Adam, store the new
-            # parameters into every replica (gradients were written into the peer arena by the backward)
+        if args.sync in ("peer", "backward"):
+            # peer: one kernel sums the N gradient replicas of this rank's shard over NVLink, applies Adam and
+            # stores the new parameters into every replica (gradients were written into the peer arena by the
+            # backward); backward: K8+K9 already applied the update, step() only closes the bookkeeping
             opt.step()
         else:
             # N > 1: chunked in-place NCCL all-reduce (AVG) overlapped with the per-chunk Adam update

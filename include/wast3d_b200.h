@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define WAST3D_ABI_VERSION 3
+#define WAST3D_ABI_VERSION 4
 
 enum wast3d_status {
     WAST3D_OK = 0,
@@ -212,6 +212,65 @@ int wast3d_cdist_topk(int Na, int Nb, const float* a, const float* b, int k, flo
  * (optional) is the column matched to row i, the plan is P/n.  1 <= n <= 1023. */
 int wast3d_emd2_uniform(int n, const float* xa, const float* xb, float* out_cost, int32_t* out_perm,
                         void* stream);
+
+/* wast3d_kmeans_lloyd: Lloyd's K-Means on 3-D points from a given initialisation — replaces
+ * `sklearn.cluster.KMeans(n_clusters=K, n_init=.., max_iter=..).fit_predict(xyz)` of
+ * aux_save_clusters_clean.py:32-47 / train_st.py:54-70 (scikit-learn is an un-vendored, unpinned dependency
+ * whose default k-means++ initialisation is unseeded in the reference; the caller supplies `centers` [K,3]
+ * initialised with the rows it chose and gets the final centres back).  Every iteration is an E-step
+ * (labels[i] = argmin_j cdist(points, centers)[i,j] exactly as wast3d_nn_match decides it, ties to the lowest j)
+ * and an M-step (centre = mean of its members, accumulated in double; an empty cluster keeps its centre).
+ * Stops after max_iter M-steps, when no label changed, or when the summed squared centre shift of the last
+ * M-step is <= tol (absolute; sklearn's `tol` is relative: pass tol_sklearn * mean(var(points, axis=0))); the
+ * returned labels always come from an E-step against the returned centres.
+ * Host outputs (optional): inertia = sum_i |x_i - c_label(i)|^2, number of M-steps done, last shift. */
+int wast3d_kmeans_lloyd(int n, int K, const float* points, float* centers, int32_t* labels, int max_iter,
+                        double tol, double* out_inertia_host, int* out_n_iter_host, double* out_shift_host,
+                        void* stream);
+
+/* Sparse pairwise-distance terms.  A "pair" is (row i, neighbour j):
+ *   d[i,j] = row_scale[i] * dist(a[center ? center[i] : i, 0:3], b[idx[i,j], 0:3]),  i < n, j < k
+ * formula 0: dist = sqrt((dx^2+dy^2)+dz^2) — `torch.norm(X_nns[:,1:] - X_nns[:,0].unsqueeze(1), dim=-1)` of
+ *            get_descriptors (notebooks/25.4.Optimize_with_SAM_masks_clean.ipynb cell 72) with
+ *            a = b = X, center = idx_full[:,0], idx = idx_full[:,1:];
+ * formula 1: dist = sqrt(max(0, |a|^2 + |b|^2 - 2 a.b)) in torch.cdist's matmul-path order (the entries of
+ *            `torch.cdist(A, xyz)` at aux_optimize_cluster_D_W_distance.py:253-256), center = NULL.
+ * a and b are row-strided (lda, ldb floats per row, >= 3) so that `_rotation[:, :-1]` / `[:, 1:]` views
+ * are passed without a copy.  center, row_scale may be NULL. */
+typedef struct wast3d_pair_args {
+    long long n;
+    int k;
+    int formula;
+    const float* a;
+    int lda;
+    const float* b;
+    int ldb;
+    const int32_t* center;   /* [n] or NULL   */
+    const int32_t* idx;      /* [n,k]         */
+    const float* row_scale;  /* [n] or NULL   */
+    const float* a2;         /* optional second a operand (same rows as a): d = dist(a,b) + dist(a2,b) — the  */
+    int lda2;                /* rotation term cdist(rot[:, :-1], xyz) + cdist(rot[:, 1:], xyz) of :254-255     */
+} wast3d_pair_args;
+/* out_d [n,k].  backward: grad_d [n,k] -> grad_a [rows of a, 3], grad_b [rows of b, 3], dense, ACCUMULATED
+ * (zero-fill them first; any may be NULL; grad_a2 [rows of a2, 3] only with a2; grad_a and grad_b may be the same
+ * buffer when a == b): g * (a-b)/d, 0 at d == 0
+ * like torch's norm / cdist backward.  Sums use unordered float atomics. */
+int wast3d_pair_dist_forward(const wast3d_pair_args* args, float* out_d, void* stream);
+int wast3d_pair_dist_backward(const wast3d_pair_args* args, const float* grad_d, float* grad_a, float* grad_a2,
+                              float* grad_b, void* stream);
+/* Fused loss over the pairs: loss = scale * sum_{i,j} weight[i,j] * rho(d[i,j] - target[i,j]), rho = |.| (mode 0)
+ * or (.)^2 (mode 1); weight NULL = 1.  With the kNN mask of the target scene as (idx, weight) and
+ * scale = 1/(n * rows_of_b) this is `torch.mean(torch.abs(D - D_target) * D_xyz_target_mask)`
+ * (aux_optimize_cluster_D_W_distance.py:278-280) without any N x N matrix; with mode 1 and scale = 1/(n k) it is
+ * `torch.mean(torch.square(descriptors - target))` (notebooks/25.4 cell 72).  The value is reduced in a fixed
+ * order (deterministic).  scratch: wast3d_pair_loss_scratch_bytes() bytes, zero-filled once, reusable on the
+ * same stream.  backward: grad_out DEVICE scalar or NULL (= 1); grad_a / grad_b as above. */
+size_t wast3d_pair_loss_scratch_bytes(void);
+int wast3d_pair_loss_forward(const wast3d_pair_args* args, const float* target, const float* weight, int mode,
+                             double scale, void* scratch, float* out_loss, void* stream);
+int wast3d_pair_loss_backward(const wast3d_pair_args* args, const float* target, const float* weight, int mode,
+                              double scale, const float* grad_out, float* grad_a, float* grad_a2, float* grad_b,
+                              void* stream);
 
 /* wast3d_w2_match: content clusters (mean_c [Kc,3], cov_c [Kc,6]) against style clusters
  * (mean_s [Ks,3], cov_s [Ks,6]): out_idx[i] = argmin_j W2^2(N(mc_i,Sc_i), N(ms_j,Ss_j)),

@@ -48,6 +48,14 @@ class AdamGroup(C.Structure):
                 ("reserved", C.c_int)]
 
 
+class PairArgs(C.Structure):
+    """struct wast3d_pair_args (include/wast3d_b200.h)."""
+
+    _fields_ = [("n", C.c_longlong), ("k", C.c_int), ("formula", C.c_int), ("a", C.c_void_p), ("lda", C.c_int),
+                ("b", C.c_void_p), ("ldb", C.c_int), ("center", C.c_void_p), ("idx", C.c_void_p),
+                ("row_scale", C.c_void_p), ("a2", C.c_void_p), ("lda2", C.c_int)]
+
+
 # name -> (restype, argtypes); every symbol of include/wast3d_b200.h
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
@@ -85,6 +93,13 @@ SIGNATURES = {
     "wast3d_pixel_loss_scratch_bytes": (_sz, []),
     "wast3d_pixel_loss_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp]),
     "wast3d_pixel_loss_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "wast3d_kmeans_lloyd": (_i, [_i, _i, _vp, _vp, _vp, _i, C.c_double, C.POINTER(C.c_double), C.POINTER(_i),
+                                 C.POINTER(C.c_double), _vp]),
+    "wast3d_pair_dist_forward": (_i, [C.POINTER(PairArgs), _vp, _vp]),
+    "wast3d_pair_dist_backward": (_i, [C.POINTER(PairArgs), _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_pair_loss_scratch_bytes": (_sz, []),
+    "wast3d_pair_loss_forward": (_i, [C.POINTER(PairArgs), _vp, _vp, _i, C.c_double, _vp, _vp, _vp]),
+    "wast3d_pair_loss_backward": (_i, [C.POINTER(PairArgs), _vp, _vp, _i, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_peer_flag_bytes": (_sz, []),
     "wast3d_peer_adam_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _i, _f, C.c_uint,
                                    C.c_double, _vp]),

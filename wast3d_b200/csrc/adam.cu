@@ -4,23 +4,21 @@
 // Arithmetic follows torch's single-tensor Adam update:
 //   m = m + (1-b1) (g - m);  v = b2 v + (1-b2) g g;
 //   p = p - (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+// (adam_update in common.cuh: m, v exact; sqrt and quotient through the SFU, update term within 4 ulp)
 #include "common.cuh"
 
 namespace w3d {
 
 __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, float one_minus_b1,
                                          float b2, float one_minus_b2, float step_size,
-                                         float bc2_sqrt, float eps) {
-    m = m + one_minus_b1 * (g - m);
-    v = v * b2 + one_minus_b2 * g * g;
-    const float denom = sqrtf(v) / bc2_sqrt + eps;
-    p = p - step_size * (m / denom);
+                                         float inv_bc2_sqrt, float eps) {
+    p = adam_update(p, g, m, v, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps);
 }
 
 __global__ void __launch_bounds__(256)
 adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
             float* __restrict__ v, float one_minus_b1, float b2, float one_minus_b2,
-            float step_size, float bc2_sqrt, float eps, bool vec_ok) {
+            float step_size, float inv_bc2_sqrt, float eps, bool vec_ok) {
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     size_t done = 0;
@@ -32,16 +30,16 @@ adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float*
         float4* v4 = reinterpret_cast<float4*>(v);
         for (size_t i = tid; i < n4; i += stride) {
             float4 pp = p4[i], gg = g4[i], mm = m4[i], vv = v4[i];
-            adam_one(pp.x, gg.x, mm.x, vv.x, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps);
-            adam_one(pp.y, gg.y, mm.y, vv.y, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps);
-            adam_one(pp.z, gg.z, mm.z, vv.z, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps);
-            adam_one(pp.w, gg.w, mm.w, vv.w, one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps);
+            adam_one(pp.x, gg.x, mm.x, vv.x, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps);
+            adam_one(pp.y, gg.y, mm.y, vv.y, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps);
+            adam_one(pp.z, gg.z, mm.z, vv.z, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps);
+            adam_one(pp.w, gg.w, mm.w, vv.w, one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps);
             p4[i] = pp; m4[i] = mm; v4[i] = vv;
         }
         done = n4 * 4;
     }
     for (size_t i = done + tid; i < n; i += stride)
-        adam_one(p[i], g[i], m[i], v[i], one_minus_b1, b2, one_minus_b2, step_size, bc2_sqrt, eps);
+        adam_one(p[i], g[i], m[i], v[i], one_minus_b1, b2, one_minus_b2, step_size, inv_bc2_sqrt, eps);
 }
 
 }  // namespace w3d
@@ -52,17 +50,15 @@ extern "C" int wast3d_adam_step(size_t n, float* param, const float* grad, float
     if (n == 0) return WAST3D_OK;
     if (!param || !grad || !exp_avg || !exp_avg_sq || step < 1) return WAST3D_ERR_INVALID_ARGUMENT;
     cudaStream_t s = (cudaStream_t)stream_v;
-    const double bc1 = 1.0 - pow((double)beta1, (double)step);
-    const double bc2 = 1.0 - pow((double)beta2, (double)step);
-    const float step_size = (float)((double)lr / bc1);
-    const float bc2_sqrt = (float)sqrt(bc2);
+    const w3d::AdamScalars sc = w3d::adam_scalars(lr, beta1, beta2, step);
     const bool vec_ok = ((((size_t)param | (size_t)grad | (size_t)exp_avg | (size_t)exp_avg_sq) & 15) == 0);
     size_t blocks = (n / 4 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 16) blocks = 148 * 16;
     w3d::ProfScope ps(w3d::PS_ADAM, s);
-    w3d::adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, param, grad, exp_avg, exp_avg_sq, 1.0f - beta1,
-                                                      beta2, 1.0f - beta2, step_size, bc2_sqrt, eps, vec_ok);
+    w3d::adam_kernel<<<(unsigned)blocks, 256, 0, s>>>(n, param, grad, exp_avg, exp_avg_sq, sc.one_minus_b1,
+                                                      sc.b2, sc.one_minus_b2, sc.step_size, sc.inv_bc2_sqrt, eps,
+                                                      vec_ok);
     W3D_AFTER_LAUNCH(s, false);
     return WAST3D_OK;
 }

@@ -7,9 +7,64 @@
 #include <cstddef>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <cstdlib>
+#include <cmath>
 #include "../../include/wast3d_b200.h"
 
 namespace w3d {
+
+// Hyper-parameters cross the C ABI as float, but torch.optim.Adam derives 1-beta, beta^t and lr/(1-beta1^t)
+// from the Python double the user wrote (0.999, not 0.999f = 0.99900001287...): 1.0f - 0.999f is off by
+// 1.3e-5 relative from torch's (float)(1 - 0.999).  as_written() returns the double with the shortest
+// decimal representation that still rounds to `f` (what `repr(numpy.float32(f))` prints), i.e. the
+// literal the caller passed in every practical case.
+inline double as_written(float f) {
+    if (!(f == f) || f == 0.0f) return (double)f;
+    char buf[40];
+    for (int prec = 1; prec <= 9; ++prec) {
+        snprintf(buf, sizeof buf, "%.*g", prec, (double)f);
+        const double d = strtod(buf, nullptr);
+        if ((float)d == f) return d;
+    }
+    return (double)f;
+}
+struct AdamScalars {
+    float step_size, inv_bc2_sqrt, one_minus_b1, b2, one_minus_b2;
+};
+inline AdamScalars adam_scalars(float lr, float beta1, float beta2, int step) {
+    const double b1 = as_written(beta1), b2 = as_written(beta2), l = as_written(lr);
+    const double bc1 = 1.0 - pow(b1, (double)step);
+    const double bc2 = 1.0 - pow(b2, (double)step);
+    AdamScalars a;
+    a.step_size = (float)(l / bc1);
+    a.inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+    a.one_minus_b1 = (float)(1.0 - b1);
+    a.b2 = (float)b2;
+    a.one_minus_b2 = (float)(1.0 - b2);
+    return a;
+}
+
+// One element of torch's Adam update (scene/gaussian_model.py:154-163: no weight decay, no amsgrad):
+//   m = m + (1-b1)(g - m);  v = b2 v + (1-b2) g g;  p = p - step_size * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+// m and v are computed exactly as torch's kernels do.  The square root and the quotient use the SFU
+// approximations (sqrt.approx, MUFU.RCP; <= 2 ulp each): IEEE sqrtf and '/' call slow-path subroutines whenever
+// one lane of the warp sees a zero, subnormal or tiny operand — which is every warp here (culled Gaussians have
+// g = m = v = 0, eps is 1e-15) — and made the optimizer-in-backward kernel instruction bound (ncu: 963 M warp
+// instructions, 12% BRA, 17 M CALLs; profiles/r01_adam_in_backward.md).  The update term differs from torch's
+// by <= 4 ulp of ITSELF, i.e. far below one ulp of p.
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float adam_update(float p, float g, float& m, float& v, float one_minus_b1, float b2,
+                                             float one_minus_b2, float step_size, float inv_bc2_sqrt, float eps) {
+    m = m + one_minus_b1 * (g - m);
+    v = v * b2 + one_minus_b2 * g * g;
+    const float denom = sqrt_approx(v) * inv_bc2_sqrt + eps;
+    return p - step_size * __fdividef(m, denom);
+}
+
 
 constexpr int TILE_X = 16;   // cuda_rasterizer/config.h:16-17
 constexpr int TILE_Y = 16;

@@ -424,6 +424,64 @@ __global__ void cluster_out_kernel(int K, const double* __restrict__ mean, const
     for (int d = 0; d < 6; ++d) cov_out[6 * k + d] = c ? (float)(acc[6 * k + d] / c) : 0.f;
 }
 
+// ---------------------------------------------------------------- K-Means (Lloyd) ---------------
+// One Lloyd iteration = nearest-centre assignment (the MODE_NN match above: tensor-core lower bound +
+// exact fp32 cdist evaluation, ties to the lowest centre) followed by the centre update below.
+// Sums are double atomics (order independent after rounding to fp32).  acc: [K,3] sums, cnt: [K],
+// stat[0] = labels changed, stat[1] (as double bits in stat64) = inertia.
+__global__ void __launch_bounds__(256)
+kmeans_accumulate_kernel(int n, const float* __restrict__ pts, const int32_t* __restrict__ new_label,
+                         const float* __restrict__ dist, int32_t* __restrict__ label, double* __restrict__ acc,
+                         int32_t* __restrict__ cnt, unsigned long long* __restrict__ changed,
+                         double* __restrict__ inertia) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int ch = 0;
+    double d2 = 0.0;
+    if (i < n) {
+        const int k = new_label[i];
+        ch = label[i] != k;
+        label[i] = k;
+        const float d = dist[i];
+        d2 = (double)d * (double)d;
+        atomicAdd(cnt + k, 1);
+        atomicAdd(acc + 3 * k + 0, (double)pts[3 * i + 0]);
+        atomicAdd(acc + 3 * k + 1, (double)pts[3 * i + 1]);
+        atomicAdd(acc + 3 * k + 2, (double)pts[3 * i + 2]);
+    }
+    // block-level pre-reduction of the two scalars
+    __shared__ double s_d[8];
+    __shared__ int s_c[8];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+        ch += __shfl_xor_sync(0xffffffffu, ch, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_d[threadIdx.x >> 5] = d2; s_c[threadIdx.x >> 5] = ch; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0; int c = 0;
+        for (int w = 0; w < 8; ++w) { t += s_d[w]; c += s_c[w]; }
+        atomicAdd(inertia, t);
+        if (c) atomicAdd(changed, (unsigned long long)c);
+    }
+}
+// new centre = mean of members (an empty cluster keeps its centre); shift2 += |new - old|^2
+__global__ void kmeans_update_kernel(int K, const double* __restrict__ acc, const int32_t* __restrict__ cnt,
+                                     float* __restrict__ centers, double* __restrict__ shift2) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const int c = cnt[k];
+    if (c == 0) return;
+    double s = 0.0;
+    for (int d = 0; d < 3; ++d) {
+        const float nc = (float)(acc[3 * k + d] / c);
+        const double df = (double)nc - (double)centers[3 * k + d];
+        s += df * df;
+        centers[3 * k + d] = nc;
+    }
+    atomicAdd(shift2, s);
+}
+
 // ---------------------------------------------------------------- host --------------------------
 template <int MODE>
 static int run_match(int Kc, int Ks, const float* mean_c, const float* cov_c, const float* mean_s,
@@ -537,5 +595,64 @@ extern "C" int wast3d_cluster_stats(int n, int K, const float* points, const int
     } while (0);
     if (rc == WAST3D_ERR_CUDA) set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
     cudaFreeAsync(buf, s);
+    return rc;
+}
+
+// Lloyd's K-Means on 3-D points (replaces sklearn.cluster.KMeans(...).fit_predict as called by
+// aux_save_clusters_clean.py:32-47 and train_st.py:54-70, for a given initialisation).
+extern "C" int wast3d_kmeans_lloyd(int n, int K, const float* points, float* centers, int32_t* labels,
+                                   int max_iter, double tol, double* out_inertia_host, int* out_n_iter_host,
+                                   double* out_shift_host, void* stream_v) {
+    if (n < 1 || K < 1 || K > n || !points || !centers || !labels || max_iter < 0 || !(tol >= 0.0))
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    Carver sizer(nullptr);
+    sizer.take<double>((size_t)3 * K + 2); sizer.take<unsigned long long>(1); sizer.take<int32_t>(K);
+    sizer.take<int32_t>(n); sizer.take<float>(n);
+    void* chunk = nullptr;
+    W3D_CUDA_TRY(cudaMallocAsync(&chunk, sizer.bytes(), s));
+    Carver c(chunk);
+    double* acc = c.take<double>((size_t)3 * K + 2);
+    double* inertia = acc + 3 * (size_t)K;
+    double* shift2 = inertia + 1;
+    unsigned long long* changed = c.take<unsigned long long>(1);
+    int32_t* cnt = c.take<int32_t>(K);
+    int32_t* new_label = c.take<int32_t>(n);
+    float* dist = c.take<float>(n);
+    int rc = WAST3D_OK;
+    int it = 0;
+    double h_inertia = 0.0, h_shift = 0.0;
+    do {
+        if (cudaMemsetAsync(labels, 0xFF, sizeof(int32_t) * (size_t)n, s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+        // E-step, M-step, ... ; the loop always ends on an E-step against the FINAL centres so that labels and
+        // centres are consistent (sklearn re-runs the E-step after a tolerance-based stop as well)
+        for (;;) {
+            rc = run_match<MODE_NN>(n, K, points, nullptr, centers, nullptr, new_label, dist, nullptr, nullptr, s);
+            if (rc != WAST3D_OK) break;
+            if (cudaMemsetAsync(acc, 0, sizeof(double) * ((size_t)3 * K + 2), s) != cudaSuccess ||
+                cudaMemsetAsync(changed, 0, sizeof(unsigned long long), s) != cudaSuccess ||
+                cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)K, s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+            kmeans_accumulate_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, points, new_label, dist, labels, acc, cnt,
+                                                                      changed, inertia);
+            count_launch();
+            unsigned long long h_changed = 0;
+            if (cudaMemcpyAsync(&h_changed, changed, sizeof(h_changed), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaMemcpyAsync(&h_inertia, inertia, sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+            // stop: iteration budget used, labels stable (strict convergence), or the last update moved the
+            // centres by no more than tol (then this E-step was the consistency pass)
+            if (it >= max_iter || h_changed == 0 || (it > 0 && h_shift <= tol)) break;
+            kmeans_update_kernel<<<(K + 127) / 128, 128, 0, s>>>(K, acc, cnt, centers, shift2);
+            count_launch();
+            if (cudaMemcpyAsync(&h_shift, shift2, sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+            ++it;
+        }
+    } while (0);
+    if (rc == WAST3D_ERR_CUDA) set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+    cudaFreeAsync(chunk, s);
+    if (out_inertia_host) *out_inertia_host = h_inertia;
+    if (out_n_iter_host) *out_n_iter_host = it;
+    if (out_shift_host) *out_shift_host = h_shift;
     return rc;
 }

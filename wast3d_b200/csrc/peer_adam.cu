@@ -31,7 +31,7 @@ constexpr int PEER_THREADS = 512;
 
 struct PeerSeg {  // device-side copy of wast3d_adam_segment with derived constants
     unsigned long long begin4, end4;
-    float step_size, bc2_sqrt, one_minus_b1, b2, one_minus_b2, eps;
+    float step_size, inv_bc2_sqrt, one_minus_b1, b2, one_minus_b2, eps;
 };
 
 struct PeerArgs {
@@ -108,9 +108,7 @@ __device__ bool wait_flags(const uint32_t* row, int world, uint32_t epoch, unsig
 
 __device__ __forceinline__ void adam4(float4& p, const float4& g, float4& m, float4& v, const PeerSeg& s) {
 #define W3D_ADAM1(c)                                                      \
-    m.c = m.c + s.one_minus_b1 * (g.c - m.c);                             \
-    v.c = v.c * s.b2 + s.one_minus_b2 * g.c * g.c;                        \
-    p.c = p.c - s.step_size * (m.c / (sqrtf(v.c) / s.bc2_sqrt + s.eps));
+    p.c = adam_update(p.c, g.c, m.c, v.c, s.one_minus_b1, s.b2, s.one_minus_b2, s.step_size, s.inv_bc2_sqrt, s.eps);
     W3D_ADAM1(x) W3D_ADAM1(y) W3D_ADAM1(z) W3D_ADAM1(w)
 #undef W3D_ADAM1
 }
@@ -270,16 +268,15 @@ extern "C" int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs
         const wast3d_adam_segment& h = segs[k];
         if (h.end4 < h.begin4 || h.begin4 < prev_end || h.step < 1) return WAST3D_ERR_INVALID_ARGUMENT;
         prev_end = h.end4;
-        const double bc1 = 1.0 - pow((double)h.beta1, (double)h.step);
-        const double bc2 = 1.0 - pow((double)h.beta2, (double)h.step);
+        const w3d::AdamScalars sc = w3d::adam_scalars(h.lr, h.beta1, h.beta2, h.step);
         PeerSeg& d = a.segs[k];
         d.begin4 = h.begin4;
         d.end4 = h.end4;
-        d.step_size = (float)((double)h.lr / bc1);
-        d.bc2_sqrt = (float)sqrt(bc2);
-        d.one_minus_b1 = 1.0f - h.beta1;
-        d.b2 = h.beta2;
-        d.one_minus_b2 = 1.0f - h.beta2;
+        d.step_size = sc.step_size;
+        d.inv_bc2_sqrt = sc.inv_bc2_sqrt;
+        d.one_minus_b1 = sc.one_minus_b1;
+        d.b2 = sc.b2;
+        d.one_minus_b2 = sc.one_minus_b2;
         d.eps = h.eps;
     }
     a.nsegs = nsegs;

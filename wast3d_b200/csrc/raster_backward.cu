@@ -494,15 +494,13 @@ struct AdamSlot {  // one GaussianModel parameter group
     float* p;
     float* m;
     float* v;
-    float step_size, bc2_sqrt, one_minus_b1, b2, one_minus_b2, eps;
+    float step_size, inv_bc2_sqrt, one_minus_b1, b2, one_minus_b2, eps;
 };
 struct AdamFused {
     AdamSlot g[6];  // xyz, f_dc, f_rest, opacity, scaling, rotation
 };
 __device__ __forceinline__ float adam_elem(float p, float g, float& m, float& v, const AdamSlot& s) {
-    m = m + s.one_minus_b1 * (g - m);
-    v = v * s.b2 + s.one_minus_b2 * g * g;
-    return p - s.step_size * (m / (sqrtf(v) / s.bc2_sqrt + s.eps));
+    return adam_update(p, g, m, v, s.one_minus_b1, s.b2, s.one_minus_b2, s.step_size, s.inv_bc2_sqrt, s.eps);
 }
 template <int N>
 __device__ __forceinline__ void adam_small(const AdamSlot& s, size_t base, const float (&g)[N]) {
@@ -514,7 +512,10 @@ __device__ __forceinline__ void adam_small(const AdamSlot& s, size_t base, const
 #pragma unroll
     for (int k = 0; k < N; ++k) { s.p[base + k] = p[k]; s.m[base + k] = m[k]; s.v[base + k] = v[k]; }
 }
-// Adam over a warp's contiguous block of `total` elements whose gradients sit in shared memory
+// Adam over a warp's contiguous block of `total` elements whose gradients sit in shared memory.
+// U float4 per lane are loaded from each of p / m / v before any of them is consumed (3U independent 16-byte
+// loads in flight per lane): this loop moves 76% of the fused kernel's bytes and is latency bound otherwise.
+template <int U>
 __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base, int total,
                                                  const float* s_grad, float* g_out, int lane) {
     float* P_ = s.p + base;
@@ -524,19 +525,31 @@ __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base,
                      (g_out == nullptr || (((size_t)(g_out + base)) & 15) == 0);
     if (vec) {
         const int n4 = total >> 2;
-        for (int q = lane; q < n4; q += 32) {
-            const float4 g = *reinterpret_cast<const float4*>(s_grad + 4 * q);
-            float4 p = reinterpret_cast<float4*>(P_)[q];
-            float4 m = reinterpret_cast<float4*>(M_)[q];
-            float4 v = reinterpret_cast<float4*>(V_)[q];
-            p.x = adam_elem(p.x, g.x, m.x, v.x, s);
-            p.y = adam_elem(p.y, g.y, m.y, v.y, s);
-            p.z = adam_elem(p.z, g.z, m.z, v.z, s);
-            p.w = adam_elem(p.w, g.w, m.w, v.w, s);
-            reinterpret_cast<float4*>(P_)[q] = p;
-            reinterpret_cast<float4*>(M_)[q] = m;
-            reinterpret_cast<float4*>(V_)[q] = v;
-            if (g_out) reinterpret_cast<float4*>(g_out + base)[q] = g;
+        float4* P4 = reinterpret_cast<float4*>(P_);
+        float4* M4 = reinterpret_cast<float4*>(M_);
+        float4* V4 = reinterpret_cast<float4*>(V_);
+        for (int q0 = 0; q0 < n4; q0 += 32 * U) {
+            float4 p[U], m[U], v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + 32 * u + lane;
+                if (q < n4) { p[u] = __ldcs(P4 + q); m[u] = __ldcs(M4 + q); v[u] = __ldcs(V4 + q); }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int q = q0 + 32 * u + lane;
+                if (q < n4) {
+                    const float4 g = *reinterpret_cast<const float4*>(s_grad + 4 * q);
+                    p[u].x = adam_elem(p[u].x, g.x, m[u].x, v[u].x, s);
+                    p[u].y = adam_elem(p[u].y, g.y, m[u].y, v[u].y, s);
+                    p[u].z = adam_elem(p[u].z, g.z, m[u].z, v[u].z, s);
+                    p[u].w = adam_elem(p[u].w, g.w, m[u].w, v[u].w, s);
+                    P4[q] = p[u];
+                    __stcs(M4 + q, m[u]);
+                    __stcs(V4 + q, v[u]);
+                    if (g_out) reinterpret_cast<float4*>(g_out + base)[q] = g;
+                }
+            }
         }
     } else {
         for (int q = lane; q < total; q += 32) {
@@ -556,7 +569,7 @@ __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base,
 // dL_dsh is dL/d_features_dc [P,1,3] and dL_dsh_rest is dL/d_features_rest [P,M-1,3].
 // ADAM (RAW only): apply the optimizer update in place (AdamFused); the gradient outputs of the six
 // leaves become optional (non-NULL ones are still written: tests).
-template <bool RAW, bool ADAM>
+template <bool RAW, bool ADAM, int ADAM_U = 4>
 __global__ void __launch_bounds__(GB_THREADS)
 gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                          const int* __restrict__ radii, const float* __restrict__ shs,
@@ -849,7 +862,7 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                     if (dL_dsh) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
                 }
                 if (rest_floats > 0)
-                    adam_rows_linear(af.g[2], (size_t)warp_first * rest_floats, rows_valid * rest_floats, s_sh[warp],
+                    adam_rows_linear<ADAM_U>(af.g[2], (size_t)warp_first * rest_floats, rows_valid * rest_floats, s_sh[warp],
                                      dL_dsh_rest, lane);
             } else if (RAW) {
                 if (live) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
@@ -949,7 +962,10 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
         W3D_AFTER_LAUNCH(s, debug);
     }
     ProfScope ps_gb(PS_GAUSS_BWD, s);
-    auto gb = prm->raw_params ? (adam ? gaussian_backward_kernel<true, true> : gaussian_backward_kernel<true, false>)
+    static const int adam_u = getenv("WAST3D_ADAM_UNROLL") ? atoi(getenv("WAST3D_ADAM_UNROLL")) : 4;
+    auto gb_adam = adam_u == 1 ? gaussian_backward_kernel<true, true, 1>
+                 : adam_u == 2 ? gaussian_backward_kernel<true, true, 2> : gaussian_backward_kernel<true, true, 4>;
+    auto gb = prm->raw_params ? (adam ? gb_adam : gaussian_backward_kernel<true, false>)
                               : gaussian_backward_kernel<false, false>;
     const AdamFused af = adam ? *adam : AdamFused{};
     gb<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
@@ -1023,17 +1039,16 @@ extern "C" int wast3d_raster_backward_raw_adam(const wast3d_raster_params* prm, 
         if (absent) continue;
         if (!h.param || h.param != expect[k] || !h.exp_avg || !h.exp_avg_sq || h.step < 1)
             return WAST3D_ERR_INVALID_ARGUMENT;
-        const double bc1 = 1.0 - pow((double)h.beta1, (double)h.step);
-        const double bc2 = 1.0 - pow((double)h.beta2, (double)h.step);
+        const w3d::AdamScalars sc = w3d::adam_scalars(h.lr, h.beta1, h.beta2, h.step);
         AdamSlot& d = af.g[k];
         d.p = h.param;
         d.m = h.exp_avg;
         d.v = h.exp_avg_sq;
-        d.step_size = (float)((double)h.lr / bc1);
-        d.bc2_sqrt = (float)sqrt(bc2);
-        d.one_minus_b1 = 1.0f - h.beta1;
-        d.b2 = h.beta2;
-        d.one_minus_b2 = 1.0f - h.beta2;
+        d.step_size = sc.step_size;
+        d.inv_bc2_sqrt = sc.inv_bc2_sqrt;
+        d.one_minus_b1 = sc.one_minus_b1;
+        d.b2 = sc.b2;
+        d.one_minus_b2 = sc.one_minus_b2;
         d.eps = h.eps;
     }
     float* go[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
