@@ -37,6 +37,12 @@ constexpr int ACC_STRIDE = 12;
 //  0 dmean2D.x  1 dmean2D.y  2 dconic.x  3 dconic.y | 4 dconic.w  5 dopacity  6 dviewdepth  7 - |
 //  8 dcolor.r   9 dcolor.g  10 dcolor.b  11 -
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Sum v[0..11] over the warp.  On return lane L holds in the result the total of slot
 //   slot(L) = 6*b4 + 3*b3 + 2*b2 + b1   (b_k = bit k of L), valid when (2*b2+b1) < 3;
 // lanes L and L^1 hold the same value.
@@ -222,7 +228,10 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
                                 active = true;
                                 const float4 c = r2[j];
                                 // backward.cu:529-563
-                                T = T / (1.f - alpha);
+                                // one approximate reciprocal (MUFU.RCP, <= 1 ulp; 1 - alpha is in [0.01, 1]) serves both
+                                // divisions of backward.cu:530,562: two IEEE divisions were 30 of this loop's 187 instructions
+                                const float inv_1ma = rcp_approx(1.f - alpha);
+                                T = T * inv_1ma;
                                 const float dchannel_dcolor = alpha * T;
                                 float dL_dalpha = 0.0f;
                                 accum0 = last_alpha * last_c0 + (1.f - last_alpha) * accum0;
@@ -241,7 +250,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 
                                 dL_dalpha *= T;
                                 last_alpha = alpha;
-                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                                dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                                 // backward.cu:567-583
                                 const float dL_dG = con_o.w * dL_dalpha;
@@ -427,7 +436,10 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
                                 active = true;
                                 const float4 c = r2[j];
                                 // backward.cu:529-563
-                                T = T / (1.f - alpha);
+                                // one approximate reciprocal (MUFU.RCP, <= 1 ulp; 1 - alpha is in [0.01, 1]) serves both
+                                // divisions of backward.cu:530,562: two IEEE divisions were 30 of this loop's 187 instructions
+                                const float inv_1ma = rcp_approx(1.f - alpha);
+                                T = T * inv_1ma;
                                 const float dchannel_dcolor = alpha * T;
                                 float dL_dalpha = 0.0f;
                                 accum0 = last_alpha * last_c0 + (1.f - last_alpha) * accum0;
@@ -446,7 +458,7 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
 
                                 dL_dalpha *= T;
                                 last_alpha = alpha;
-                                dL_dalpha += (-T_final / (1.f - alpha)) * bg_dot_dpixel;
+                                dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                                 // backward.cu:567-583
                                 const float dL_dG = con_o.w * dL_dalpha;

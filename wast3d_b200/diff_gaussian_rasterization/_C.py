@@ -68,9 +68,11 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
             _lib.stream_ptr())
     for b in (geom, binning, img):
         if b.error is not None:
-            raise b.error
+            err = b.error
+            geom.take(), binning.take(), img.take()
+            raise err
     _lib.check(st, "rasterize_gaussians")
-    return rendered.value, out_color, out_depth, radii, geom.tensor, binning.tensor, img.tensor
+    return rendered.value, out_color, out_depth, radii, geom.take(), binning.take(), img.take()
 
 
 def rasterize_gaussians_backward(background, means3D, radii, colors, scales, rotations,

@@ -57,14 +57,14 @@ class _RasterizeModel(torch.autograd.Function):
             st = lib.wast3d_raster_forward(
                 C.byref(prm), geom.cb, None, binning.cb, None, img.cb, None, color.data_ptr(),
                 depth.data_ptr(), radii.data_ptr() if P else None, C.byref(rendered), _lib.stream_ptr())
+        geom_t, binning_t, img_t = geom.take(), binning.take(), img.take()
         for b in (geom, binning, img):
             if b.error is not None:
                 raise b.error
         _lib.check(st, "rasterize_model")
         ctx.raster_settings = rs
         ctx.num_rendered = rendered.value
-        ctx.save_for_backward(xyz, f_dc, f_rest, opacity, scaling, rotation, radii, geom.tensor,
-                              binning.tensor, img.tensor,
+        ctx.save_for_backward(xyz, f_dc, f_rest, opacity, scaling, rotation, radii, geom_t, binning_t, img_t,
                               sampling_offsets if sampling_offsets is not None else torch.empty(0))
         ctx.mark_non_differentiable(radii)
         return color, depth, radii
