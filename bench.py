@@ -57,6 +57,10 @@ def parse():
                          "(with one GPU: just the dense fused Adam); 'backward' (one GPU only) = the Adam update applied by the "
                          "rasteriser's per-Gaussian backward kernel, leaf gradients never written (optim.BackwardFusedAdam); "
                          "'auto' = peer with N > 1, backward with N = 1")
+    ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
+                    help="peer arm: 1 = the SH features (81%% of the parameter bytes) are reduced / updated / all-gathered by "
+                         "a second launch on a side stream that overlaps the next view's projection, sorting and binning "
+                         "(the rasteriser's colour kernel waits for it); 0 = one launch, the step waits for all of it")
     ap.add_argument("--tile-cut", type=int, default=1, choices=[0, 1],
                     help="1 = instantiate Gaussians only in tiles that can see alpha >= 1/255 (default), "
                          "0 = the reference's radius rectangles")
@@ -286,13 +290,14 @@ def main():
     pc = GaussianModel.from_arrays(arrs, sh_degree=3, device=dev)
     pc.spatial_lr_scale = 5.0
     if args.sync == "peer":
-        opt = pc.training_setup(peer=True, average=True)
+        opt = pc.training_setup(peer=True, average=True, overlap_features=bool(args.overlap))
     elif args.sync == "backward":
         opt = pc.training_setup(in_backward=True)
     else:
         opt = pc.training_setup(fused=True)
     if args.sync == "peer":
-        PEER_BACKEND[0] = opt.buffer.backend + ("+multicast" if opt.multicast else "")
+        PEER_BACKEND[0] = (opt.buffer.backend + ("+multicast" if opt.multicast else "")
+                           + ("+overlapped-features" if opt.overlap_late else ""))
     cams = scene_cameras(spec, 8, device=dev)
     pipe = PipelineParams()
     bg = torch.zeros(3, device=dev)
@@ -398,6 +403,8 @@ def main():
             marks.append(time.perf_counter())
             allocs.append(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))
         drain()  # the last step's loss is read before the region closes
+        if hasattr(opt, "sync"):
+            opt.sync()  # the last step's side-stream launch (feature exchange) is inside the bracket
         b.record()
         barrier()
         host = [(y - x) * 1e3 for x, y in zip(marks, marks[1:])]

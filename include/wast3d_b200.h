@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define WAST3D_ABI_VERSION 4
+#define WAST3D_ABI_VERSION 5
 
 enum wast3d_status {
     WAST3D_OK = 0,
@@ -79,6 +79,14 @@ typedef struct wast3d_raster_params {
      * colors_precomp / cov3D_precomp must be NULL in this mode. */
     int raw_params;
     const float* shs_rest;        /* [P,M-1,3] or NULL when M == 1 (raw_params only)        */
+    /* ---- ABI v5: overlap of the SH parameters' arrival with projection / sorting / binning -----
+     * colour_wait_event (a cudaEvent_t, or NULL) is honoured by wast3d_raster_forward only: SH -> RGB
+     * (forward.cu:241-246) is evaluated by a separate kernel launched just before the tile render,
+     * after cudaStreamWaitEvent(stream, event).  `shs` / `shs_rest` may therefore still be written by
+     * another stream (the view-parallel optimizer's parameter all-gather, wast3d_peer_adam_step on a
+     * side stream) while K1's geometry part and K2-K5 run; results are bit-identical.  The wait also
+     * orders the render and everything after it on `stream` behind the event. */
+    void* colour_wait_event;
 } wast3d_raster_params;
 
 /* Replaces RasterizeGaussiansCUDA -> CudaRasterizer::Rasterizer::forward

@@ -42,6 +42,76 @@ def test_peer_adam_world1_matches_fused_and_torch(built):
     oa.close()
 
 
+def test_peer_adam_late_class_matches_fused(built):
+    """late_params: second launch on a side stream, own flag set, own shard + moment slice; same results."""
+    from wast3d_b200.optim import FusedAdam
+    from wast3d_b200.peer import PeerShardedAdam
+    torch.manual_seed(1)
+    shapes = [(100003, 3), (5000, 15, 3), (777, 1), (5,), (64, 4)]
+    p0 = [torch.randn(s, device="cuda") for s in shapes]
+    pa = [torch.nn.Parameter(p.clone()) for p in p0]
+    pb = [torch.nn.Parameter(p.clone()) for p in p0]
+    oa = PeerShardedAdam(_groups(pa), lr=0.0, eps=1e-15, late_params=[pa[1], pa[3]])
+    ob = FusedAdam(_groups(pb), lr=0.0, eps=1e-15)
+    assert oa.overlap_late and oa.take_late_event() is None
+    for it in range(5):
+        for a, b in zip(pa, pb):
+            g = torch.randn_like(b) * (10.0 ** (it - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        oa.step(); ob.step()
+        oa.zero_grad()
+        if it % 2 == 0:  # consumer orders itself; otherwise the next step() does
+            ev = oa.take_late_event()
+            assert ev is not None and oa.take_late_event() is None
+            torch.cuda.current_stream().wait_event(ev)
+    oa.sync()
+    oa.check_peers()
+    for a, b, p in zip(pa, pb, p0):
+        assert a.shape == p.shape and torch.equal(a.detach(), b.detach())
+    oa.close()
+
+
+def test_training_loop_with_overlapped_features_equals_plain_peer(built):
+    """Three optimisation steps through render(): overlap_features (colour kernel behind the side-stream
+    launch) against the single-launch peer optimizer.  The first image is bit-identical; after a step the
+    parameters differ by the rounding of K7's unordered float atomics (~1e-7 in the image), whereas features
+    read one step too early would be off by the learning rate (~1e-3)."""
+    from wast3d_b200.gaussian_renderer import render
+    from wast3d_b200.scene import GaussianModel, PipelineParams, orbit_cameras, synthetic_gaussians
+    arrs = synthetic_gaussians(20000, seed=5, log_scale_mu=-3.2)
+    cams = orbit_cameras(3, 4.03, 0.0, 0.6911, 160, 112, device="cuda", sphere=True)
+    bg = torch.zeros(3, device="cuda")
+    offs = -torch.rand(112, 160, 2, device="cuda")
+
+    def run(overlap):
+        m = GaussianModel.from_arrays(arrs, device="cuda")
+        m.spatial_lr_scale = 1.0
+        opt = m.training_setup(peer=True, overlap_features=overlap)
+        imgs = []
+        for cam in cams:
+            out = render(cam, m, PipelineParams(), bg, sampling_offsets=offs)
+            imgs.append(out["render"].detach().clone())
+            (out["render"].square().mean() + 0.1 * out["depth"].mean()).backward()
+            opt.step(); opt.zero_grad()
+        if overlap:
+            assert opt.take_late_event() is not None  # the last step's launch nobody rendered after
+            opt._late_pending = True
+            opt.sync()
+        torch.cuda.synchronize()
+        res = imgs, [p.detach().clone() for p in m.parameters()]
+        opt.close()
+        return res
+
+    ia, pa = run(False)
+    ib, pb = run(True)
+    assert torch.equal(ia[0], ib[0])
+    for a, b in zip(ia[1:], ib[1:]):
+        assert (a - b).abs().max().item() <= 2e-5
+    assert (ia[0] - ia[1]).abs().max().item() > 1e-3  # the views do differ
+    for a, b in zip(pa, pb):
+        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
+
+
 def test_render_writes_gradients_into_the_arena(built):
     """render() with a grad sink: .grad are the arena views, equal to the plain autograd gradients, and a
     second backward before the step accumulates like autograd does."""

@@ -27,6 +27,30 @@ def test_layout_padding_and_shards():
         assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1
 
 
+def test_layout_late_class_is_contiguous_and_sharded_per_class():
+    numels = [torch.Size(s).numel() for s in SHAPES]
+    late = [False, True, True, False, False, False, False, True]
+    lay = ArenaLayout(numels, late)
+    # slots stay in tensor order; early tensors fill [0, split4), late ones [split4, total4), no gaps
+    early = sorted((sl.begin4, sl.end4) for sl, l in zip(lay.slots, late) if not l)
+    lates = sorted((sl.begin4, sl.end4) for sl, l in zip(lay.slots, late) if l)
+    assert early[0][0] == 0 and early[-1][1] == lay.split4 == lates[0][0] and lates[-1][1] == lay.total4
+    for rng in (early, lates):
+        assert all(a[1] == b[0] for a, b in zip(rng, rng[1:]))
+    assert [sl.numel for sl in lay.slots] == numels
+    for w in (1, 2, 3, 8):
+        for cls, (lo, hi) in enumerate(((0, lay.split4), (lay.split4, lay.total4))):
+            b = [lay.shard4(r, w, cls) for r in range(w)]
+            assert b[0][0] == lo and b[-1][1] == hi
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1
+    hyper = [dict(lr=lr, betas=(0.9, 0.999), eps=1e-15) for lr in LRS]
+    segs = lay.segments(hyper, [1] * len(SHAPES))
+    assert all(a["end4"] <= b["begin4"] for a, b in zip(segs, segs[1:]))  # ascending for the kernel
+    assert all(s["end4"] <= lay.split4 or s["begin4"] >= lay.split4 for s in segs)  # none spans the classes
+    assert ArenaLayout(numels).split4 == ArenaLayout(numels).total4  # no late class: everything early
+
+
 def test_segments_skip_empty_and_carry_hyperparameters():
     lay = ArenaLayout([torch.Size(s).numel() for s in SHAPES])
     hyper = [dict(lr=lr, betas=(0.9, 0.999), eps=1e-15) for lr in LRS]

@@ -265,6 +265,50 @@ def test_autograd_module_and_render(built):
     assert torch.equal(out2["radii"], out["radii"]) or (out2["radii"] != out["radii"]).float().mean() < 1e-3
 
 
+@pytest.mark.parametrize("name", ["sh3_jitter", "deg1_big_splats", "deg0_scale_mod", "precomp", "garden_culling"])
+def test_deferred_colour_kernel_is_bit_identical_and_ordered(built, cut, name):
+    """ABI v5 colour_wait_event: K1 without colour + sh_colour_kernel behind the event give the same bits
+    as the one-kernel preprocess (image, depth, radii, buffers, gradients of a fixed replay order aside),
+    and the SH coefficients are really read only behind the event: a side stream that is still busy
+    rewrites them and records the event afterwards — the image must show the NEW coefficients."""
+    case = raster_case(**CASES[name])
+    tc = to_cuda(case)
+    ref = call_forward(tc)
+    ev = torch.cuda.Event()
+    ev.record()
+    got = call_forward(tc, colour_wait_event=ev)
+    assert got[0] == ref[0]
+    for a, b in zip(got[1:4], ref[1:4]):
+        assert torch.equal(a, b)
+    sa, sb = export(tc, got), export(tc, ref)
+    for k in ("rgb", "clamped", "conic_opacity", "means2D", "depths", "point_list", "ranges", "n_contrib", "final_T"):
+        if k in sa:
+            assert torch.equal(sa[k], sb[k]), k
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    dpix = torch.randn(3, case["H"], case["W"], device="cuda", generator=gen)
+    ddep = torch.randn(case["H"], case["W"], device="cuda", generator=gen)
+    for a, b in zip(call_backward(tc, got, dpix, ddep), call_backward(tc, ref, dpix, ddep)):
+        if a is not None and a.numel() and b.norm().item() > 0:
+            assert rel_l2(a, b) <= 1e-5
+    if tc.get("shs") is None:
+        return
+    # ordering: the coefficients change on a side stream AFTER the forward was enqueued
+    new_sh = tc["shs"] * 0.5 + 0.1
+    want = call_forward(dict(tc, shs=new_sh))
+    live = tc["shs"].clone()
+    tc2 = dict(tc, shs=live)
+    side = torch.cuda.Stream()
+    ev2 = torch.cuda.Event()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(int(2e8))  # ~0.1 s: K1 .. tile ranges are long done when the copy runs
+        live.copy_(new_sh)
+        ev2.record(side)
+    out = call_forward(tc2, colour_wait_event=ev2)
+    torch.cuda.synchronize()
+    assert torch.equal(out[1], want[1]) and torch.equal(out[2], want[2]) and torch.equal(out[3], want[3])
+
+
 @pytest.mark.parametrize("P,sh_degree,active,W,H", [(5000, 3, 3, 160, 120), (4999, 3, 1, 97, 61),
                                                      (777, 0, 0, 64, 48), (2050, 2, 2, 80, 80), (31, 1, 1, 33, 17)])
 def test_model_render_matches_unfused(built, P, sh_degree, active, W, H):

@@ -47,7 +47,7 @@ def to_cuda(case: dict) -> dict:
 EMPTY = None
 
 
-def call_forward(tc: dict, debug=False):
+def call_forward(tc: dict, debug=False, colour_wait_event=None):
     """Run our `_C.rasterize_gaussians` on a CUDA case dict."""
     from wast3d_b200.diff_gaussian_rasterization import _C
     e = torch.empty(0)
@@ -55,7 +55,8 @@ def call_forward(tc: dict, debug=False):
     return _C.rasterize_gaussians(
         tc["bg"], tc["means3D"], g("colors_precomp"), tc["opacities"], g("scales"), g("rotations"),
         tc["scale_modifier"], g("cov3D_precomp"), tc["view"], tc["proj"], tc["tan_fovx"], tc["tan_fovy"],
-        tc["H"], tc["W"], g("shs"), tc["D"], tc["campos"], False, debug, g("sampling_offsets"))
+        tc["H"], tc["W"], g("shs"), tc["D"], tc["campos"], False, debug, g("sampling_offsets"),
+        _colour_wait_event=colour_wait_event)
 
 
 def call_backward(tc: dict, fwd, dL_dpix, dL_ddepth, debug=False, scratch=True):

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel device time of
-the LAST complete step (a step ends with the last fused-Adam launch), as shares of the step.
+the LAST complete step (a step ends with the last fused-Adam launch or, with Adam applied inside the
+backward, with gaussian_backward_kernel), as shares of the step.
 
     python tools/launch_summary.py gpurun_out/launches_r01.csv [> profiles/r01_launches.md]
 """
@@ -16,6 +17,8 @@ def main(path, adam_per_step=6):
     rows = list(csv.DictReader(lines))
     adam = [i for i, x in enumerate(rows) if "adam" in x["Kernel Name"]]
     ends = [adam[i] for i in range(adam_per_step - 1, len(adam), adam_per_step)]
+    if not adam:  # optimizer-in-backward: the per-Gaussian backward kernel is the step's last launch
+        ends = [i for i, x in enumerate(rows) if "gaussian_backward" in x["Kernel Name"]]
     if len(ends) < 2:
         raise SystemExit("need at least two complete steps in the launch list")
     s, e = ends[-2] + 1, ends[-1] + 1

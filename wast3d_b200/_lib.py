@@ -29,7 +29,7 @@ class RasterParams(C.Structure):
         ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p),
         ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
         ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("sampling_offsets", C.c_void_p),
-        ("raw_params", C.c_int), ("shs_rest", C.c_void_p),
+        ("raw_params", C.c_int), ("shs_rest", C.c_void_p), ("colour_wait_event", C.c_void_p),
     ]
 
 

@@ -20,6 +20,7 @@
 //
 // Arithmetic per element is adam.cu's (torch single-tensor Adam order).
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -303,7 +304,12 @@ extern "C" int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs
                 &per_sm, peer_adam_kernel<N, MCFLAG>, PEER_THREADS, 0));                                  \
             if (per_sm < 1) per_sm = 1;                                                                   \
         }                                                                                                 \
-        if (blocks > (size_t)148 * per_sm) blocks = (size_t)148 * per_sm;                                 \
+        {                                                                                                 \
+            /* WAST3D_PEER_CTAS_PER_SM: cap the persistent grid so kernels of another stream can co-run */  \
+            static const int cap = getenv("WAST3D_PEER_CTAS_PER_SM") ? atoi(getenv("WAST3D_PEER_CTAS_PER_SM")) : 0; \
+            const int use = (cap > 0 && cap < per_sm) ? cap : per_sm;                                     \
+            if (blocks > (size_t)148 * use) blocks = (size_t)148 * use;                                   \
+        }                                                                                                 \
         peer_adam_kernel<N, MCFLAG><<<(unsigned)blocks, PEER_THREADS, 0, s>>>(a);                         \
     }
 #define W3D_PEER_CASE(N)                                                                                  \

@@ -96,7 +96,11 @@ __device__ __forceinline__ float2 cutoff_extent(float A, float B, float C, float
 }
 
 // RAW: model-space inputs (wast3d_raster_params::raw_params) — activations applied here.
-template <bool RAW>
+// COLOUR: true = SH -> RGB evaluated here (one kernel, as in the reference's preprocessCUDA);
+// false = geometry only: rgb is left to sh_colour_kernel, which the host launches just before the
+// tile render (wast3d_raster_params::colour_wait_event: the SH coefficients may still be in flight
+// from the optimizer's parameter all-gather while projection, sorting and binning already run).
+template <bool RAW, bool COLOUR>
 __global__ void __launch_bounds__(PRE_THREADS)
 preprocess_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                   const float* __restrict__ scales, const float scale_modifier,
@@ -185,7 +189,9 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     // colour: SH -> RGB for survivors only
     float3 rgb = make_float3(0.f, 0.f, 0.f);
     unsigned clamp_bits = 0;
-    if (colors_precomp == nullptr) {
+    if (!COLOUR) {
+        // deferred: sh_colour_kernel fills rgb and the clamp bits
+    } else if (colors_precomp == nullptr) {
         const unsigned need = __ballot_sync(0xffffffffu, visible);
         if (need) {
             const int rows_valid = min(32, P - warp_first);
@@ -222,6 +228,52 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
         rec[3 * idx + 0] = make_float4(point_image.x, point_image.y, p_view.z, ext.x);
         rec[3 * idx + 1] = make_float4(conic.x, conic.y, conic.z, opac);
         rec[3 * idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, ext.y);
+    }
+}
+
+// Deferred colour pass (forward.cu:20-71,241-246 for the Gaussians preprocess_kernel<.., false> kept):
+// same staging and arithmetic as the fused kernel, so the render record it completes is bit-identical.
+template <bool RAW>
+__global__ void __launch_bounds__(PRE_THREADS)
+sh_colour_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
+                 const float* __restrict__ shs, const float* __restrict__ shs_rest,
+                 const float* __restrict__ cam_pos, float4* __restrict__ rec, uint8_t* __restrict__ clamped) {
+    __shared__ __align__(16) float s_sh[PRE_WARPS][32 * SH_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
+    const int warp_first = blockIdx.x * PRE_THREADS + warp * 32;
+    const bool visible = idx < P && (clamped[idx] & 8u) != 0;  // bit 3: render record written
+    const unsigned need = __ballot_sync(0xffffffffu, visible);
+    if (!need) return;
+    float3 p_orig = make_float3(0.f, 0.f, 0.f);
+    if (visible) p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+    float3 rgb = make_float3(0.f, 0.f, 0.f);
+    unsigned clamp_bits = 0;
+    const int rows_valid = min(32, P - warp_first);
+    const int used = 3 * (D + 1) * (D + 1);
+    const float3 cam = *reinterpret_cast<const float3*>(cam_pos);
+    if (RAW) {
+        float dc[3] = {0.f, 0.f, 0.f};
+        if (visible) { dc[0] = shs[3 * idx]; dc[1] = shs[3 * idx + 1]; dc[2] = shs[3 * idx + 2]; }
+        const int rest_floats = 3 * (M - 1);
+        if (used > 3)
+            stage_rows_linear(shs_rest + (size_t)warp_first * rest_floats, rest_floats, used - 3,
+                              rows_valid, need, s_sh[warp], lane);
+        if (visible) rgb = sh_to_rgb(D, dc, s_sh[warp] + lane * rest_floats - 3, p_orig, cam, &clamp_bits);
+    } else {
+        const int row_floats = 3 * M;
+        stage_sh_rows(shs + (size_t)warp_first * row_floats, row_floats, used, rows_valid, need,
+                      s_sh[warp], SH_STRIDE, lane);
+        __syncwarp();
+        const float* row = s_sh[warp] + lane * SH_STRIDE;
+        if (visible) rgb = sh_to_rgb(D, row, row, p_orig, cam, &clamp_bits);
+    }
+    if (visible) {
+        float* c = reinterpret_cast<float*>(rec + 3 * (size_t)idx + 2);  // .w (cutoff half-extent y) stays
+        c[0] = rgb.x;
+        c[1] = rgb.y;
+        c[2] = rgb.z;
+        clamped[idx] = (uint8_t)(clamp_bits | 8u);
     }
 }
 
@@ -653,7 +705,10 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         sample_bounds_kernel<<<148 * 2, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
         W3D_AFTER_LAUNCH(s, debug);
     }
-    auto pre = prm->raw_params ? preprocess_kernel<true> : preprocess_kernel<false>;
+    // colour_wait_event: SH -> RGB moves into its own kernel behind that event (see sh_colour_kernel)
+    const bool defer_colour = prm->colour_wait_event != nullptr && prm->colors_precomp == nullptr;
+    auto pre = prm->raw_params ? (defer_colour ? preprocess_kernel<true, false> : preprocess_kernel<true, true>)
+                               : (defer_colour ? preprocess_kernel<false, false> : preprocess_kernel<false, true>);
     pre<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, prm->scales, prm->scale_modifier, prm->rotations,
         prm->opacities, prm->shs, prm->shs_rest, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
@@ -775,6 +830,17 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         W3D_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, num_tiles * sizeof(uint2), s));
     }
 
+    if (prm->colour_wait_event != nullptr) {
+        // the event also orders everything after it (render, backward) behind the parameter exchange
+        W3D_CUDA_TRY(cudaStreamWaitEvent(s, (cudaEvent_t)prm->colour_wait_event, 0));
+        if (prm->colors_precomp == nullptr) {
+            ProfScope ps(PS_PREPROCESS, s);
+            auto col = prm->raw_params ? sh_colour_kernel<true> : sh_colour_kernel<false>;
+            col<<<(P + PRE_THREADS - 1) / PRE_THREADS, PRE_THREADS, 0, s>>>(
+                P, prm->D, prm->M, prm->means3D, prm->shs, prm->shs_rest, prm->campos, g.rec, g.clamped);
+            W3D_AFTER_LAUNCH(s, debug);
+        }
+    }
     ProfScope ps_render(PS_RENDER_FWD, s);
     render_forward_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, point_list_ptr(bn, num_tiles), W, H, g.rec,
                                                     prm->background, prm->sampling_offsets, im.final_T,

@@ -21,7 +21,7 @@ NUM_CHANNELS = 3  # cuda_rasterizer/config.h:15
 
 def _params(keep, *, P, D, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefiltered, debug, bg,
             means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
-            campos, sampling_offsets, raw_params=False, sh_rest=None):
+            campos, sampling_offsets, raw_params=False, sh_rest=None, colour_wait_event=None):
     f = _lib.fptr
     return _lib.RasterParams(
         P=P, D=int(D), M=M, width=int(W), height=int(H), tan_fovx=float(tan_fovx),
@@ -32,7 +32,7 @@ def _params(keep, *, P, D, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefilte
         rotations=f(rotations, keep), cov3D_precomp=f(cov3D_precomp, keep),
         viewmatrix=f(viewmatrix, keep), projmatrix=f(projmatrix, keep), campos=f(campos, keep),
         sampling_offsets=f(sampling_offsets, keep), raw_params=int(bool(raw_params)),
-        shs_rest=f(sh_rest, keep))
+        shs_rest=f(sh_rest, keep), colour_wait_event=colour_wait_event)
 
 
 def _sh_coeffs(sh) -> int:
@@ -42,7 +42,9 @@ def _sh_coeffs(sh) -> int:
 
 def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations, scale_modifier,
                         cov3D_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, image_height,
-                        image_width, sh, degree, campos, prefiltered, debug, sampling_offsets):
+                        image_width, sh, degree, campos, prefiltered, debug, sampling_offsets,
+                        *, _colour_wait_event=None):
+    """`_colour_wait_event` (extension, torch.cuda.Event): `sh` is read only behind this event (ABI v5)."""
     if means3D.dim() != 2 or means3D.size(1) != 3:
         raise RuntimeError("means3D must have dimensions (num_points, 3)")
     _lib.require_device(means3D)
@@ -59,7 +61,8 @@ def rasterize_gaussians(background, means3D, colors, opacity, scales, rotations,
                   debug=debug, bg=background, means3D=means3D, sh=sh, colors=colors,
                   opacity=opacity, scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp,
                   viewmatrix=viewmatrix, projmatrix=projmatrix, campos=campos,
-                  sampling_offsets=sampling_offsets)
+                  sampling_offsets=sampling_offsets,
+                  colour_wait_event=int(_colour_wait_event.cuda_event) if _colour_wait_event is not None else None)
     rendered = C.c_int(0)
     with torch.cuda.device(dev):
         st = lib.wast3d_raster_forward(

@@ -54,14 +54,20 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
         projmatrix=viewpoint_camera.full_proj_transform,
         sh_degree=pc.active_sh_degree, campos=viewpoint_camera.camera_center,
         prefiltered=False, debug=pipe.debug)
+    # view-parallel optimizer with overlapped feature exchange (peer.PeerShardedAdam late_params): the SH
+    # features of the last step() may still be in flight; only code behind this event may read them
+    take = getattr(getattr(pc, "optimizer", None), "take_late_event", None)
+    features_ready = take() if take is not None else None
     if (override_color is None and not pipe.convert_SHs_python and not pipe.compute_cov3D_python
             and getattr(pipe, "fused_activations", True) and model_supports_fusion(pc)):
         image, depth, radii = rasterize_model(
             xyz, screenspace_points, pc._features_dc, pc._features_rest, pc._opacity, pc._scaling,
-            pc._rotation, settings, sampling_offsets, getattr(pc, "grad_sink", None))
+            pc._rotation, settings, sampling_offsets, getattr(pc, "grad_sink", None), features_ready)
         return {"render": image, "depth": depth, "viewspace_points": screenspace_points,
                 "visibility_filter": radii > 0, "radii": radii}
 
+    if features_ready is not None:  # op-by-op path: torch kernels read the features right away
+        torch.cuda.current_stream(dev).wait_event(features_ready)
     rasterizer = GaussianRasterizer(raster_settings=settings)
 
     scales = rotations = cov3D_precomp = None

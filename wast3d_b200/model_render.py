@@ -21,7 +21,8 @@ from .diff_gaussian_rasterization import GaussianRasterizationSettings
 from .diff_gaussian_rasterization import _C as dgr_C
 
 
-def _prm(keep, rs: GaussianRasterizationSettings, xyz, f_dc, f_rest, opacity, scaling, rotation, offsets):
+def _prm(keep, rs: GaussianRasterizationSettings, xyz, f_dc, f_rest, opacity, scaling, rotation, offsets,
+         colour_wait_event=None):
     P = int(xyz.size(0))
     M = 1 + (int(f_rest.size(1)) if f_rest.numel() else 0)
     return dgr_C._params(
@@ -29,13 +30,13 @@ def _prm(keep, rs: GaussianRasterizationSettings, xyz, f_dc, f_rest, opacity, sc
         tan_fovy=rs.tanfovy, scale_modifier=rs.scale_modifier, prefiltered=rs.prefiltered, debug=rs.debug,
         bg=rs.bg, means3D=xyz, sh=f_dc, colors=None, opacity=opacity, scales=scaling, rotations=rotation,
         cov3D_precomp=None, viewmatrix=rs.viewmatrix, projmatrix=rs.projmatrix, campos=rs.campos,
-        sampling_offsets=offsets, raw_params=True, sh_rest=f_rest)
+        sampling_offsets=offsets, raw_params=True, sh_rest=f_rest, colour_wait_event=colour_wait_event)
 
 
 class _RasterizeModel(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, means2D, f_dc, f_rest, opacity, scaling, rotation, raster_settings,
-                sampling_offsets, grad_sink=None):
+                sampling_offsets, grad_sink=None, colour_wait_event=None):
         rs = raster_settings
         # peer.GradSink: the leaf gradients go straight into the optimizer's peer-visible arena
         ctx.grad_sink = grad_sink
@@ -51,7 +52,9 @@ class _RasterizeModel(torch.autograd.Function):
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         geom, binning, img = _lib.GrowBuffer(dev, "geom"), _lib.GrowBuffer(dev, "binning"), _lib.GrowBuffer(dev, "img")
         keep: list = []
-        prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation, sampling_offsets)
+        # colour_wait_event (torch.cuda.Event): f_dc / f_rest are only read behind it (ABI v5)
+        ev = int(colour_wait_event.cuda_event) if colour_wait_event is not None else None
+        prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation, sampling_offsets, ev)
         rendered = C.c_int(0)
         with torch.cuda.device(dev):
             st = lib.wast3d_raster_forward(
@@ -107,7 +110,7 @@ class _RasterizeModel(torch.autograd.Function):
                 _lib.check(st, "rasterize_model_backward_adam")
             fused_opt._applied = True
             sink.fresh = False
-            return None, d_m2d, None, None, None, None, None, None, None, None
+            return None, d_m2d, None, None, None, None, None, None, None, None, None
         if sink is not None and sink.fresh:
             sunk = [sink.view_for(p) for p in ctx.sink_params]
             if any(v is None for v in sunk):
@@ -143,20 +146,23 @@ class _RasterizeModel(torch.autograd.Function):
             for p_, v in zip(ctx.sink_params, sunk):
                 p_.grad = v
             sink.fresh = False
-            return None, d_m2d, None, None, None, None, None, None, None, None
-        return d_xyz, d_m2d, d_dc, d_rest, d_op, d_sc, d_rot, None, None, None
+            return None, d_m2d, None, None, None, None, None, None, None, None, None
+        return d_xyz, d_m2d, d_dc, d_rest, d_op, d_sc, d_rot, None, None, None, None
 
 
 def rasterize_model(xyz, means2D, features_dc, features_rest, opacity_logits, log_scales, rotations,
-                    raster_settings: GaussianRasterizationSettings, sampling_offsets=None, grad_sink=None):
+                    raster_settings: GaussianRasterizationSettings, sampling_offsets=None, grad_sink=None,
+                    colour_wait_event=None):
     """(color[3,H,W], depth[H,W], radii[P]) from the RAW GaussianModel parameters.
-    `grad_sink` (peer.GradSink, optional): destination of the leaf gradients (see peer.py)."""
+    `grad_sink` (peer.GradSink, optional): destination of the leaf gradients (see peer.py).
+    `colour_wait_event` (torch.cuda.Event, optional): the features are read only by a colour kernel that
+    waits for this event, so their all-gather may overlap projection, sorting and binning."""
     for name, t in (("features_dc", features_dc), ("features_rest", features_rest),
                     ("opacity", opacity_logits), ("scaling", log_scales), ("rotation", rotations)):
         if not t.is_contiguous() or t.dtype != torch.float32:
             raise RuntimeError(f"rasterize_model: {name} must be contiguous float32")
     return _RasterizeModel.apply(xyz, means2D, features_dc, features_rest, opacity_logits, log_scales,
-                                 rotations, raster_settings, sampling_offsets, grad_sink)
+                                 rotations, raster_settings, sampling_offsets, grad_sink, colour_wait_event)
 
 
 def model_supports_fusion(pc) -> bool:

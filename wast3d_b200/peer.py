@@ -37,23 +37,41 @@ class ArenaLayout:
     """Flat layout of several fp32 tensors, each padded to a multiple of 4 floats (16-byte accesses,
     segment boundaries on float4 units), plus the balanced contiguous shard of every rank."""
 
-    def __init__(self, numels: Sequence[int]):
-        self.slots: list[ArenaSlot] = []
+    def __init__(self, numels: Sequence[int], late: Sequence[bool] | None = None):
+        """`late[k]` places tensor k in the second ("late") class: the arena holds all early tensors
+        first, then all late ones (order kept inside a class), and every rank owns a balanced shard of
+        EACH class, so the two classes can be exchanged by two independent launches.  slots[] stays in
+        the caller's tensor order."""
+        late = [False] * len(numels) if late is None else [bool(x) for x in late]
+        if len(late) != len(numels):
+            raise ValueError("late must have one entry per tensor")
+        self.slots: list[ArenaSlot] = [None] * len(numels)  # type: ignore[list-item]
+        self.late = late
         off = 0
-        for n in numels:
-            n = int(n)
-            if n < 0:
-                raise ValueError("negative size")
-            n4 = (n + 3) // 4
-            self.slots.append(ArenaSlot(off, off + n4, n))
-            off += n4
+        for cls in (False, True):
+            if cls:
+                self.split4 = off
+            for k, n in enumerate(numels):
+                if late[k] != cls:
+                    continue
+                n = int(n)
+                if n < 0:
+                    raise ValueError("negative size")
+                n4 = (n + 3) // 4
+                self.slots[k] = ArenaSlot(off, off + n4, n)
+                off += n4
         self.total4 = off
 
-    def shard4(self, rank: int, world: int) -> tuple[int, int]:
-        """[begin4, end4) owned by `rank`: contiguous and balanced over the whole arena (a shard may
-        span several parameter groups; the kernel intersects it with the segment table)."""
+    def shard4(self, rank: int, world: int, cls: int | None = None) -> tuple[int, int]:
+        """[begin4, end4) owned by `rank`: contiguous and balanced over the whole arena (cls None; a
+        shard may span several parameter groups; the kernel intersects it with the segment table), or
+        over the early (cls 0) / late (cls 1) class only."""
         from .distributed import shard_bounds
-        return shard_bounds(self.total4, rank, world)
+        if cls is None:
+            return shard_bounds(self.total4, rank, world)
+        lo, hi = (0, self.split4) if cls == 0 else (self.split4, self.total4)
+        b, e = shard_bounds(hi - lo, rank, world)
+        return lo + b, lo + e
 
     def segments(self, hyper: Sequence[dict], steps: Sequence[int]) -> list[dict]:
         """One Adam segment per non-empty slot: float4 range + that group's hyper-parameters."""
@@ -64,6 +82,7 @@ class ArenaLayout:
             b1, b2 = h["betas"]
             out.append(dict(begin4=slot.begin4, end4=slot.end4, lr=float(h["lr"]), beta1=float(b1),
                             beta2=float(b2), eps=float(h["eps"]), step=int(t)))
+        out.sort(key=lambda d: d["begin4"])  # the kernel wants ascending, disjoint ranges
         return out
 
 
@@ -212,7 +231,12 @@ class PeerShardedAdam(torch.optim.Optimizer):
     `exp_avg` / `exp_avg_sq` (this rank's shard, flat)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, group=None, average=True,
-                 backend: str | None = None, timeout_s: float = 20.0):
+                 backend: str | None = None, timeout_s: float = 20.0, late_params=None):
+        """`late_params` (optional list of parameters, e.g. the SH features): these are exchanged by a
+        second launch on a side stream; step() returns with only the other ("early") parameters ordered
+        on the current stream, and `take_late_event()` hands the consumer the event behind which the late
+        ones are valid (render() passes it to the rasteriser, whose colour kernel is the only reader of
+        the features: their all-gather then overlaps projection, sorting and binning of the next view)."""
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.group = group
         self.average = average
@@ -231,14 +255,21 @@ class PeerShardedAdam(torch.optim.Optimizer):
             if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev:
                 raise RuntimeError("PeerShardedAdam: parameters must be contiguous float32 on one CUDA device")
         self.device = dev
-        self.layout = ArenaLayout([p.numel() for p in self._params])
+        late_ids = {id(p) for p in (late_params or [])}
+        late = [id(p) in late_ids for p in self._params]
+        if late_ids - {id(p) for p in self._params}:
+            raise ValueError("late_params must be a subset of the optimised parameters")
+        self.layout = ArenaLayout([p.numel() for p in self._params], late)
+        self.overlap_late = any(late) and not all(late)
         lib = _lib.load()
+        # two flag sets: the early and the late launch of a step may be in flight at the same time
         self._flag_bytes = (int(lib.wast3d_peer_flag_bytes()) + 255) // 256 * 256
+        head = 2 * self._flag_bytes
         region = self.layout.total4 * 16
-        self.buffer = PeerBuffer(self._flag_bytes + 2 * region, dev, group=group, backend=backend)
+        self.buffer = PeerBuffer(head + 2 * region, dev, group=group, backend=backend)
         base = self.buffer.local
-        self._param_flat = base[self._flag_bytes:self._flag_bytes + region].view(torch.float32)
-        self._grad_flat = base[self._flag_bytes + region:self._flag_bytes + 2 * region].view(torch.float32)
+        self._param_flat = base[head:head + region].view(torch.float32)
+        self._grad_flat = base[head + region:head + 2 * region].view(torch.float32)
         views = {}
         with torch.no_grad():
             for p, slot in zip(self._params, self.layout.slots):
@@ -247,25 +278,65 @@ class PeerShardedAdam(torch.optim.Optimizer):
                 p.data = pv
                 views[id(p)] = self._grad_flat[4 * slot.begin4:4 * slot.begin4 + slot.numel].view(p.shape)
         self.grad_sink = GradSink(views)
-        self.shard = self.layout.shard4(self.rank, self.world)
-        n = 4 * (self.shard[1] - self.shard[0])
-        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        # shards: one over the whole arena, or one per class (early, late)
+        if self.overlap_late:
+            self.shards = [self.layout.shard4(self.rank, self.world, 0), self.layout.shard4(self.rank, self.world, 1)]
+        else:
+            self.shards = [self.layout.shard4(self.rank, self.world)]
+        self.shard = self.shards[0]
+        n = 4 * sum(e - b for b, e in self.shards)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)      # [early shard | late shard]
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self._steps = [0] * len(self._params)
         self._epoch = 0
         W = self.world
-        self._grad_ptrs = (C.c_void_p * W)(*[q + self._flag_bytes + region for q in self.buffer.ptrs])
-        self._param_ptrs = (C.c_void_p * W)(*[q + self._flag_bytes for q in self.buffer.ptrs])
-        self._flag_ptrs = (C.c_void_p * W)(*self.buffer.ptrs)
+        self._grad_ptrs = (C.c_void_p * W)(*[q + head + region for q in self.buffer.ptrs])
+        self._param_ptrs = (C.c_void_p * W)(*[q + head for q in self.buffer.ptrs])
+        self._flag_ptrs = [(C.c_void_p * W)(*[q + k * self._flag_bytes for q in self.buffer.ptrs]) for k in (0, 1)]
         mc = self.buffer.mc_ptr if W > 1 else 0
-        self._mc_params = (mc + self._flag_bytes) if mc else None
-        self._mc_grads = (mc + self._flag_bytes + region) if mc else None
+        self._mc_params = (mc + head) if mc else None
+        self._mc_grads = (mc + head + region) if mc else None
         self.multicast = bool(mc)
+        self._side = torch.cuda.Stream(device=dev) if self.overlap_late else None
+        self._early_done = torch.cuda.Event() if self.overlap_late else None
+        self._late_event = torch.cuda.Event() if self.overlap_late else None
+        self._late_pending = False
         if W > 1:  # replicas start identical: rank 0's values win (the reference has one copy)
             dist.broadcast(self._param_flat, src=dist.get_global_rank(group, 0) if group is not None else 0,
                            group=group)
             torch.cuda.synchronize(dev)
             dist.barrier(group=group)
+
+    # -- late class
+    def take_late_event(self):
+        """The event behind which the late parameters of the last step() are valid, or None.  The taker
+        must make its stream wait for it before reading them (the rasteriser does: ABI v5
+        colour_wait_event); after that the current stream is ordered and nobody else needs to wait."""
+        if not self._late_pending:
+            return None
+        self._late_pending = False
+        return self._late_event
+
+    def sync(self):
+        """Order the current stream behind the late launch (for readers other than render())."""
+        ev = self.take_late_event()
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def _launch(self, cls: int, segs, scale: float):
+        b4, e4 = self.shards[cls]
+        lo, hi = (0, self.layout.total4) if not self.overlap_late else \
+            ((0, self.layout.split4) if cls == 0 else (self.layout.split4, self.layout.total4))
+        segs = [s for s in segs if s["begin4"] >= lo and s["end4"] <= hi]
+        arr = (_lib.AdamSegment * max(1, len(segs)))()
+        for k, s in enumerate(segs):
+            arr[k] = _lib.AdamSegment(s["begin4"], s["end4"], s["lr"], s["beta1"], s["beta2"], s["eps"], s["step"], 0)
+        moff = 16 * sum(e - b for b, e in self.shards[:cls])  # bytes into the moment arrays
+        rc = _lib.load().wast3d_peer_adam_step(
+            self.world, self.rank, self._grad_ptrs, self._param_ptrs, self._flag_ptrs[cls],
+            self._mc_grads, self._mc_params, self.exp_avg.data_ptr() + moff, self.exp_avg_sq.data_ptr() + moff,
+            b4, e4, arr, len(segs), scale, self._epoch, float(self.timeout_s), _lib.stream_ptr())
+        _lib.check(rc, "peer_adam_step")
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -273,6 +344,7 @@ class PeerShardedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        self.sync()  # a late launch nobody consumed: everything below touches the arena
         # gradients that were produced outside the sink (plain autograd) are copied into the arena
         for p in self._params:
             gv = self.grad_sink.view_for(p)
@@ -283,17 +355,20 @@ class PeerShardedAdam(torch.optim.Optimizer):
         for k in range(len(self._params)):
             self._steps[k] += 1
         segs = self.layout.segments(self._hyper_of, self._steps)
-        arr = (_lib.AdamSegment * max(1, len(segs)))()
-        for k, s in enumerate(segs):
-            arr[k] = _lib.AdamSegment(s["begin4"], s["end4"], s["lr"], s["beta1"], s["beta2"], s["eps"], s["step"], 0)
         self._epoch += 1
         scale = 1.0 / self.world if self.average else 1.0
         with torch.cuda.device(self.device):
-            rc = _lib.load().wast3d_peer_adam_step(
-                self.world, self.rank, self._grad_ptrs, self._param_ptrs, self._flag_ptrs,
-                self._mc_grads, self._mc_params, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(), self.shard[0], self.shard[1], arr, len(segs),
-                scale, self._epoch, float(self.timeout_s), _lib.stream_ptr())
-        _lib.check(rc, "peer_adam_step")
+            self._launch(0, segs, scale)
+            if self.overlap_late:
+                # the late launch starts when the early one is done (two persistent, flag-spinning grids
+                # of one GPU never compete for the SMs) and runs beside whatever the caller enqueues next
+                main = torch.cuda.current_stream(self.device)
+                self._early_done.record(main)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(self._early_done)
+                    self._launch(1, segs, scale)
+                    self._late_event.record(self._side)
+                self._late_pending = True
         return loss
 
     def zero_grad(self, set_to_none: bool = True):

@@ -293,11 +293,14 @@ class GaussianModel:
         self._opacity = nn.Parameter(opacities.requires_grad_(True))
 
     def training_setup(self, training_args: OptimizationParams = OptimizationParams(), fused: bool = False,
-                       peer: bool = False, group=None, average: bool = True, in_backward: bool = False):
+                       peer: bool = False, group=None, average: bool = True, in_backward: bool = False,
+                       overlap_features: bool = False):
         """Adam with the reference's six groups (scene/gaussian_model.py:154-163).
         `fused=True` swaps torch.optim.Adam for the library's fused Adam kernel (same maths);
         `peer=True` for the view-parallel single-kernel optimizer over NVLink peer memory
         (peer.PeerShardedAdam; parameters move into its arena, render() writes gradients there);
+        with `overlap_features=True` the SH features (81% of the bytes) are exchanged on a side stream
+        while the next render() projects, sorts and bins — render() orders its colour kernel behind them;
         `in_backward=True` (single GPU) applies the update inside the rasteriser's backward kernel
         (optim.BackwardFusedAdam): no gradient tensors, optimizer.step() launches nothing."""
         a = training_args
@@ -312,7 +315,9 @@ class GaussianModel:
         self.grad_sink = None
         if peer:
             from .peer import PeerShardedAdam
-            self.optimizer = PeerShardedAdam(groups, lr=0.0, eps=1e-15, group=group, average=average)
+            late = [self._features_dc, self._features_rest] if overlap_features else None
+            self.optimizer = PeerShardedAdam(groups, lr=0.0, eps=1e-15, group=group, average=average,
+                                             late_params=late)
             self.grad_sink = self.optimizer.grad_sink
         elif in_backward:
             from .optim import BackwardFusedAdam
