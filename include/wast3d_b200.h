@@ -343,7 +343,11 @@ int wast3d_pixel_loss_backward(int C, int H, int W, const float* img, const floa
  * gradients (multimem.ld_reduce) and broadcasts the parameters (multimem.st): ~1x the arena crosses
  * each NVLink direction per step instead of 2 (N-1)/N x with per-peer loads and stores.
  * A rank that waits longer than timeout_s (<= 0: 20 s) for a peer sets a sticky error
- * (wast3d_peer_error) instead of hanging the GPU. */
+ * (wast3d_peer_error) instead of hanging the GPU.
+ * max_ctas (ABI v5; 0 = as many as are resident at once): cap of the persistent grid.  A launch that is
+ * meant to run BESIDE other kernels (the side-stream exchange of the SH features, see
+ * wast3d_raster_params::colour_wait_event) saturates NVLink with a few dozen CTAs and must leave the
+ * other SMs to the rasteriser. */
 #define WAST3D_PEER_MAX_WORLD 8
 #define WAST3D_PEER_MAX_SEGMENTS 8
 #define WAST3D_PEER_HANDLE_BYTES 64
@@ -358,7 +362,8 @@ int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs, void* con
                           void* const* flag_ptrs, void* mc_grads, void* mc_params,
                           float* exp_avg, float* exp_avg_sq,
                           size_t shard_begin4, size_t shard_end4, const wast3d_adam_segment* segs,
-                          int nsegs, float grad_scale, unsigned epoch, double timeout_s, void* stream);
+                          int nsegs, float grad_scale, unsigned epoch, double timeout_s, int max_ctas,
+                          void* stream);
 /* 0 = no error; k > 0 = timed out waiting for rank k-1.  reset != 0 clears it. */
 int wast3d_peer_error(int reset);
 /* Peer-visible device memory for the arena: cudaMalloc'ed (zero-filled) and shared between the

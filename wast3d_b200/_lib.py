@@ -102,7 +102,7 @@ SIGNATURES = {
     "wast3d_pair_loss_backward": (_i, [C.POINTER(PairArgs), _vp, _vp, _i, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_peer_flag_bytes": (_sz, []),
     "wast3d_peer_adam_step": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _sz, _vp, _i, _f, C.c_uint,
-                                   C.c_double, _vp]),
+                                   C.c_double, _i, _vp]),
     "wast3d_peer_error": (_i, [_i]),
     "wast3d_peer_alloc": (_i, [_sz, C.POINTER(_vp)]),
     "wast3d_peer_export": (_i, [_vp, _vp]),

@@ -234,7 +234,7 @@ extern "C" int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs
                                      float* exp_avg, float* exp_avg_sq,
                                      size_t shard_begin4, size_t shard_end4,
                                      const wast3d_adam_segment* segs, int nsegs, float grad_scale,
-                                     unsigned epoch, double timeout_s, void* stream_v) {
+                                     unsigned epoch, double timeout_s, int max_ctas_arg, void* stream_v) {
     if (world < 1 || world > PEER_MAX_WORLD || rank < 0 || rank >= world || nsegs < 0 || nsegs > PEER_MAX_SEGS ||
         !grad_ptrs || !param_ptrs || shard_end4 < shard_begin4)
         return WAST3D_ERR_INVALID_ARGUMENT;
@@ -307,8 +307,10 @@ extern "C" int wast3d_peer_adam_step(int world, int rank, void* const* grad_ptrs
         {                                                                                                 \
             /* WAST3D_PEER_CTAS_PER_SM: cap the persistent grid so kernels of another stream can co-run */  \
             static const int cap = getenv("WAST3D_PEER_CTAS_PER_SM") ? atoi(getenv("WAST3D_PEER_CTAS_PER_SM")) : 0; \
+            const int max_ctas = max_ctas_arg;                                                            \
             const int use = (cap > 0 && cap < per_sm) ? cap : per_sm;                                     \
             if (blocks > (size_t)148 * use) blocks = (size_t)148 * use;                                   \
+            if (max_ctas > 0 && blocks > (size_t)max_ctas) blocks = (size_t)max_ctas;                     \
         }                                                                                                 \
         peer_adam_kernel<N, MCFLAG><<<(unsigned)blocks, PEER_THREADS, 0, s>>>(a);                         \
     }

@@ -297,10 +297,16 @@ class PeerShardedAdam(torch.optim.Optimizer):
         self._mc_params = (mc + head) if mc else None
         self._mc_grads = (mc + head + region) if mc else None
         self.multicast = bool(mc)
-        self._side = torch.cuda.Stream(device=dev) if self.overlap_late else None
+        # WAST3D_PEER_SIDE_PRIORITY: CUDA stream priority of the late launch (0 = default, -1.. = higher)
+        prio = int(os.environ.get("WAST3D_PEER_SIDE_PRIORITY", "0"))
+        self._side = torch.cuda.Stream(device=dev, priority=prio) if self.overlap_late else None
         self._early_done = torch.cuda.Event() if self.overlap_late else None
         self._late_event = torch.cuda.Event() if self.overlap_late else None
         self._late_pending = False
+        # persistent-grid cap of the late launch: it runs beside the next view's projection / sorting / binning;
+        # its duration does not change between 148 and 20 CTAs (NVLink/NVSwitch bound), the slowdown of the kernels
+        # beside it does (tools/diag_overlap.py, profiles/r01_overlap.md)
+        self.late_ctas = int(os.environ.get("WAST3D_PEER_LATE_CTAS", "20"))
         if W > 1:  # replicas start identical: rank 0's values win (the reference has one copy)
             dist.broadcast(self._param_flat, src=dist.get_global_rank(group, 0) if group is not None else 0,
                            group=group)
@@ -335,7 +341,8 @@ class PeerShardedAdam(torch.optim.Optimizer):
         rc = _lib.load().wast3d_peer_adam_step(
             self.world, self.rank, self._grad_ptrs, self._param_ptrs, self._flag_ptrs[cls],
             self._mc_grads, self._mc_params, self.exp_avg.data_ptr() + moff, self.exp_avg_sq.data_ptr() + moff,
-            b4, e4, arr, len(segs), scale, self._epoch, float(self.timeout_s), _lib.stream_ptr())
+            b4, e4, arr, len(segs), scale, self._epoch, float(self.timeout_s),
+            self.late_ctas if (cls == 1 and self.overlap_late) else 0, _lib.stream_ptr())
         _lib.check(rc, "peer_adam_step")
 
     @torch.no_grad()
