@@ -13,6 +13,26 @@
 
 namespace w3d {
 
+// One instruction, no registers, no shared memory: L2 fetches `bytes` (multiple of 16, 16-byte aligned
+// address) from HBM while the warp is busy with arithmetic; the later loads find the lines in L2.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+// Hint for a warp's contiguous tile of `rows` rows of `row_floats` floats starting at row `first`: skipped
+// when the tile is not 16-byte granular (a partial last warp with an odd row count).
+__device__ __forceinline__ void l2_prefetch_rows(const float* base, size_t first, int rows, int row_floats) {
+    if (base == nullptr) return;
+    const float* a = base + first * (size_t)row_floats;
+    const uint32_t bytes = (uint32_t)(rows * row_floats * 4);
+    if (bytes >= 16 && (bytes & 15) == 0 && (((size_t)a) & 15) == 0) l2_prefetch_bulk(a, bytes);
+}
+// WAST3D_L2_PREFETCH=0 disables the hints (A/B measurements)
+inline bool l2_prefetch_enabled() {
+    static const int on = getenv("WAST3D_L2_PREFETCH") ? atoi(getenv("WAST3D_L2_PREFETCH")) : 1;
+    return on != 0;
+}
+
+
 // Hyper-parameters cross the C ABI as float, but torch.optim.Adam derives 1-beta, beta^t and lr/(1-beta1^t)
 // from the Python double the user wrote (0.999, not 0.999f = 0.99900001287...): 1.0f - 0.999f is off by
 // 1.3e-5 relative from torch's (float)(1 - 0.999).  as_written() returns the double with the shortest

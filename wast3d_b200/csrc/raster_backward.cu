@@ -510,7 +510,9 @@ struct AdamSlot {  // one GaussianModel parameter group
 };
 struct AdamFused {
     AdamSlot g[6];  // xyz, f_dc, f_rest, opacity, scaling, rotation
+    int l2_prefetch;  // 1: each warp asks L2 for its parameter / moment tiles before the chain rule
 };
+
 __device__ __forceinline__ float adam_elem(float p, float g, float& m, float& v, const AdamSlot& s) {
     return adam_update(p, g, m, v, s.one_minus_b1, s.b2, s.one_minus_b2, s.step_size, s.inv_bc2_sqrt, s.eps);
 }
@@ -603,6 +605,25 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
     const int warp_first = blockIdx.x * GB_THREADS + warp * 32;
     const bool live = idx < P;
+    if (RAW && ADAM && af.l2_prefetch && warp_first < P) {
+        // The optimizer's operands of this warp's 32 Gaussians (parameters and both moments of the six groups,
+        // 22 KB, 76% of them the SH rest rows) are needed only after the chain rule below: one lane per
+        // (group, array) starts their HBM -> L2 transfer now.  Purely a hint: skipped where a tile is not
+        // 16-byte granular (partial last warp with an odd row count).
+        const int rows = min(32, P - warp_first);
+        if (lane < 18) {
+            const int grp = lane / 3, arr = lane - 3 * grp;
+            const AdamSlot& sl = af.g[grp];
+            const float* base = (arr == 0 ? sl.p : arr == 1 ? sl.m : sl.v);
+            const int fl = grp == 2 ? 3 * (M - 1) : grp == 3 ? 1 : grp == 5 ? 4 : 3;
+            l2_prefetch_rows(base, (size_t)warp_first, rows, fl);
+        }
+    } else if (!ADAM && af.l2_prefetch && warp_first < P && lane == 0 && shs != nullptr) {
+        // without the optimizer epilogue: the SH rows are staged only after the chain rule
+        const int rows = min(32, P - warp_first);
+        if (RAW) l2_prefetch_rows(shs_rest, (size_t)warp_first, rows, 3 * (M - 1));
+        else l2_prefetch_rows(shs, (size_t)warp_first, rows, 3 * M);
+    }
     const bool vis = live && radii[idx] > 0;
 
     float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, g2 = g0;
@@ -979,7 +1000,8 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
                  : adam_u == 2 ? gaussian_backward_kernel<true, true, 2> : gaussian_backward_kernel<true, true, 4>;
     auto gb = prm->raw_params ? (adam ? gb_adam : gaussian_backward_kernel<true, false>)
                               : gaussian_backward_kernel<false, false>;
-    const AdamFused af = adam ? *adam : AdamFused{};
+    AdamFused af = adam ? *adam : AdamFused{};
+    af.l2_prefetch = l2_prefetch_enabled() ? 1 : 0;
     gb<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, radii, prm->shs, prm->shs_rest, g.rec, g.clamped, prm->scales,
         prm->rotations, prm->scale_modifier, prm->cov3D_precomp, prm->viewmatrix, prm->projmatrix,
