@@ -304,9 +304,9 @@ class PeerShardedAdam(torch.optim.Optimizer):
         self._late_event = torch.cuda.Event() if self.overlap_late else None
         self._late_pending = False
         # persistent-grid cap of the late launch: it runs beside the next view's projection / sorting / binning;
-        # its duration does not change between 148 and 20 CTAs (NVLink/NVSwitch bound), the slowdown of the kernels
-        # beside it does (tools/diag_overlap.py, profiles/r01_overlap.md)
-        self.late_ctas = int(os.environ.get("WAST3D_PEER_LATE_CTAS", "20"))
+        # its duration barely changes between 148 and 12-20 CTAs (NVLink/NVSwitch bound), the slowdown of the kernels
+        # beside it does: every request it keeps in flight queues in front of theirs (profiles/r01_overlap.md)
+        self.late_ctas = int(os.environ.get("WAST3D_PEER_LATE_CTAS", "12" if self.multicast else "20"))
         if W > 1:  # replicas start identical: rank 0's values win (the reference has one copy)
             dist.broadcast(self._param_flat, src=dist.get_global_rank(group, 0) if group is not None else 0,
                            group=group)
