@@ -243,6 +243,11 @@ class GaussianModel:
 
     @property
     def get_features(self):
+        # a view-parallel optimizer may still be exchanging the features on its side stream
+        # (peer.PeerShardedAdam late_params): order the current stream behind it before reading them
+        sync = getattr(getattr(self, "optimizer", None), "sync", None)
+        if callable(sync):
+            sync()
         return torch.cat((self._features_dc, self._features_rest), dim=1)
 
     @property
