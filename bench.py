@@ -245,6 +245,44 @@ def implementation_info(sync):
     return {"grad_sync": sync, "peer_backend": PEER_BACKEND[0] if sync == "peer" else None, "loss": LOSS_KIND[0]}
 
 
+def c1_case(dev, n_content=50_000, n_style=10_000):
+    from wast3d_b200 import matching
+    from wast3d_b200.simple_knn._C import distCUDA2
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(n_content, 3, generator=g) * 1.3, torch.randn(n_style, 3, generator=g) * 1.3
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    idx_cpu = torch.cat([torch.cdist(a[i:i + 8192], b).argmin(1) for i in range(0, n_content, 8192)])
+    t1 = time.perf_counter()
+    d_cpu = torch.cat([torch.cdist(a[i:i + 4096], a).square().topk(4, largest=False).values[:, 1:].mean(1)
+                       for i in range(0, n_content, 4096)])
+    t2 = time.perf_counter()
+    ag, bg = a.to(dev), b.to(dev)
+
+    def gpu_ms(fn, reps=10):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, out
+
+    m_ms, (idx_gpu, _) = gpu_ms(lambda: matching.nn_match(ag, bg))
+    k_ms, d_gpu = gpu_ms(lambda: distCUDA2(ag))
+    pairs = n_content * n_style
+    return {"content_points": n_content, "style_points": n_style, "cores": os.cpu_count(),
+            "nn_match": {"cpu_torch_s": round(t1 - t0, 3), "gpu_ms": round(m_ms, 4),
+                         "cpu_pairs_per_s": pairs / (t1 - t0), "gpu_pairs_per_s": pairs / (m_ms * 1e-3),
+                         "indices_equal_fraction": float((idx_gpu.cpu() == idx_cpu).float().mean())},
+            "knn3": {"cpu_torch_s": round(t2 - t1, 3), "gpu_ms": round(k_ms, 4),
+                     "cpu_points_per_s": n_content / (t2 - t1), "gpu_points_per_s": n_content / (k_ms * 1e-3),
+                     "max_rel_diff": float(((d_gpu.cpu() - d_cpu).abs() / d_cpu.clamp_min(1e-12)).max())}}
+
+
 # --------------------------------------------------------------------------------- GPU arm
 def instance_count(pc, cam, bg):
     from wast3d_b200.diff_gaussian_rasterization import _C
@@ -627,6 +665,16 @@ def main():
         kms = a.elapsed_time(b) / 5
         extra["knn"] = {"points": spec.P, "ms": round(kms, 3), "points_per_s": spec.P / (kms * 1e-3),
                         "algorithmic_GBps": round(16.0 * spec.P / (kms * 1e-3) / 1e9, 2)}
+
+    if rank == 0 and world == 1 and not args.no_extra and not args.no_cpu_baseline:
+        # BASELINE.json configs[0] (the reference's CPU-runnable case): 50k content + 10k style points,
+        # nearest-neighbour matching exactly as the notebooks write it (torch.cdist -> argmin, rows in batches,
+        # 29.2...ipynb cell 58) and brute-force 3-NN mean squared distance (cdist + topk(4), 25.4...ipynb cell 73,
+        # standing in for distCUDA2) on the host cores, beside the same two operators on the GPU
+        try:
+            extra["c1_cpu_torch_vs_gpu"] = c1_case(dev)
+        except Exception as e:  # a side metric never fails the bench line
+            extra["c1_cpu_torch_vs_gpu"] = {"error": repr(e)}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
