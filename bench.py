@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--config", default="c3", choices=["c2", "c3", "c5"])
     ap.add_argument("--no-extra", action="store_true", help="skip the kNN / matching side metrics")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-stride", type=int, default=10,
+                    help="--impl reference / cpu_baseline: the CPU port runs every k-th Gaussian of the scene at the "
+                         "full resolution and the time is scaled by k (bounded sample)")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="pixel losses (L1 + TV + depth L2) through the fused kernels of csrc/loss.cu or as torch expressions")
     ap.add_argument("--sync", default="auto", choices=["auto", "peer", "nccl", "backward"],
@@ -205,7 +208,7 @@ def run_reference(args, spec):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    stride = 10
+    stride = max(1, args.ref_stride)
     cores = os.cpu_count() or 1
     cpu, inp, dpix, ddep = cpu_sample(spec, stride=stride, threads=cores)
     for _ in range(max(1, min(args.warmup, 2))):
@@ -678,7 +681,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        stride = 10
+        stride = max(1, args.ref_stride)
         cores = os.cpu_count() or 1
         cpu, inp, dpix, ddep = cpu_sample(spec, stride=stride, threads=cores)
         cpu_step(cpu, inp, dpix, ddep)
