@@ -105,11 +105,16 @@ def test_training_loop_with_overlapped_features_equals_plain_peer(built):
     ia, pa = run(False)
     ib, pb = run(True)
     assert torch.equal(ia[0], ib[0])
+    # K7's float atomics are unordered in both runs: where a gradient sum nearly cancels its sign (and with it
+    # Adam's first update, +-lr) may differ for an isolated element.  Stale features would move nearly every
+    # covered pixel by ~1e-3; so the bar is on the mean and on the fraction of outliers, not on the maximum.
     for a, b in zip(ia[1:], ib[1:]):
-        assert (a - b).abs().max().item() <= 2e-5
-    assert (ia[0] - ia[1]).abs().max().item() > 1e-3  # the views do differ
+        d = (a - b).abs()
+        assert d.mean().item() <= 2e-6 and (d > 2e-5).float().mean().item() <= 1e-3
+    assert (ia[0] - ia[1]).abs().mean().item() > 1e-3  # the views do differ
     for a, b in zip(pa, pb):
-        assert (a - b).abs().max().item() <= 1e-5 * max(1.0, b.abs().max().item())
+        d = (a - b).abs() / max(1.0, b.abs().max().item())
+        assert (d > 1e-5).float().mean().item() <= 1e-3
 
 
 def test_render_writes_gradients_into_the_arena(built):
