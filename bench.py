@@ -54,11 +54,13 @@ def parse():
                          "full resolution and the time is scaled by k (bounded sample)")
     ap.add_argument("--loss", default="fused", choices=["fused", "torch"],
                     help="pixel losses (L1 + TV + depth L2) through the fused kernels of csrc/loss.cu or as torch expressions")
-    ap.add_argument("--sync", default="auto", choices=["auto", "peer", "nccl", "backward"],
+    ap.add_argument("--sync", default="auto", choices=["auto", "peer", "nccl", "backward", "records"],
                     help="optimizer step: 'peer' = one fused reduce+Adam+broadcast kernel over NVLink peer memory "
                          "(peer.PeerShardedAdam), 'nccl' = chunked NCCL all-reduce overlapped with the dense fused Adam "
                          "(with one GPU: just the dense fused Adam); 'backward' (one GPU only) = the Adam update applied by the "
                          "rasteriser's per-Gaussian backward kernel, leaf gradients never written (optim.BackwardFusedAdam); "
+                         "'records' = STAGED, not yet run on a GPU: peer launch for the 11 geometry floats, SH features rebuilt "
+                         "on every rank from 16-byte colour records (peer_records.PeerRecordAdam); "
                          "'auto' = peer with N > 1, backward with N = 1")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],
                     help="peer arm: 1 = the SH features (81%% of the parameter bytes) are reduced / updated / all-gathered by "
@@ -245,7 +247,8 @@ def workload_config(spec, n):
 
 
 def implementation_info(sync):
-    return {"grad_sync": sync, "peer_backend": PEER_BACKEND[0] if sync == "peer" else None, "loss": LOSS_KIND[0]}
+    return {"grad_sync": sync, "peer_backend": PEER_BACKEND[0] if sync in ("peer", "records") else None,
+            "loss": LOSS_KIND[0]}
 
 
 def c1_case(dev, n_content=50_000, n_style=10_000):
@@ -336,10 +339,14 @@ def main():
     pc.spatial_lr_scale = 5.0
     if args.sync == "peer":
         opt = pc.training_setup(peer=True, average=True, overlap_features=bool(args.overlap))
+    elif args.sync == "records":
+        opt = pc.training_setup(peer=True, average=True, feature_records=True)
     elif args.sync == "backward":
         opt = pc.training_setup(in_backward=True)
     else:
         opt = pc.training_setup(fused=True)
+    if args.sync == "records":
+        PEER_BACKEND[0] = opt.buffer.backend + "+colour-records"
     if args.sync == "peer":
         PEER_BACKEND[0] = (opt.buffer.backend + ("+multicast" if opt.multicast else "")
                            + ("+overlapped-features" if opt.overlap_late else ""))
@@ -352,6 +359,7 @@ def main():
     dtgt_host = [(torch.rand(H, W, generator=gen) * 10).pin_memory() for _ in range(2)]
     tgt_dev = [t.to(dev) for t in tgt_host]
     dtgt_dev = [t.to(dev) for t in dtgt_host]
+    centres_host = [c.camera_center.detach().cpu() for c in cams]
     cam_host = [(c.world_view_transform.cpu().pin_memory(), c.full_proj_transform.cpu().pin_memory(),
                  c.camera_center.cpu().pin_memory()) for c in cams]
     params = pc.parameters()
@@ -406,7 +414,9 @@ def main():
         loss.backward()
         if host_io:
             stage_free[k].record(main)
-        if args.sync in ("peer", "backward"):
+        if args.sync == "records":
+            opt.set_view_centres(torch.stack([centres_host[(i * world + q) % len(cams)] for q in range(world)]))
+        if args.sync in ("peer", "backward", "records"):
             # peer: one kernel sums the N gradient replicas of this rank's shard over NVLink, applies Adam and
             # stores the new parameters into every replica (gradients were written into the peer arena by the
             # backward); backward: K8+K9 already applied the update, step() only closes the bookkeeping
@@ -710,7 +720,7 @@ def main():
                 "scene": {"visible_gaussians": vis, "tile_instances_R": R, "tile_instances_R_reference_rects": R_ref,
                           "tile_cut": args.tile_cut, "pixels": N}, "extra": extra}
         print(json.dumps(line), flush=True)
-    if args.sync == "peer":
+    if args.sync in ("peer", "records"):
         opt.check_peers()
         opt.close()
     if world > 1:

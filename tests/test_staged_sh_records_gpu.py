@@ -83,3 +83,44 @@ def test_sh_adam_from_records_equals_summed_gradients_then_adam(built, degree, P
     never = torch.stack([r[:, 3] == 0 for r in recs]).all(0)
     if never.any():  # never visible: zero gradient, zero moments -> parameters untouched
         assert torch.equal(p_dc[never], shs[:, :1][never])
+
+
+def test_training_loop_with_colour_records_equals_plain_peer(built):
+    """World size 1: peer_records.PeerRecordAdam (features rebuilt from this view's colour records, side stream)
+    against the single-launch peer optimizer over three optimisation steps through render()."""
+    from wast3d_b200.gaussian_renderer import render
+    from wast3d_b200.scene import GaussianModel, PipelineParams, orbit_cameras, synthetic_gaussians
+    arrs = synthetic_gaussians(20000, seed=5, log_scale_mu=-3.2)
+    cams = orbit_cameras(3, 4.03, 0.0, 0.6911, 160, 112, device="cuda", sphere=True)
+    bg = torch.zeros(3, device="cuda")
+    offs = -torch.rand(112, 160, 2, device="cuda")
+
+    def run(records):
+        m = GaussianModel.from_arrays(arrs, device="cuda")
+        m.spatial_lr_scale = 1.0
+        m.active_sh_degree = 3
+        opt = m.training_setup(peer=True, feature_records=records)
+        imgs = []
+        for cam in cams:
+            out = render(cam, m, PipelineParams(), bg, sampling_offsets=offs)
+            imgs.append(out["render"].detach().clone())
+            (out["render"].square().mean() + 0.1 * out["depth"].mean()).backward()
+            if records:
+                opt.set_view_centres(cam.camera_center.detach().cpu().reshape(1, 3))
+            opt.step(); opt.zero_grad()
+        if records:
+            opt.sync()
+        torch.cuda.synchronize()
+        res = imgs, [p.detach().clone() for p in m.parameters()]
+        opt.close()
+        return res
+
+    ia, pa = run(False)
+    ib, pb = run(True)
+    assert torch.equal(ia[0], ib[0])
+    for a, b in zip(ia[1:], ib[1:]):
+        d = (a - b).abs()
+        assert d.mean().item() <= 1e-5 and (d > 2e-5).float().mean().item() <= 1e-2
+    for a, b in zip(pa, pb):
+        d = (a - b).abs() / max(1.0, b.abs().max().item())
+        assert (d > 1e-5).float().mean().item() <= 1e-3

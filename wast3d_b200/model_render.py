@@ -139,6 +139,11 @@ class _RasterizeModel(torch.autograd.Function):
                     _lib.fptr(img, keep, torch.uint8), _lib.fptr(g_color, keep), _lib.fptr(g_depth, keep),
                     p(d_xyz), p(d_dc), p(d_rest), p(d_op), p(d_sc), p(d_rot), p(d_m2d), _lib.stream_ptr())
             _lib.check(st, "rasterize_model_backward")
+            if sink is not None and getattr(sink, "record_out", None) is not None:
+                # staged (peer_records.PeerRecordAdam): this view's 16-byte colour records for the feature exchange
+                from .peer_records import write_colour_records
+                with torch.cuda.device(dev):
+                    write_colour_records(sink, P, radii, geom, _lib.stream_ptr())
         elif sunk is not None:
             for v in sunk:
                 v.zero_()

@@ -299,7 +299,7 @@ class GaussianModel:
 
     def training_setup(self, training_args: OptimizationParams = OptimizationParams(), fused: bool = False,
                        peer: bool = False, group=None, average: bool = True, in_backward: bool = False,
-                       overlap_features: bool = False):
+                       overlap_features: bool = False, feature_records: bool = False):
         """Adam with the reference's six groups (scene/gaussian_model.py:154-163).
         `fused=True` swaps torch.optim.Adam for the library's fused Adam kernel (same maths);
         `peer=True` for the view-parallel single-kernel optimizer over NVLink peer memory
@@ -318,7 +318,14 @@ class GaussianModel:
             {"params": [self._rotation], "lr": a.rotation_lr, "name": "rotation"},
         ]
         self.grad_sink = None
-        if peer:
+        if peer and feature_records:
+            # staged for round 2 (peer_records.py): features updated from per-view colour records, never exchanged
+            from .peer_records import PeerRecordAdam
+            self.optimizer = PeerRecordAdam(groups, self._xyz, self._features_dc, self._features_rest,
+                                            lambda: self.active_sh_degree, lr=0.0, eps=1e-15, group=group,
+                                            average=average)
+            self.grad_sink = self.optimizer.grad_sink
+        elif peer:
             from .peer import PeerShardedAdam
             late = [self._features_dc, self._features_rest] if overlap_features else None
             self.optimizer = PeerShardedAdam(groups, lr=0.0, eps=1e-15, group=group, average=average,
