@@ -662,9 +662,20 @@ def main():
         t = torch.tensor([a.elapsed_time(b) / reps], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_s = float(t.item()) * 1e-3
+        pk = ROOT / "MEASURED_PEAKS.json"
+        bf16_peak = float(json.loads(pk.read_text()).get("bf16_tflops", 0.0)) if pk.exists() else 0.0
         extra["w2_match"] = {"content_clusters": Kc, "style_clusters": Ks, "ms": round(float(t.item()), 4),
-                             "pairs_per_s": Kc * Ks / (float(t.item()) * 1e-3),
-                             "exact_eval_fraction": st["exact_evals"] / max(st["pairs"], 1)}
+                             "pairs_per_s": Kc * Ks / t_s,
+                             "exact_eval_fraction": st["exact_evals"] / max(st["pairs"], 1),
+                             # algorithmic GEMM flops 2 Kc Ks D (D = 3: the -2ab term of the mean
+                             # distance) and executed 2 Kc Ks 16 (bf16 hi/lo split operands, one tcgen05.mma per
+                             # 128x128 tile); the inner dimension is far too small for the tensor pipe to be the
+                             # bound: the fraction is reported, not targeted
+                             "gemm_algorithmic_TFLOPs": 2.0 * Kc * Ks * 3 / t_s / 1e12,
+                             "gemm_executed_TFLOPs": 2.0 * Kc * Ks * 16 / t_s / 1e12,
+                             "tensor_pipe_frac_of_measured_bf16_peak":
+                                 (2.0 * Kc * Ks * 16 / t_s / 1e12 / bf16_peak) if bf16_peak > 0 else None}
         pts = pc.get_xyz.detach()
         for _ in range(2):
             distCUDA2(pts)
@@ -677,7 +688,8 @@ def main():
         barrier()
         kms = a.elapsed_time(b) / 5
         extra["knn"] = {"points": spec.P, "ms": round(kms, 3), "points_per_s": spec.P / (kms * 1e-3),
-                        "algorithmic_GBps": round(16.0 * spec.P / (kms * 1e-3) / 1e9, 2)}
+                        "algorithmic_GBps": round(16.0 * spec.P / (kms * 1e-3) / 1e9, 2),
+                        "sort_inclusive_GBps": round(80.0 * spec.P / (kms * 1e-3) / 1e9, 2)}
 
     if rank == 0 and world == 1 and not args.no_extra and not args.no_cpu_baseline:
         # BASELINE.json configs[0] (the reference's CPU-runnable case): 50k content + 10k style points,
