@@ -23,6 +23,11 @@ int wast3d_staged_colour_records(int P, const int* radii, const void* geom_buffe
 int wast3d_staged_sh_adam_from_records(int P, int D, int M, int views, const float* const* records,
                                        const float* campos_host, const float* xyz, float grad_scale,
                                        const wast3d_adam_group* dc, const wast3d_adam_group* rest, void* stream);
+/* CPU emulation of the kernel behind wast3d_staged_sh_adam_from_records for tests without a GPU: the same
+ * per-Gaussian accumulation statements compiled for the host, Adam with IEEE sqrt / division.  HOST pointers. */
+int wast3d_staged_sh_adam_host_emulation(int P, int D, int M, int views, const float* const* records,
+                                         const float* campos_host, const float* xyz, float grad_scale,
+                                         const wast3d_adam_group* dc, const wast3d_adam_group* rest);
 #ifdef __cplusplus
 }
 #endif

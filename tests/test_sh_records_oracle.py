@@ -37,3 +37,63 @@ def test_sh_gradient_from_colour_records_equals_sum_of_views(built, degree):
     assert np.all(got[:, (degree + 1) ** 2:] == 0) and np.all(want[:, (degree + 1) ** 2:] == 0)
     # records are 16 bytes per Gaussian and view
     assert recs[0].dtype == np.float32 and recs[0].shape == (xyz.shape[0], 4)
+
+
+def test_staged_kernel_statements_on_the_cpu(built):
+    """csrc/sh_adam.cu compiles its per-Gaussian accumulation for host and device; the host emulation entry point
+    runs those statements on the CPU: gradient rebuilt from the records (checked through two Adam steps from zero
+    moments, where the update is -lr * g / (|g| + eps) and then depends on g's magnitude) against the numpy
+    restatement + a numpy Adam."""
+    import ctypes as C
+    from oracle import cpu, sh_records
+
+    class AdamGroup(C.Structure):
+        _fields_ = [("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("lr", C.c_float),
+                    ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int), ("reserved", C.c_int)]
+
+    lib = C.CDLL(str(built["cuda"]))
+    f = lib.wast3d_staged_sh_adam_host_emulation
+    f.restype = C.c_int
+    f.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
+    degree, P = 3, 2001
+    views = []
+    for cam_index in (0, 2, 5):
+        case = raster_case(P=P, W=96, H=64, seed=8, cam_index=cam_index, degree=degree, log_scale_mu=-3.0)
+        inp = cpu.RasterInputs(**case)
+        fwd = cpu.forward_all(inp)
+        rng = np.random.default_rng(cam_index)
+        g = cpu.backward_all(inp, fwd, rng.normal(size=(3, 64, 96)).astype(np.float32),
+                             rng.normal(size=(64, 96)).astype(np.float32))
+        views.append((case, sh_records.colour_records(g["dL_dcolor"], fwd["pre"]["clamped"], fwd["pre"]["radii"])))
+    xyz = np.ascontiguousarray(views[0][0]["means3D"], np.float32)
+    shs = views[0][0]["shs"]
+    M = shs.shape[1]
+    recs = [np.ascontiguousarray(r, np.float32) for _, r in views]
+    campos = np.ascontiguousarray(np.stack([c["campos"] for c, _ in views]), np.float32)
+    scale = np.float32(1.0 / len(views))
+    grad = (sh_records.sh_grad_from_records(xyz, list(campos), recs, degree, M) * scale).astype(np.float32)
+
+    def np_adam(p, g, m, v, lr, t, b1=0.9, b2=0.999, eps=1e-15):
+        m[:] = m + np.float32(1 - b1) * (g - m)
+        v[:] = v * np.float32(b2) + np.float32(1 - b2) * g * g
+        step = np.float32(lr / (1 - b1 ** t))
+        inv = np.float32(1.0 / np.sqrt(1 - b2 ** t))
+        p[:] = p - step * (m / (np.sqrt(v) * inv + np.float32(eps)))
+
+    lrs = (2.5e-3, 1.25e-4)
+    e_dc, e_rest = shs[:, :1].copy(), shs[:, 1:].copy()
+    em = [np.zeros_like(e_dc), np.zeros_like(e_dc), np.zeros_like(e_rest), np.zeros_like(e_rest)]
+    p_dc, p_rest = np.ascontiguousarray(e_dc.copy()), np.ascontiguousarray(e_rest.copy())
+    sm = [np.zeros_like(p_dc), np.zeros_like(p_dc), np.zeros_like(p_rest), np.zeros_like(p_rest)]
+    ptrs = (C.c_void_p * len(recs))(*[r.ctypes.data for r in recs])
+    for t in (1, 2):
+        np_adam(e_dc, grad[:, :1], em[0], em[1], lrs[0], t)
+        np_adam(e_rest, grad[:, 1:], em[2], em[3], lrs[1], t)
+        gd = AdamGroup(p_dc.ctypes.data, sm[0].ctypes.data, sm[1].ctypes.data, lrs[0], 0.9, 0.999, 1e-15, t, 0)
+        gr = AdamGroup(p_rest.ctypes.data, sm[2].ctypes.data, sm[3].ctypes.data, lrs[1], 0.9, 0.999, 1e-15, t, 0)
+        assert f(P, degree, M, len(recs), ptrs, campos.ctypes.data, xyz.ctypes.data, float(scale), C.byref(gd), C.byref(gr)) == 0
+    assert np.abs(p_dc - shs[:, :1]).max() > 1e-3  # something moved
+    # moments carry the gradient itself: first moment after two steps = (1-b1)(1 + b1) g
+    want_m = (np.float32(0.1) * np.float32(1.9)) * grad[:, 1:]
+    assert np.abs(sm[2] - want_m).max() <= 1e-5 * max(1e-12, np.abs(want_m).max())
+    assert np.abs(p_dc - e_dc).max() <= 1e-6 and np.abs(p_rest - e_rest).max() <= 1e-6

@@ -42,6 +42,71 @@ struct ShAdamArgs {
     int l2_prefetch;
 };
 
+// round-to-nearest product / sum that the compiler may not contract into an FMA (device), plain on the host
+__host__ __device__ inline float mul_rn(float x, float y) {
+#ifdef __CUDA_ARCH__
+    return __fmul_rn(x, y);
+#else
+    volatile float r = x * y;
+    return r;
+#endif
+}
+__host__ __device__ inline float add_rn(float x, float y) {
+#ifdef __CUDA_ARCH__
+    return __fadd_rn(x, y);
+#else
+    volatile float r = x + y;
+    return r;
+#endif
+}
+
+// Gradient of Gaussian `idx` summed over the views: dc[3] (coefficient 0) and mine[3(k-1) + c] (coefficients 1..).
+// __host__ __device__ so that wast3d_staged_sh_adam_host_emulation can run the very same statements on the CPU.
+__host__ __device__ inline void accumulate_views(const ShAdamArgs& a, int idx, float* mine, float dc[3]) {
+    constexpr float C0 = 0.28209479177387814f, C1 = 0.4886025119029199f;
+    constexpr float C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f, -1.0925484305920792f,
+                             0.5462742152960396f};
+    constexpr float C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f, 0.3731763325901154f,
+                             -0.4570457994644658f, 1.445305721320277f, -0.5900435899266435f};
+    const int M = a.M, D = a.D;
+    const int rest_floats = 3 * (M - 1);
+    for (int q = 0; q < rest_floats; ++q) mine[q] = 0.f;
+    const float px = a.xyz[3 * (size_t)idx], py = a.xyz[3 * (size_t)idx + 1], pz = a.xyz[3 * (size_t)idx + 2];
+    const int ncoef = M < (D + 1) * (D + 1) ? M : (D + 1) * (D + 1);
+    for (int vw = 0; vw < a.views; ++vw) {
+        const float4 r = a.records[vw][idx];
+        if (r.w == 0.f) continue;  // culled in this view: contributes exactly zero
+        // direction and basis as gaussian_backward_kernel / backward.cu:36-128 write them
+        const float dx = px - a.campos[vw][0], dy = py - a.campos[vw][1], dz = pz - a.campos[vw][2];
+        const float len = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float x = dx / len, y = dy / len, z = dz / len;
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        float basis[16];
+        basis[0] = C0;
+        basis[1] = -C1 * y; basis[2] = C1 * z; basis[3] = -C1 * x;
+        basis[4] = C2[0] * xy; basis[5] = C2[1] * yz; basis[6] = C2[2] * (2.f * zz - xx - yy);
+        basis[7] = C2[3] * xz; basis[8] = C2[4] * (xx - yy);
+        basis[9] = C3[0] * y * (3.f * xx - yy); basis[10] = C3[1] * xy * z;
+        basis[11] = C3[2] * y * (4.f * zz - xx - yy);
+        basis[12] = C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
+        basis[13] = C3[4] * x * (4.f * zz - xx - yy); basis[14] = C3[5] * z * (xx - yy);
+        basis[15] = C3[6] * x * (xx - 3.f * yy);
+        const float rgb[3] = {r.x, r.y, r.z};
+        // product rounded, then added in view order: the bits an all-reduce in rank order would produce
+        for (int c = 0; c < 3; ++c) dc[c] = add_rn(dc[c], mul_rn(basis[0], rgb[c]));
+        for (int k = 1; k < 16; ++k) {
+            if (k < ncoef) {
+                for (int c = 0; c < 3; ++c)
+                    mine[3 * (k - 1) + c] = add_rn(mine[3 * (k - 1) + c], mul_rn(basis[k], rgb[c]));
+            }
+        }
+    }
+    if (a.grad_scale != 1.f) {
+        for (int c = 0; c < 3; ++c) dc[c] *= a.grad_scale;
+        for (int q = 0; q < rest_floats; ++q) mine[q] *= a.grad_scale;
+    }
+}
+
 __device__ __forceinline__ float upd(float p, float g, float& m, float& v, const Slot& s) {
     return adam_update(p, g, m, v, s.one_minus_b1, s.b2, s.one_minus_b2, s.step_size, s.inv_bc2_sqrt, s.eps);
 }
@@ -83,45 +148,7 @@ sh_adam_records_kernel(const __grid_constant__ ShAdamArgs a) {
     float* mine = s_g[warp] + lane * rest_floats;  // this Gaussian's row of rest gradients: mine[3(k-1) + c]
     float dc[3] = {0.f, 0.f, 0.f};
     if (live) {
-        for (int q = 0; q < rest_floats; ++q) mine[q] = 0.f;
-        const float3 pos = make_float3(a.xyz[3 * (size_t)idx], a.xyz[3 * (size_t)idx + 1], a.xyz[3 * (size_t)idx + 2]);
-        const int ncoef = min(M, (D + 1) * (D + 1));
-        for (int vw = 0; vw < a.views; ++vw) {
-            const float4 r = a.records[vw][idx];
-            if (r.w == 0.f) continue;  // culled in this view: contributes exactly zero
-            // direction and basis exactly as gaussian_backward_kernel / backward.cu:36-128 write them
-            const float3 dir_orig = make_float3(pos.x - a.campos[vw][0], pos.y - a.campos[vw][1], pos.z - a.campos[vw][2]);
-            const float len = sqrtf(dir_orig.x * dir_orig.x + dir_orig.y * dir_orig.y + dir_orig.z * dir_orig.z);
-            const float x = dir_orig.x / len, y = dir_orig.y / len, z = dir_orig.z / len;
-            const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
-            float basis[16];
-            basis[0] = SH_C0;
-            basis[1] = -SH_C1 * y; basis[2] = SH_C1 * z; basis[3] = -SH_C1 * x;
-            basis[4] = SH_C2[0] * xy; basis[5] = SH_C2[1] * yz; basis[6] = SH_C2[2] * (2.f * zz - xx - yy);
-            basis[7] = SH_C2[3] * xz; basis[8] = SH_C2[4] * (xx - yy);
-            basis[9] = SH_C3[0] * y * (3.f * xx - yy); basis[10] = SH_C3[1] * xy * z;
-            basis[11] = SH_C3[2] * y * (4.f * zz - xx - yy);
-            basis[12] = SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy);
-            basis[13] = SH_C3[4] * x * (4.f * zz - xx - yy); basis[14] = SH_C3[5] * z * (xx - yy);
-            basis[15] = SH_C3[6] * x * (xx - 3.f * yy);
-            const float rgb[3] = {r.x, r.y, r.z};
-            // product rounded, then added in view order: the bits an all-reduce in rank order would produce
-#pragma unroll
-            for (int c = 0; c < 3; ++c) dc[c] = __fadd_rn(dc[c], __fmul_rn(basis[0], rgb[c]));
-#pragma unroll
-            for (int k = 1; k < 16; ++k) {
-                if (k < ncoef) {
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        mine[3 * (k - 1) + c] = __fadd_rn(mine[3 * (k - 1) + c], __fmul_rn(basis[k], rgb[c]));
-                }
-            }
-        }
-        if (a.grad_scale != 1.f) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) dc[c] *= a.grad_scale;
-            for (int q = 0; q < rest_floats; ++q) mine[q] *= a.grad_scale;
-        }
+        accumulate_views(a, idx, mine, dc);
         // _features_dc [P,1,3]: three elements per Gaussian
         float p[3], m[3], v[3];
 #pragma unroll
@@ -248,5 +275,45 @@ extern "C" int wast3d_staged_sh_adam_from_records(int P, int D, int M, int views
     ProfScope ps(PS_ADAM, s);
     sh_adam_records_kernel<<<(P + SA_THREADS - 1) / SA_THREADS, SA_THREADS, 0, s>>>(a);
     W3D_AFTER_LAUNCH(s, false);
+    return WAST3D_OK;
+}
+
+// CPU emulation of sh_adam_records_kernel for the tests (same accumulate_views statements; Adam with IEEE sqrt and
+// division instead of the SFU approximations).  All pointers are HOST pointers.
+extern "C" int wast3d_staged_sh_adam_host_emulation(int P, int D, int M, int views, const float* const* records,
+                                                    const float* campos_host, const float* xyz, float grad_scale,
+                                                    const wast3d_adam_group* dc, const wast3d_adam_group* rest) {
+    if (P < 0 || D < 0 || D > 3 || M < 1 || M > 16 || views < 1 || views > SA_MAX_VIEWS || !records || !campos_host ||
+        !dc || (M > 1 && !rest) || (P > 0 && !xyz))
+        return WAST3D_ERR_INVALID_ARGUMENT;
+    ShAdamArgs a{};
+    for (int v = 0; v < views; ++v) {
+        a.records[v] = reinterpret_cast<const float4*>(records[v]);
+        for (int c = 0; c < 3; ++c) a.campos[v][c] = campos_host[3 * v + c];
+    }
+    a.xyz = xyz;
+    int st = fill_slot(a.dc, *dc);
+    if (st != WAST3D_OK) return st;
+    if (M > 1 && (st = fill_slot(a.rest, *rest)) != WAST3D_OK) return st;
+    a.P = P; a.D = D; a.M = M; a.views = views; a.grad_scale = grad_scale;
+    const int rest_floats = 3 * (M - 1);
+    auto host_upd = [](float p, float g, float& m, float& v, const Slot& s) {
+        m = m + s.one_minus_b1 * (g - m);
+        v = v * s.b2 + s.one_minus_b2 * g * g;
+        return p - s.step_size * (m / (sqrtf(v) * s.inv_bc2_sqrt + s.eps));
+    };
+    float row[SA_MAX_REST];
+    for (int idx = 0; idx < P; ++idx) {
+        float g0[3] = {0.f, 0.f, 0.f};
+        accumulate_views(a, idx, row, g0);
+        for (int c = 0; c < 3; ++c) {
+            const size_t e = 3 * (size_t)idx + c;
+            a.dc.p[e] = host_upd(a.dc.p[e], g0[c], a.dc.m[e], a.dc.v[e], a.dc);
+        }
+        for (int q = 0; q < rest_floats; ++q) {
+            const size_t e = (size_t)idx * rest_floats + q;
+            a.rest.p[e] = host_upd(a.rest.p[e], row[q], a.rest.m[e], a.rest.v[e], a.rest);
+        }
+    }
     return WAST3D_OK;
 }
