@@ -97,3 +97,54 @@ def test_staged_kernel_statements_on_the_cpu(built):
     want_m = (np.float32(0.1) * np.float32(1.9)) * grad[:, 1:]
     assert np.abs(sm[2] - want_m).max() <= 1e-5 * max(1e-12, np.abs(want_m).max())
     assert np.abs(p_dc - e_dc).max() <= 1e-6 and np.abs(p_rest - e_rest).max() <= 1e-6
+
+
+def _record_exchange_job(rank, world):
+    """One view-parallel step at world size 2 over gloo with REAL per-view gradients (CPU oracle): the features'
+    update rebuilt on every rank from all-gathered 16-byte colour records against all-reduce(dL/dsh) + Adam."""
+    import torch
+    import torch.distributed as dist
+    from oracle import cpu, sh_records
+    cpu.set_threads(2)
+    degree, P = 2, 1500
+    case = raster_case(P=P, W=64, H=48, seed=6, cam_index=1 + 3 * rank, degree=degree, log_scale_mu=-3.0)
+    inp = cpu.RasterInputs(**case)
+    fwd = cpu.forward_all(inp)
+    rng = np.random.default_rng(50 + rank)
+    g = cpu.backward_all(inp, fwd, rng.normal(size=(3, 48, 64)).astype(np.float32),
+                         rng.normal(size=(48, 64)).astype(np.float32))
+    xyz, shs = case["means3D"], case["shs"]
+    M = shs.shape[1]
+
+    def adam1(p, grad, lr):  # first step from zero moments
+        m = np.float32(0.1) * grad
+        v = np.float32(1 - 0.999) * grad * grad
+        return p - np.float32(lr / (1 - 0.9)) * (m / (np.sqrt(v) * np.float32(1 / np.sqrt(1 - 0.999)) + np.float32(1e-15)))
+
+    # (a) textbook: all-reduce (average) of the SH gradients
+    gsum = torch.from_numpy(g["dL_dsh"].copy())
+    dist.all_reduce(gsum)
+    base = adam1(shs, (gsum.numpy() / np.float32(world)).astype(np.float32), 2.5e-3)
+    # (b) all-gather of the colour records and camera centres; every rank rebuilds the summed gradient
+    rec = torch.from_numpy(sh_records.colour_records(g["dL_dcolor"], fwd["pre"]["clamped"], fwd["pre"]["radii"]))
+    recs = [torch.empty_like(rec) for _ in range(world)]
+    dist.all_gather(recs, rec)
+    cam = torch.from_numpy(case["campos"].astype(np.float32))
+    cams = [torch.empty_like(cam) for _ in range(world)]
+    dist.all_gather(cams, cam)
+    grad = sh_records.sh_grad_from_records(xyz, [c.numpy() for c in cams], [r.numpy() for r in recs], degree, M)
+    mine = adam1(shs, (grad / np.float32(world)).astype(np.float32), 2.5e-3)
+    # replicas: every rank computed the same bits
+    flat = torch.from_numpy(mine.copy())
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    return {"identical": bool(torch.equal(flat, ref)), "max_diff": float(np.abs(mine - base).max()),
+            "moved": float(np.abs(mine - shs).max()), "bytes_per_gaussian": rec.element_size() * rec.shape[1]}
+
+
+def test_colour_record_exchange_world2_gloo(built):
+    from tests.test_distributed_gloo import _run
+    out = _run(_record_exchange_job, world=2)
+    for o in out:
+        assert o["identical"] and o["bytes_per_gaussian"] == 16
+        assert o["moved"] > 1e-3 and o["max_diff"] <= 2e-6
