@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define WAST3D_ABI_VERSION 5
+#define WAST3D_ABI_VERSION 6
 
 enum wast3d_status {
     WAST3D_OK = 0,
@@ -174,6 +174,14 @@ int wast3d_raster_export_state(const wast3d_raster_params* prm, int num_rendered
  * radius rectangles (auxiliary.h:46-56), which reproduces its num_rendered and point list exactly. */
 int wast3d_set_tile_cut(int mode);
 
+/* Summation order of the tile backward (process-wide; returns the previous mode, any other `mode` value only
+ * queries).  0 (default; env WAST3D_DETERMINISTIC) = one float atomic per (warp, Gaussian) hit and gradient
+ * slot, unordered like the reference's atomicAdds (backward.cu:576-583); 1 = no float atomics: per-instance
+ * partial records are added per Gaussian in point-list order, so gradients (and everything downstream: Adam,
+ * the next image) are bit-reproducible from run to run.  Slower and memory hungry (48 B per instance); meant
+ * for tests that compare two schedules of the same computation bit for bit. */
+int wast3d_set_deterministic(int mode);
+
 /* Replaces markVisible -> checkFrustum (rasterize_points.cu:208-227,
  * rasterizer_impl.cu:54-66,141-153).  present is bool[P] (1 byte each). */
 int wast3d_mark_visible(int P, const float* means3D, const float* viewmatrix,
@@ -200,9 +208,10 @@ int wast3d_cluster_stats(int n, int K, const float* points, const int32_t* label
 
 /* wast3d_nn_match: for each query row a[i] ([Na,3]) the index of the nearest b[j] ([Nb,3])
  * = argmin_j cdist(a,b)[i,j] with ties to the lowest j; out_dist = that Euclidean distance.
- * Decided on fp32 values computed in torch.cdist's operation order (oracle/match_oracle.c). */
+ * Decided on fp32 values computed in torch.cdist's operation order (oracle/match_oracle.c).
+ * scratch / scratch_bytes: see wast3d_match_scratch_bytes (ABI v6). */
 int wast3d_nn_match(int Na, int Nb, const float* a, const float* b, int32_t* out_idx,
-                    float* out_dist, void* stream);
+                    float* out_dist, void* scratch, size_t scratch_bytes, void* stream);
 
 /* wast3d_cdist_topk: the k smallest entries of every row of torch.cdist(a, b) ([Na,3] x [Nb,3])
  * without materialising the matrix: out_dist [Na,k] ascending, out_idx [Na,k] int32, rows ordered by
@@ -286,10 +295,16 @@ int wast3d_pair_loss_backward(const wast3d_pair_args* args, const float* target,
  * ties to the lowest j; out_cost = that W2^2 (fp32, fixed operation order, see
  * oracle/match_oracle.c).  A tcgen05 GEMM over augmented bf16-split descriptors gives a
  * lower bound per pair; only pairs that can beat the row's running best get the exact
- * Bures term.  stats (optional, [4] uint64): pairs, exact_evals, gemm_tiles, reserved. */
+ * Bures term.  stats (optional, DEVICE [4] uint64): pairs, exact_evals, gemm_tiles, error word.
+ * ABI v6 — like wast3d_knn_dist2 the call takes caller scratch: wast3d_match_scratch_bytes(Kc, Ks)
+ * bytes, 128-byte aligned, contents irrelevant, reusable across calls on the same stream (NULL = a
+ * stream-ordered allocation inside the call).  The call never synchronises the stream: the (never
+ * expected) tensor-core barrier time-out is reported as out_idx[i] = -2, out_cost[i] = NaN for every row
+ * and a non-zero stats[3]. */
+size_t wast3d_match_scratch_bytes(int Kc, int Ks);
 int wast3d_w2_match(int Kc, int Ks, const float* mean_c, const float* cov_c,
                     const float* mean_s, const float* cov_s, int32_t* out_idx, float* out_cost,
-                    unsigned long long* stats, void* stream);
+                    unsigned long long* stats, void* scratch, size_t scratch_bytes, void* stream);
 
 /* Test hook: wast3d_w2_match that additionally writes the tensor-core lower-bound matrix
  * (margin already subtracted) to lb_dump [Kc,Ks]; used by tests to validate the tcgen05 path. */

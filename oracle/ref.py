@@ -23,6 +23,7 @@ def lib():
         _lib = C.CDLL(str(_PATH))
         _lib.ref_ctx_create.restype = C.c_void_p
         _lib.ref_ctx_destroy.argtypes = [C.c_void_p]
+        _lib.ref_ctx_set_async.argtypes = [C.c_void_p, C.c_int]
     return _lib
 
 
@@ -36,8 +37,11 @@ def _p(t):
 class RefRasterizer:
     """One forward (+ optional backward) of the reference rasteriser on raw tensors."""
 
-    def __init__(self):
+    def __init__(self, asynchronous=False):
+        """asynchronous=True: the wrapper does not cudaDeviceSynchronize after each call (event timing)."""
         self.ctx = C.c_void_p(lib().ref_ctx_create())
+        self.asynchronous = bool(asynchronous)
+        lib().ref_ctx_set_async(self.ctx, int(self.asynchronous))
 
     def __del__(self):
         try:
@@ -47,18 +51,22 @@ class RefRasterizer:
 
     def forward(self, *, bg, means3D, opacities, view, proj, campos, W, H, tan_fovx, tan_fovy,
                 shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None,
-                sampling_offsets=None, D=0, scale_modifier=1.0, prefiltered=False):
-        torch.cuda.synchronize()
+                sampling_offsets=None, D=0, scale_modifier=1.0, prefiltered=False, offsets_prepadded=False):
+        if not self.asynchronous:
+            torch.cuda.synchronize()
         dev = means3D.device
         P = means3D.shape[0]
         M = shs.shape[1] if shs is not None else 0
-        if sampling_offsets is None:  # the reference dereferences it unconditionally (forward.cu:287)
-            sampling_offsets = torch.zeros(H, W, 2, device=dev)
-        # the reference reads sampling_offsets / dL_ddepth of out-of-image threads:
-        # pad so that those reads stay inside an allocation
-        pad = torch.zeros(((H + 16) * (W + 16), 2), device=dev)
-        pad[: H * W] = sampling_offsets.reshape(-1, 2)
-        self.offsets = pad
+        if offsets_prepadded:  # caller padded once (ref_step.pad_offsets): nothing extra inside a timed step
+            self.offsets = sampling_offsets
+        else:
+            if sampling_offsets is None:  # the reference dereferences it unconditionally (forward.cu:287)
+                sampling_offsets = torch.zeros(H, W, 2, device=dev)
+            # the reference reads sampling_offsets / dL_ddepth of out-of-image threads:
+            # pad so that those reads stay inside an allocation
+            pad = torch.zeros(((H + 16) * (W + 16), 2), device=dev)
+            pad[: H * W] = sampling_offsets.reshape(-1, 2)
+            self.offsets = pad
         self.args = dict(bg=bg, means3D=means3D, view=view, proj=proj, campos=campos, W=W, H=H,
                          tan_fovx=tan_fovx, tan_fovy=tan_fovy, shs=shs, colors_precomp=colors_precomp,
                          scales=scales, rotations=rotations, cov3D_precomp=cov3D_precomp, D=D, M=M,
@@ -86,11 +94,12 @@ class RefRasterizer:
              "clamped": torch.zeros(P, 3, dtype=torch.uint8, device=dev),
              "final_T": torch.zeros(a["H"], a["W"], device=dev),
              "n_contrib": torch.zeros(a["H"], a["W"], dtype=torch.int32, device=dev),
-             "point_list": torch.zeros(max(self.R, 1), dtype=torch.int32, device=dev)}
+             "point_list": torch.zeros(max(self.R, 1), dtype=torch.int32, device=dev),
+             "ranges": torch.zeros(((a["W"] + 15) // 16) * ((a["H"] + 15) // 16), 2, dtype=torch.int32, device=dev)}
         rc = lib().ref_raster_export_state(
             self.ctx, _p(o["depths"]), _p(o["means2D"]), _p(o["cov3D"]), _p(o["conic_opacity"]),
             _p(o["rgb"]), _p(o["tiles_touched"]), _p(o["clamped"]), _p(o["final_T"]),
-            _p(o["n_contrib"]), _p(o["point_list"]))
+            _p(o["n_contrib"]), _p(o["point_list"]), _p(o["ranges"]))
         assert rc == 0
         o["point_list"] = o["point_list"][: self.R]
         # untouched entries of culled Gaussians are uninitialised in the reference: mask them

@@ -30,13 +30,19 @@ struct RefCtx {
     char* bin = nullptr;   size_t bin_bytes = 0;
     char* img = nullptr;   size_t img_bytes = 0;
     int P = 0, W = 0, H = 0, R = 0;
+    bool async = false;  // true: no cudaDeviceSynchronize after the call (timing with CUDA events)
 };
 
+// Grow-only, like torch's `resize_` on the three byte tensors (rasterize_points.cu:27-33): a call that
+// needs no more than the buffer already holds does not touch the allocator (with torch's caching
+// allocator the reference pays no cudaMalloc in steady state either).
 std::function<char*(size_t)> grow(char** p, size_t* n) {
     return [p, n](size_t N) -> char* {
-        if (*p) cudaFree(*p);
-        cudaMalloc((void**)p, N ? N : 1);
-        *n = N;
+        if (*p == nullptr || N > *n) {
+            if (*p) cudaFree(*p);
+            cudaMalloc((void**)p, N ? N : 1);
+            *n = N;
+        }
         return *p;
     };
 }
@@ -45,6 +51,8 @@ std::function<char*(size_t)> grow(char** p, size_t* n) {
 extern "C" {
 
 void* ref_ctx_create() { return new RefCtx(); }
+
+void ref_ctx_set_async(void* h, int on) { ((RefCtx*)h)->async = on != 0; }
 
 void ref_ctx_destroy(void* h) {
     RefCtx* c = (RefCtx*)h;
@@ -71,7 +79,7 @@ int ref_raster_forward(void* h, int P, int D, int M, const float* background, in
         rotations, cov3D_precomp, viewmatrix, projmatrix, campos, tan_fovx, tan_fovy,
         prefiltered != 0, out_color, out_depth, sampling_offsets, radii, false);
     c->R = R;
-    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (!c->async && cudaDeviceSynchronize() != cudaSuccess) return -1;
     return R;
 }
 
@@ -91,6 +99,7 @@ int ref_raster_backward(void* h, int P, int D, int M, int R, const float* backgr
         c->geom, c->bin, c->img, dL_dpix, dL_ddepth, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor,
         dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, dL_dcamViewDepth, false,
         sampling_offsets);
+    if (c->async) return cudaGetLastError() == cudaSuccess ? 0 : -1;
     return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
 }
 
@@ -100,7 +109,7 @@ int ref_raster_backward(void* h, int P, int D, int M, int R, const float* backgr
 int ref_raster_export_state(void* h, float* depths, float* means2D, float* cov3D,
                             float* conic_opacity, float* rgb, uint32_t* tiles_touched,
                             unsigned char* clamped, float* final_T, uint32_t* n_contrib,
-                            uint32_t* point_list) {
+                            uint32_t* point_list, uint32_t* ranges /* [tiles,2] */) {
     RefCtx* c = (RefCtx*)h;
     char* g = c->geom;
     CudaRasterizer::GeometryState gs = CudaRasterizer::GeometryState::fromChunk(g, c->P);
@@ -119,6 +128,7 @@ int ref_raster_export_state(void* h, float* depths, float* means2D, float* cov3D
     cp(clamped, gs.clamped, 3 * P);
     cp(final_T, is.accum_alpha, 4 * N);
     cp(n_contrib, is.n_contrib, 4 * N);
+    cp(ranges, is.ranges, 8 * (size_t)((c->W + 15) / 16) * (size_t)((c->H + 15) / 16));
     if (point_list && c->R > 0) {
         char* b = c->bin;
         CudaRasterizer::BinningState bs = CudaRasterizer::BinningState::fromChunk(b, c->R);

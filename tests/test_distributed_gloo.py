@@ -52,7 +52,10 @@ def _grad_job(rank, world):
     g = torch.Generator().manual_seed(100 + rank)
     for p in ps[:3]:
         p.grad = torch.randn(p.shape, generator=g)
-    # ps[3] has no grad: must be skipped on every rank
+    # ps[3]: only rank 1 has a gradient, and a NON-CONTIGUOUS one — the ranks must still issue the same collectives
+    # (the work list is derived from the parameter shapes; a missing gradient counts as zeros)
+    if rank == 1:
+        ps[3].grad = torch.arange(14.0)[::2]
     wd.allreduce_gradients(ps, bucket_bytes=20000, small_bytes=5000)  # in-place chunks + one packed buffer
     return [p.grad.clone() if p.grad is not None else None for p in ps]
 
@@ -73,7 +76,7 @@ def test_view_parallel_gradient_allreduce():
     for r in range(2):
         for i in range(3):
             assert torch.equal(out[r][i], sums[i])      # two-rank fp32 sum is order independent
-        assert out[r][3] is None
+        assert torch.equal(out[r][3], torch.arange(14.0)[::2])
 
 
 class _RangeSGD:

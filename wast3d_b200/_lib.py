@@ -74,13 +74,15 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp]),
     "wast3d_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_set_tile_cut": (_i, [_i]),
+    "wast3d_set_deterministic": (_i, [_i]),
     "wast3d_knn_scratch_bytes": (_sz, [_i]),
     "wast3d_knn_dist2": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wast3d_cluster_stats": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "wast3d_nn_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_match_scratch_bytes": (_sz, [_i, _i]),
+    "wast3d_nn_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wast3d_cdist_topk": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "wast3d_emd2_uniform": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
-    "wast3d_w2_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_w2_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wast3d_w2_match_debug": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_test_sort_pairs": (_i, [_sz, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "wast3d_test_scan": (_i, [_sz, _vp, _vp, _vp, _vp, _i, _vp]),
@@ -226,6 +228,12 @@ def set_tile_cut(mode: int) -> int:
     """1 (default) = Gaussians are instantiated only in tiles that can see alpha >= 1/255; 0 = the
     reference's radius rectangles (reproduces its num_rendered / point list).  Returns the old mode."""
     return int(load().wast3d_set_tile_cut(int(mode)))
+
+
+def set_deterministic(mode: int) -> int:
+    """1 = the tile backward adds in a fixed order (no float atomics; bit-reproducible gradients, tests);
+    0 (default) = unordered float atomics like the reference.  Returns the old mode."""
+    return int(load().wast3d_set_deterministic(int(mode)))
 
 
 def profile_slots() -> list:

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include <cuda_bf16.h>
 #include <cfloat>
+#include <atomic>
 
 namespace w3d {
 
@@ -110,9 +111,15 @@ template <int MODE>
 __global__ void __launch_bounds__(128)
 match_prep_kernel(int K, const float* __restrict__ mean, const float* __restrict__ cov6, bool style_side,
                   float* __restrict__ desc /*[K,16]*/, __nv_bfloat16* __restrict__ oper /*[Kpad,16]*/,
-                  int Kpad) {
+                  int Kpad, unsigned long long* __restrict__ packed /* content side: [K] row results to reset */,
+                  uint32_t* __restrict__ err, unsigned long long* __restrict__ stats) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && err != nullptr) {   // the content-side launch also resets the call's state words
+        err[0] = 0u;
+        if (stats != nullptr) stats[0] = stats[1] = stats[2] = stats[3] = 0ull;
+    }
     if (i >= Kpad) return;
+    if (packed != nullptr && i < K) packed[i] = ~0ull;
     __nv_bfloat16 row[16];
     if (i < K) {
         float d[16];
@@ -228,151 +235,286 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // ---------------------------------------------------------------- match -------------------------
-// grid = (row blocks, column splits); block = 128 threads (thread t <-> content row / TMEM lane t)
+// grid = (row blocks, column splits); block = 256 threads.  Thread t serves content row (t & 127) of the
+// block (TMEM lane t & 127); warps 0-3 read columns [0,64) of a tile's accumulator, warps 4-7 columns
+// [64,128) (a warp can only address the TMEM lane quarter warp_id % 4).
+//
+// Per 128 x 128 tile:
+//   MMA      one tcgen05.mma into one of two TMEM buffers, issued one tile AHEAD of its epilogue, operands and
+//            exact style descriptors staged with cp.async two tiles ahead (double buffered);
+//   phase A  every thread compares its 64 lower bounds with the row's threshold and appends the survivors
+//            (row, column) to a shared candidate list (warp-aggregated append);
+//   phase B  the 256 threads evaluate the candidates' exact costs — one candidate per thread and round, so
+//            the long exact evaluation (20 dependent square roots for W2) never runs with 1/32 of a warp
+//            active — and merge (cost, column) into the row's packed best with a shared 64-bit atomicMin
+//            (cost bits high, column low: ties go to the lowest column in any evaluation order).
+// The first tile of a CTA starts best-first: every row evaluates the column with the smallest bound, which
+// makes the thresholds tight before the first candidate list is built.  Column splits of the same rows share
+// their progress through the global packed word (read before, published after every tile).
+constexpr int MT_THREADS = 256;
+constexpr int DESC_STRIDE = 20;   // floats per descriptor row in shared memory (80 B: conflict-free float4 rows)
+
+struct MatchSmem {
+    uint8_t A[MT_M * MT_K * 2];
+    uint8_t B[2][MT_N * MT_K * 2];
+    float desc_s[2][MT_N * DESC_STRIDE];
+    float desc_c[MT_M * DESC_STRIDE];
+    unsigned long long best[MT_M];
+    uint16_t cand[MT_M * MT_N];
+    uint64_t bar[2];
+    uint32_t tmem;
+    uint32_t n_cand;
+};
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void load_desc(const float* s, float* d) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(s + 4 * k);
+        d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+    }
+}
+// the packed word's cost as a threshold in lower-bound units (W2: the cost itself; NN: the squared distance,
+// rounded up so that every column whose ROUNDED distance can tie is still evaluated)
 template <int MODE>
-__global__ void __launch_bounds__(MT_M)
+__device__ __forceinline__ float thresh_of(unsigned long long packed) {
+    if (packed == ~0ull) return __int_as_float(0x7f800000);
+    const float c = __uint_as_float((uint32_t)(packed >> 32));
+    if (MODE == MODE_W2) return c;
+    return __fmul_ru(__fmul_ru(c, c), 1.0000004f);
+}
+template <int MODE>
+__device__ __forceinline__ unsigned long long exact_packed(const float* dc, const float* ds, int j) {
+    float c;
+    if (MODE == MODE_W2) c = w2_cost(dc, ds);
+    else c = __fsqrt_rn(nn_cost_sq(dc, ds));
+    return ((unsigned long long)__float_as_uint(c) << 32) | (unsigned)j;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(MT_THREADS)
 match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __restrict__ desc_s,
              const __nv_bfloat16* __restrict__ oper_c, const __nv_bfloat16* __restrict__ oper_s,
              int tiles_per_split, unsigned long long* __restrict__ best_packed,
              unsigned long long* __restrict__ stats, float* __restrict__ lb_dump, uint32_t* __restrict__ err_flag) {
-    __shared__ __align__(1024) uint8_t s_A[MT_M * MT_K * 2];
-    __shared__ __align__(1024) uint8_t s_B[MT_N * MT_K * 2];
-    __shared__ __align__(16) float s_desc[MT_N * 16];
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_tmem;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    MatchSmem& sm = *reinterpret_cast<MatchSmem*>(smem_raw);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int row = blockIdx.x * MT_M + tid;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rl = tid & (MT_M - 1);          // row within the block == TMEM lane
+    const int half = tid >> 7;                // which 64 columns of a tile this thread reads
+    const int row = blockIdx.x * MT_M + rl;
+    const bool row_ok = row < Kc;
     const int n_tiles = (Ks + MT_N - 1) / MT_N;
     const int tile0 = blockIdx.y * tiles_per_split;
-    const int tile1 = min(n_tiles, tile0 + tiles_per_split);
+    const int T = min(n_tiles, tile0 + tiles_per_split) - tile0;
+    if (T <= 0) return;   // uniform
 
-    if (warp == 0) tmem_alloc(&s_tmem, MT_N);
+    if (warp == 0) tmem_alloc(&sm.tmem, 2 * MT_N);
     if (tid == 0) {
-        mbar_init(&s_bar, 1);
+        mbar_init(&sm.bar[0], 1);
+        mbar_init(&sm.bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sm.n_cand = 0;
     }
-    // A tile: this thread's operand row (32 bytes) into the canonical layout
-    {
+    if (tid < MT_M) {
         const uint4* src = reinterpret_cast<const uint4*>(oper_c + 16 * (size_t)row);  // oper_c is padded to the grid
-        *reinterpret_cast<uint4*>(s_A + tile_off(tid, 0)) = src[0];
-        *reinterpret_cast<uint4*>(s_A + tile_off(tid, 8)) = src[1];
-    }
-    float dc[16];
-    if (row < Kc) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float4 v = *reinterpret_cast<const float4*>(desc_c + 16 * (size_t)row + 4 * k);
-            dc[4 * k] = v.x; dc[4 * k + 1] = v.y; dc[4 * k + 2] = v.z; dc[4 * k + 3] = v.w;
+        *reinterpret_cast<uint4*>(sm.A + tile_off(tid, 0)) = src[0];
+        *reinterpret_cast<uint4*>(sm.A + tile_off(tid, 8)) = src[1];
+        sm.best[tid] = ~0ull;
+        float4* dd = reinterpret_cast<float4*>(sm.desc_c + DESC_STRIDE * tid);
+        if (row_ok) {
+            const float4* ds = reinterpret_cast<const float4*>(desc_c + 16 * (size_t)row);
+            dd[0] = ds[0]; dd[1] = ds[1]; dd[2] = ds[2]; dd[3] = ds[3];
+        } else {
+            dd[0] = dd[1] = dd[2] = dd[3] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-    } else {
-#pragma unroll
-        for (int k = 0; k < 16; ++k) dc[k] = 0.f;
     }
+    // stage tile (tile0 + i) into buffer i & 1: operand rows (32 B per column) by threads 0-127, the exact
+    // descriptors (64 B per column) two 16-byte pieces per thread
+    auto stage = [&](int i) {
+        const int b = i & 1;
+        const int col0 = (tile0 + i) * MT_N;
+        if (tid < MT_N) {
+            const __nv_bfloat16* src = oper_s + 16 * (size_t)(col0 + tid);   // padded to whole tiles
+            cp_async16(sm.B[b] + tile_off(tid, 0), src);
+            cp_async16(sm.B[b] + tile_off(tid, 8), src + 8);
+        }
+        const int c = tid >> 1, h = tid & 1;
+        if (col0 + c < Ks) {
+            const float* src = desc_s + 16 * (size_t)(col0 + c) + 8 * h;
+            float* dst = sm.desc_s[b] + DESC_STRIDE * c + 8 * h;
+            cp_async16(dst, src);
+            cp_async16(dst + 4, src + 4);
+        }
+        cp_async_commit();
+    };
+    stage(0);
+    if (T > 1) { stage(1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> async proxy (UMMA)
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_base = s_tmem;
+    const uint32_t tmem_base = sm.tmem;
     const uint32_t idesc = umma_idesc_bf16_f32(MT_M, MT_N);
+    const uint64_t adesc = umma_desc_kmajor_noswizzle(smem_u32(sm.A));
+    if (tid == 0) {
+        umma_bf16(tmem_base, adesc, umma_desc_kmajor_noswizzle(smem_u32(sm.B[0])), idesc, 0u);
+        umma_commit(&sm.bar[0]);
+    }
 
-    float best = __int_as_float(0x7f800000);     // cost that is compared/returned
-    float thresh = __int_as_float(0x7f800000);   // same in lower-bound units (== best for W2, best^2 for NN)
-    int best_j = -1;
-    unsigned long long n_exact = 0;
-    uint32_t parity = 0;
+    unsigned long long n_exact = 0, published = ~0ull;
+    uint32_t phase0 = 0u, phase1 = 0u;   // mbarrier parities of the two TMEM buffers
     bool failed = false;
+    const float* my_dc = sm.desc_c + DESC_STRIDE * rl;
 
-    for (int t = tile0; t < tile1 && !failed; ++t) {
-        const int col0 = t * MT_N;
-        // B tile + exact descriptors of this tile's style clusters
-        {
-            const int j = col0 + tid;
-            const uint4* src = reinterpret_cast<const uint4*>(oper_s + 16 * (size_t)j);  // padded to tiles
-            *reinterpret_cast<uint4*>(s_B + tile_off(tid, 0)) = src[0];
-            *reinterpret_cast<uint4*>(s_B + tile_off(tid, 8)) = src[1];
-            float4* dd = reinterpret_cast<float4*>(s_desc + 16 * tid);
-            if (j < Ks) {
-                const float4* ds = reinterpret_cast<const float4*>(desc_s + 16 * (size_t)j);
-                dd[0] = ds[0]; dd[1] = ds[1]; dd[2] = ds[2]; dd[3] = ds[3];
-            }
+    for (int i = 0; i < T; ++i) {
+        const int b = i & 1;
+        const int col0 = (tile0 + i) * MT_N;
+        // the next tile's MMA goes first: it runs while this tile's epilogue does
+        if (i + 1 < T) {
+            cp_async_wait<0>();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> async proxy (UMMA)
-        __syncthreads();
-        if (tid == 0) {
+        __syncthreads();   // also: n_cand == 0 and last tile's best[] merges are visible
+        if (i + 1 < T && tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            umma_bf16(tmem_base, umma_desc_kmajor_noswizzle(smem_u32(s_A)),
-                      umma_desc_kmajor_noswizzle(smem_u32(s_B)), idesc, 0u);
-            umma_commit(&s_bar);
+            umma_bf16(tmem_base + (uint32_t)((b ^ 1) * MT_N), adesc,
+                      umma_desc_kmajor_noswizzle(smem_u32(sm.B[b ^ 1])), idesc, 0u);
+            umma_commit(&sm.bar[b ^ 1]);
         }
-        // bounded wait for the MMA (never hang the device on a protocol bug)
+        // bounded wait for this tile's MMA (never hang the device on a protocol bug)
         {
             uint32_t spins = 0;
-            while (!mbar_try_wait(&s_bar, parity)) {
+            const uint32_t parity = b ? phase1 : phase0;
+            while (!mbar_try_wait(&sm.bar[b], parity)) {
                 if (++spins > (1u << 22)) { failed = true; break; }
             }
-            parity ^= 1u;
+            if (b) phase1 ^= 1u; else phase0 ^= 1u;
         }
         if (__syncthreads_or(failed)) { failed = true; break; }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
+        // progress of the other column splits of this row
+        if (tid < MT_M && row_ok) {
+            const unsigned long long g = ld_relaxed_u64(best_packed + row);
+            if (g < sm.best[tid]) sm.best[tid] = g;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(b * MT_N + half * 64);
+        const float* dsb = sm.desc_s[b];
+        if (i == 0) {
+            // best-first: exact cost of the column with the smallest bound in this thread's 64 columns
+            float vmin = __int_as_float(0x7f800000);
+            int kmin = -1;
 #pragma unroll 1
-        for (int c = 0; c < MT_N; c += 32) {
+            for (int c = 0; c < 64; c += 32) {
+                float v[32];
+                tmem_ld32(taddr + (uint32_t)c, v);
+#pragma unroll
+                for (int k = 0; k < 32; ++k) {
+                    const int cl = half * 64 + c + k;
+                    if (col0 + cl < Ks && v[k] < vmin) { vmin = v[k]; kmin = cl; }
+                }
+            }
+            __syncthreads();   // the reads of best_packed above are merged before anybody min()s into best[]
+            if (row_ok && kmin >= 0) {
+                float dc[16], ds[16];
+                load_desc(my_dc, dc);
+                load_desc(dsb + DESC_STRIDE * kmin, ds);
+                atomicMin(&sm.best[rl], exact_packed<MODE>(dc, ds, col0 + kmin));
+                ++n_exact;
+            }
+        }
+        __syncthreads();
+        const float thresh = thresh_of<MODE>(sm.best[rl]);
+
+        // ---- phase A: candidates whose (margin-adjusted) lower bound can still beat the row's best
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
             float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-            if (lb_dump != nullptr && row < Kc) {
+            tmem_ld32(taddr + (uint32_t)c, v);
+            const int cbase = half * 64 + c;
+            if (lb_dump != nullptr && row_ok) {
 #pragma unroll
                 for (int k = 0; k < 32; ++k)
-                    if (col0 + c + k < Ks) lb_dump[(size_t)row * Ks + col0 + c + k] = v[k];
+                    if (col0 + cbase + k < Ks) lb_dump[(size_t)row * Ks + col0 + cbase + k] = v[k];
             }
-            // columns whose (margin-adjusted) lower bound can still beat this row's best
             unsigned mask = 0;
 #pragma unroll
             for (int k = 0; k < 32; ++k)
-                if (row < Kc && col0 + c + k < Ks && !(v[k] > thresh)) mask |= 1u << k;
-            unsigned any = __reduce_or_sync(0xffffffffu, mask);
-            while (any) {  // ascending column order => ties keep the lowest index
-                const int k = __ffs(any) - 1;
-                any &= any - 1;
-                if ((mask >> k) & 1u) {
-                    ++n_exact;
-                    const int j = col0 + c + k;
-                    const float* dsj = s_desc + 16 * (c + k);
-                    if (MODE == MODE_W2) {
-                        const float w = w2_cost(dc, dsj);
-                        if (w < best) { best = w; thresh = w; best_j = j; }
-                    } else {
-                        const float sq = nn_cost_sq(dc, dsj);
-                        const float d = __fsqrt_rn(sq);
-                        if (d < best) { best = d; thresh = sq; best_j = j; }
-                    }
-                }
+                if (row_ok && col0 + cbase + k < Ks && !(v[k] > thresh)) mask |= 1u << k;
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int base = 0;
+            if (lane == 31 && total) base = (int)atomicAdd(&sm.n_cand, (uint32_t)total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int pos = base + incl - cnt;
+            while (mask) {
+                const int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                sm.cand[pos++] = (uint16_t)((rl << 7) | (cbase + k));
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();  // all TMEM reads and s_B / s_desc reads done before the next tile overwrites them
+        __syncthreads();
+
+        // ---- phase B: exact costs, one candidate per thread and round
+        const int n = (int)sm.n_cand;
+        for (int k = tid; k < n; k += MT_THREADS) {
+            const int cd = sm.cand[k];
+            const int r = cd >> 7, cl = cd & 127;
+            float dc[16], ds[16];
+            load_desc(sm.desc_c + DESC_STRIDE * r, dc);
+            load_desc(dsb + DESC_STRIDE * cl, ds);
+            atomicMin(&sm.best[r], exact_packed<MODE>(dc, ds, col0 + cl));
+        }
+        if (tid == 0) n_exact += (unsigned long long)n;
+        __syncthreads();
+        if (tid == 0) sm.n_cand = 0;
+        if (tid < MT_M && row_ok) {
+            const unsigned long long mine = sm.best[tid];
+            if (mine < published) { atomicMin(best_packed + row, mine); published = mine; }
+        }
+        if (i + 2 < T) stage(i + 2);   // into the buffers this tile just released
     }
+    cp_async_wait<0>();
 
     if (failed && tid == 0) atomicOr(err_flag, 1u);
-    if (!failed && row < Kc && best_j >= 0) {
-        const unsigned long long packed = ((unsigned long long)__float_as_uint(best) << 32) | (unsigned)best_j;
-        atomicMin(best_packed + row, packed);
-    }
     if (stats != nullptr) {
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) n_exact += __shfl_xor_sync(0xffffffffu, n_exact, d);
-        if ((tid & 31) == 0) atomicAdd(stats + 1, n_exact);
-        if (tid == 0) atomicAdd(stats + 2, (unsigned long long)max(tile1 - tile0, 0));
+        if (lane == 0 && n_exact) atomicAdd(stats + 1, n_exact);
+        if (tid == 0) atomicAdd(stats + 2, (unsigned long long)T);
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, MT_N);
+    if (warp == 0) tmem_dealloc(tmem_base, 2 * MT_N);
 }
 
+// out_idx = -2 / cost = NaN for every row when the MMA barrier timed out (never expected): the caller sees
+// the failure without a host round trip in the call itself.
 __global__ void match_finalize_kernel(int Kc, const unsigned long long* __restrict__ packed,
-                                      int32_t* __restrict__ out_idx, float* __restrict__ out_cost) {
+                                      int32_t* __restrict__ out_idx, float* __restrict__ out_cost,
+                                      const uint32_t* __restrict__ err, unsigned long long* __restrict__ stats,
+                                      unsigned long long pairs) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && stats != nullptr) { stats[0] = pairs; stats[3] = *err; }
     if (i >= Kc) return;
     const unsigned long long p = packed[i];
-    if (p == ~0ull) {
+    if (*err) {
+        out_idx[i] = -2;
+        if (out_cost) out_cost[i] = __int_as_float(0x7fc00000);
+    } else if (p == ~0ull) {
         out_idx[i] = -1;
         if (out_cost) out_cost[i] = __int_as_float(0x7f800000);
     } else {
@@ -439,14 +581,16 @@ kmeans_accumulate_kernel(int n, const float* __restrict__ pts, const int32_t* __
     double d2 = 0.0;
     if (i < n) {
         const int k = new_label[i];
-        ch = label[i] != k;
-        label[i] = k;
-        const float d = dist[i];
-        d2 = (double)d * (double)d;
-        atomicAdd(cnt + k, 1);
-        atomicAdd(acc + 3 * k + 0, (double)pts[3 * i + 0]);
-        atomicAdd(acc + 3 * k + 1, (double)pts[3 * i + 1]);
-        atomicAdd(acc + 3 * k + 2, (double)pts[3 * i + 2]);
+        if (k >= 0) {   // k < 0: the match failed (error word set; the host stops the loop)
+            ch = label[i] != k;
+            label[i] = k;
+            const float d = dist[i];
+            d2 = (double)d * (double)d;
+            atomicAdd(cnt + k, 1);
+            atomicAdd(acc + 3 * k + 0, (double)pts[3 * i + 0]);
+            atomicAdd(acc + 3 * k + 1, (double)pts[3 * i + 1]);
+            atomicAdd(acc + 3 * k + 2, (double)pts[3 * i + 2]);
+        }
     }
     // block-level pre-reduction of the two scalars
     __shared__ double s_d[8];
@@ -483,67 +627,107 @@ __global__ void kmeans_update_kernel(int K, const double* __restrict__ acc, cons
 }
 
 // ---------------------------------------------------------------- host --------------------------
+struct MatchScratch {
+    float* desc_c;
+    float* desc_s;
+    __nv_bfloat16* oper_c;
+    __nv_bfloat16* oper_s;
+    unsigned long long* packed;
+    uint32_t* err;
+    static MatchScratch carve(void* chunk, int Kc, int Ks, size_t* bytes) {
+        const int Kc_pad = (Kc + MT_M - 1) / MT_M * MT_M;
+        const int Ks_pad = (Ks + MT_N - 1) / MT_N * MT_N;
+        Carver c(chunk);
+        MatchScratch m;
+        m.desc_c = c.take<float>((size_t)(Kc > 0 ? Kc : 1) * 16);
+        m.desc_s = c.take<float>((size_t)(Ks > 0 ? Ks : 1) * 16);
+        m.oper_c = c.take<__nv_bfloat16>((size_t)(Kc_pad > 0 ? Kc_pad : MT_M) * 16);
+        m.oper_s = c.take<__nv_bfloat16>((size_t)(Ks_pad > 0 ? Ks_pad : MT_N) * 16);
+        m.packed = c.take<unsigned long long>(Kc > 0 ? Kc : 1);
+        m.err = c.take<uint32_t>(4);
+        if (bytes) *bytes = c.bytes();
+        return m;
+    }
+};
+
+// Internal stream-ordered allocations (callers that pass no scratch, K-Means, cluster statistics): keep freed
+// blocks in the device's default pool instead of returning them to the driver at every synchronisation
+// (release threshold 0 made a call cost a cudaMalloc — milliseconds — whenever the stream had been synced).
+static void keep_pool_memory() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    static std::atomic<unsigned long long> done_mask{0};
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done_mask.load() & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    done_mask.fetch_or(bit);
+}
+
+// No host synchronisation: the (never expected) MMA time-out is reported through out_idx = -2 / stats[3].
+// err_host_check != nullptr (K-Means, which synchronises anyway) additionally receives the device address of
+// the error word.
 template <int MODE>
 static int run_match(int Kc, int Ks, const float* mean_c, const float* cov_c, const float* mean_s,
                      const float* cov_s, int32_t* out_idx, float* out_cost, unsigned long long* stats,
-                     float* lb_dump, cudaStream_t s) {
+                     float* lb_dump, void* scratch, size_t scratch_bytes, cudaStream_t s,
+                     uint32_t** err_dev = nullptr) {
     if (Kc < 0 || Ks < 0) return WAST3D_ERR_INVALID_ARGUMENT;
     if (Kc == 0) return WAST3D_OK;
     if (!mean_c || !out_idx || (Ks > 0 && !mean_s)) return WAST3D_ERR_INVALID_ARGUMENT;
     if (MODE == MODE_W2 && (!cov_c || (Ks > 0 && !cov_s))) return WAST3D_ERR_INVALID_ARGUMENT;
     const int Kc_pad = (Kc + MT_M - 1) / MT_M * MT_M;
     const int Ks_pad = (Ks + MT_N - 1) / MT_N * MT_N;
-    // scratch (stream-ordered allocation keeps this call asynchronous)
-    Carver sizer(nullptr);
-    sizer.take<float>((size_t)Kc * 16); sizer.take<float>((size_t)(Ks > 0 ? Ks : 1) * 16);
-    sizer.take<__nv_bfloat16>((size_t)Kc_pad * 16); sizer.take<__nv_bfloat16>((size_t)(Ks_pad > 0 ? Ks_pad : MT_N) * 16);
-    sizer.take<unsigned long long>(Kc); sizer.take<uint32_t>(4);
-    void* chunk = nullptr;
-    W3D_CUDA_TRY(cudaMallocAsync(&chunk, sizer.bytes(), s));
-    Carver c(chunk);
-    float* desc_c = c.take<float>((size_t)Kc * 16);
-    float* desc_s = c.take<float>((size_t)(Ks > 0 ? Ks : 1) * 16);
-    __nv_bfloat16* oper_c = c.take<__nv_bfloat16>((size_t)Kc_pad * 16);
-    __nv_bfloat16* oper_s = c.take<__nv_bfloat16>((size_t)(Ks_pad > 0 ? Ks_pad : MT_N) * 16);
-    unsigned long long* packed = c.take<unsigned long long>(Kc);
-    uint32_t* err = c.take<uint32_t>(4);
+    size_t need = 0;
+    MatchScratch::carve(nullptr, Kc, Ks, &need);
+    void* chunk = scratch;
+    if (chunk != nullptr) {
+        if (scratch_bytes < need || ((size_t)chunk & 127) != 0) return WAST3D_ERR_INVALID_ARGUMENT;
+    } else {
+        keep_pool_memory();
+        W3D_CUDA_TRY(cudaMallocAsync(&chunk, need, s));
+    }
+    const MatchScratch m = MatchScratch::carve(chunk, Kc, Ks, nullptr);
+    if (err_dev) *err_dev = m.err;
     int rc = WAST3D_OK;
     ProfScope ps(PS_MATCH, s);
     do {
-        if (cudaMemsetAsync(packed, 0xFF, sizeof(unsigned long long) * (size_t)Kc, s) != cudaSuccess ||
-            cudaMemsetAsync(err, 0, 16, s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
-        if (stats && cudaMemsetAsync(stats, 0, 4 * sizeof(unsigned long long), s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
-        match_prep_kernel<MODE><<<(Kc_pad + 127) / 128, 128, 0, s>>>(Kc, mean_c, cov_c, false, desc_c, oper_c, Kc_pad);
-        if (Ks > 0)
-            match_prep_kernel<MODE><<<(Ks_pad + 127) / 128, 128, 0, s>>>(Ks, mean_s, cov_s, true, desc_s, oper_s, Ks_pad);
+        match_prep_kernel<MODE><<<(Kc_pad + 127) / 128, 128, 0, s>>>(Kc, mean_c, cov_c, false, m.desc_c, m.oper_c,
+                                                                     Kc_pad, m.packed, m.err, stats);
+        count_launch();
+        if (Ks > 0) {
+            match_prep_kernel<MODE><<<(Ks_pad + 127) / 128, 128, 0, s>>>(Ks, mean_s, cov_s, true, m.desc_s, m.oper_s,
+                                                                         Ks_pad, nullptr, nullptr, nullptr);
+            count_launch();
+        }
         if (cudaGetLastError() != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
         if (Ks > 0) {
             const int row_blocks = Kc_pad / MT_M;
             const int n_tiles = Ks_pad / MT_N;
-            int splits = (2 * 148 + row_blocks - 1) / row_blocks;   // aim for ~2 CTAs per SM
+            int splits = (2 * 148 + row_blocks - 1) / row_blocks;   // two CTAs (of 8 warps) per SM
             if (splits > n_tiles) splits = n_tiles;
             if (splits < 1) splits = 1;
             const int tiles_per_split = (n_tiles + splits - 1) / splits;
             splits = (n_tiles + tiles_per_split - 1) / tiles_per_split;
-            match_kernel<MODE><<<dim3(row_blocks, splits), MT_M, 0, s>>>(Kc, Ks, desc_c, desc_s, oper_c, oper_s,
-                                                                        tiles_per_split, packed, stats, lb_dump, err);
+            // per device, cheap: no process-wide "already set" flag (several devices per process)
+            if (cudaFuncSetAttribute(match_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(MatchSmem)) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+            match_kernel<MODE><<<dim3(row_blocks, splits), MT_THREADS, sizeof(MatchSmem), s>>>(
+                Kc, Ks, m.desc_c, m.desc_s, m.oper_c, m.oper_s, tiles_per_split, m.packed, stats, lb_dump, m.err);
+            count_launch();
             if (cudaGetLastError() != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
-            if (stats) {
-                const unsigned long long pairs = (unsigned long long)Kc * (unsigned long long)Ks;
-                if (cudaMemcpyAsync(stats, &pairs, sizeof(pairs), cudaMemcpyHostToDevice, s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
-            }
         }
-        match_finalize_kernel<<<(Kc + 255) / 256, 256, 0, s>>>(Kc, packed, out_idx, out_cost);
+        match_finalize_kernel<<<(Kc + 255) / 256, 256, 0, s>>>(Kc, m.packed, out_idx, out_cost, m.err, stats,
+                                                               (unsigned long long)Kc * (unsigned long long)Ks);
+        count_launch();
         if (cudaGetLastError() != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
-        for (int l = 0; l < (Ks > 0 ? 4 : 2); ++l) count_launch();
-        // the MMA-timeout flag is the only thing that needs the host; it is tiny and rare
-        uint32_t h_err = 0;
-        if (cudaMemcpyAsync(&h_err, err, sizeof(h_err), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-            cudaStreamSynchronize(s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
-        if (h_err) rc = WAST3D_ERR_CUDA;
     } while (0);
     if (rc == WAST3D_ERR_CUDA) set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
-    cudaFreeAsync(chunk, s);
+    if (scratch == nullptr) cudaFreeAsync(chunk, s);
     return rc;
 }
 
@@ -551,26 +735,34 @@ static int run_match(int Kc, int Ks, const float* mean_c, const float* cov_c, co
 
 using namespace w3d;
 
+extern "C" size_t wast3d_match_scratch_bytes(int Kc, int Ks) {
+    if (Kc < 0 || Ks < 0) return 0;
+    size_t need = 0;
+    MatchScratch::carve(nullptr, Kc, Ks, &need);
+    return need;
+}
+
 extern "C" int wast3d_w2_match(int Kc, int Ks, const float* mean_c, const float* cov_c,
                                const float* mean_s, const float* cov_s, int32_t* out_idx,
-                               float* out_cost, unsigned long long* stats, void* stream_v) {
+                               float* out_cost, unsigned long long* stats, void* scratch,
+                               size_t scratch_bytes, void* stream_v) {
     return run_match<MODE_W2>(Kc, Ks, mean_c, cov_c, mean_s, cov_s, out_idx, out_cost, stats, nullptr,
-                              (cudaStream_t)stream_v);
+                              scratch, scratch_bytes, (cudaStream_t)stream_v);
 }
 
 extern "C" int wast3d_nn_match(int Na, int Nb, const float* a, const float* b, int32_t* out_idx,
-                               float* out_dist, void* stream_v) {
+                               float* out_dist, void* scratch, size_t scratch_bytes, void* stream_v) {
     return run_match<MODE_NN>(Na, Nb, a, nullptr, b, nullptr, out_idx, out_dist, nullptr, nullptr,
-                              (cudaStream_t)stream_v);
+                              scratch, scratch_bytes, (cudaStream_t)stream_v);
 }
 
-// Test hook: also dumps the tensor-core lower-bound matrix [Kc,Ks] (see tests/test_match_gpu.py).
+// Test hook: also dumps the tensor-core lower-bound matrix [Kc,Ks] (see tests/test_knn_match_gpu.py).
 extern "C" int wast3d_w2_match_debug(int Kc, int Ks, const float* mean_c, const float* cov_c,
                                      const float* mean_s, const float* cov_s, int32_t* out_idx,
                                      float* out_cost, unsigned long long* stats, float* lb_dump,
                                      void* stream_v) {
     return run_match<MODE_W2>(Kc, Ks, mean_c, cov_c, mean_s, cov_s, out_idx, out_cost, stats, lb_dump,
-                              (cudaStream_t)stream_v);
+                              nullptr, 0, (cudaStream_t)stream_v);
 }
 
 extern "C" int wast3d_cluster_stats(int n, int K, const float* points, const int32_t* labels,
@@ -580,6 +772,7 @@ extern "C" int wast3d_cluster_stats(int n, int K, const float* points, const int
     if (!mean || !cov6 || !count || (n > 0 && (!points || !labels))) return WAST3D_ERR_INVALID_ARGUMENT;
     cudaStream_t s = (cudaStream_t)stream_v;
     double* buf = nullptr;
+    keep_pool_memory();
     W3D_CUDA_TRY(cudaMallocAsync((void**)&buf, sizeof(double) * 9 * (size_t)K, s));
     double* sum = buf;
     double* acc = buf + 3 * (size_t)K;
@@ -609,7 +802,10 @@ extern "C" int wast3d_kmeans_lloyd(int n, int K, const float* points, float* cen
     Carver sizer(nullptr);
     sizer.take<double>((size_t)3 * K + 2); sizer.take<unsigned long long>(1); sizer.take<int32_t>(K);
     sizer.take<int32_t>(n); sizer.take<float>(n);
+    const size_t match_bytes = wast3d_match_scratch_bytes(n, K);
+    sizer.take<char>(match_bytes);
     void* chunk = nullptr;
+    keep_pool_memory();
     W3D_CUDA_TRY(cudaMallocAsync(&chunk, sizer.bytes(), s));
     Carver c(chunk);
     double* acc = c.take<double>((size_t)3 * K + 2);
@@ -619,6 +815,7 @@ extern "C" int wast3d_kmeans_lloyd(int n, int K, const float* points, float* cen
     int32_t* cnt = c.take<int32_t>(K);
     int32_t* new_label = c.take<int32_t>(n);
     float* dist = c.take<float>(n);
+    void* match_scratch = c.take<char>(match_bytes);
     int rc = WAST3D_OK;
     int it = 0;
     double h_inertia = 0.0, h_shift = 0.0;
@@ -627,7 +824,9 @@ extern "C" int wast3d_kmeans_lloyd(int n, int K, const float* points, float* cen
         // E-step, M-step, ... ; the loop always ends on an E-step against the FINAL centres so that labels and
         // centres are consistent (sklearn re-runs the E-step after a tolerance-based stop as well)
         for (;;) {
-            rc = run_match<MODE_NN>(n, K, points, nullptr, centers, nullptr, new_label, dist, nullptr, nullptr, s);
+            uint32_t* err_dev = nullptr;
+            rc = run_match<MODE_NN>(n, K, points, nullptr, centers, nullptr, new_label, dist, nullptr, nullptr,
+                                    match_scratch, match_bytes, s, &err_dev);
             if (rc != WAST3D_OK) break;
             if (cudaMemsetAsync(acc, 0, sizeof(double) * ((size_t)3 * K + 2), s) != cudaSuccess ||
                 cudaMemsetAsync(changed, 0, sizeof(unsigned long long), s) != cudaSuccess ||
@@ -636,9 +835,11 @@ extern "C" int wast3d_kmeans_lloyd(int n, int K, const float* points, float* cen
                                                                       changed, inertia);
             count_launch();
             unsigned long long h_changed = 0;
-            if (cudaMemcpyAsync(&h_changed, changed, sizeof(h_changed), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            uint32_t h_err = 0;
+            if (cudaMemcpyAsync(&h_err, err_dev, sizeof(h_err), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaMemcpyAsync(&h_changed, changed, sizeof(h_changed), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
                 cudaMemcpyAsync(&h_inertia, inertia, sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-                cudaStreamSynchronize(s) != cudaSuccess) { rc = WAST3D_ERR_CUDA; break; }
+                cudaStreamSynchronize(s) != cudaSuccess || h_err) { rc = WAST3D_ERR_CUDA; break; }
             // stop: iteration budget used, labels stable (strict convergence), or the last update moved the
             // centres by no more than tol (then this E-step was the consistency pass)
             if (it >= max_iter || h_changed == 0 || (it > 0 && h_shift <= tol)) break;

@@ -23,6 +23,7 @@
 //  Summation order across pixels differs from the reference's atomics (both are unordered);
 //  gradients agree to fp32 rounding, not bitwise (tests state the tolerance per tensor).
 #include "raster_math.cuh"
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 
@@ -30,6 +31,19 @@ namespace w3d {
 
 const uint32_t* point_list_ptr(const BinningState& b, uint32_t num_tiles);
 int validate_params(const wast3d_raster_params* p, bool forward);
+
+// Deterministic backward (tests): 0 = float atomics in K7 (default), 1 = fixed summation order.
+// WAST3D_DETERMINISTIC=1 sets the initial value, wast3d_set_deterministic() changes it at run time.
+static std::atomic<int> g_deterministic{-1};
+static int deterministic_mode() {
+    int m = g_deterministic.load();
+    if (m < 0) {
+        const char* e = getenv("WAST3D_DETERMINISTIC");
+        m = (e && atoi(e) != 0) ? 1 : 0;
+        g_deterministic.store(m);
+    }
+    return m;
+}
 
 constexpr int BWD_BATCH = 256;
 constexpr int ACC_STRIDE = 12;
@@ -296,18 +310,26 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 
 // Variant: the reduce lanes add straight into the global gradient record (one 4-byte RED per
 // slot and (warp, Gaussian) hit) — no shared accumulator, no flush, one barrier per batch.
+//
+// DET = true (wast3d_set_deterministic, tests): no float atomics at all.  The eight warps of the tile park
+// their reduced partials in shared memory, one thread per instance adds them in warp order and writes the
+// 48-byte sum to inst_grad[position in the point list]; raster_backward_impl then adds every Gaussian's
+// instances in point-list order (det_gather_kernel).  Same arithmetic per pixel, a fixed summation order:
+// the gradients are bit-reproducible from run to run (and agree with the atomic path to fp32 rounding).
+template <int BWD_BATCH, bool DET>
 __global__ void __launch_bounds__(TILE_PIX)
 render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const int W, const int H, const float* __restrict__ bg_color,
                        const float4* __restrict__ rec, const float* __restrict__ sampling_offsets,
                        const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpixels, const float* __restrict__ dL_ddepths,
-                       float4* __restrict__ grad_rec) {
+                       float4* __restrict__ grad_rec, float4* __restrict__ inst_grad) {
     __shared__ float4 s_r0[2][BWD_BATCH];
     __shared__ float4 s_r1[2][BWD_BATCH];
     __shared__ float4 s_r2[2][BWD_BATCH];
     __shared__ uint32_t s_id[2][BWD_BATCH];
     __shared__ uint32_t s_warp_max[TILE_PIX / 32];
+    __shared__ __align__(16) float s_part[DET ? TILE_PIX / 32 : 1][DET ? BWD_BATCH : 1][12];
 
     float* grad_f = reinterpret_cast<float*>(grad_rec);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -366,7 +388,7 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
 
     auto prefetch = [&](int b) {
         const int p = b * BWD_BATCH + tid;
-        if (p < n) {
+        if (tid < BWD_BATCH && p < n) {
             const uint32_t id = point_list[range.x + (uint32_t)(n - 1 - p)];
             s_id[b & 1][tid] = id;
             const float4* src = rec + 3 * (size_t)id;
@@ -384,6 +406,10 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
 
     if (rounds > 0) prefetch(0);
     for (int b = 0; b < rounds; ++b) {
+        if (DET) {   // this warp's partials of the batch start at zero (a warp that skips a Gaussian adds 0)
+            float* z = &s_part[warp][0][0];
+            for (int q = lane; q < BWD_BATCH * 12; q += 32) z[q] = 0.f;
+        }
         // one barrier per batch: batch b has landed, and every warp is done with batch b-1 whose
         // buffer the prefetch of b+1 overwrites
         cp_async_wait<0>();
@@ -479,15 +505,61 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
                         const float tot = warp_reduce12(v, lane);
                         const int sub = ((lane >> 1) & 3);  // 2*b2 + b1
                         const int slot = 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1) + sub;
-                        if (!(lane & 1) && sub < 3 && slot != 7 && slot != 11)
-                            atomicAdd(grad_f + 12 * (size_t)s_id[b & 1][j] + slot, tot);
+                        if (!(lane & 1) && sub < 3 && slot != 7 && slot != 11) {
+                            if (DET) s_part[warp][j][slot] = tot;
+                            else atomicAdd(grad_f + 12 * (size_t)s_id[b & 1][j] + slot, tot);
+                        }
                     }
                 }
             }
         }
+        if (DET) {
+            __syncthreads();
+            if (tid < cnt) {
+                float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+#pragma unroll
+                for (int w = 0; w < TILE_PIX / 32; ++w) {   // fixed order
+                    const float4* q = reinterpret_cast<const float4*>(&s_part[w][tid][0]);
+                    const float4 x = q[0], y = q[1], z = q[2];
+                    a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
+                    a1.x += y.x; a1.y += y.y; a1.z += y.z; a1.w += y.w;
+                    a2.x += z.x; a2.y += z.y; a2.z += z.z; a2.w += z.w;
+                }
+                const size_t pos = (size_t)range.x + (size_t)(n - 1 - (b * BWD_BATCH + tid));
+                inst_grad[3 * pos + 0] = a0;
+                inst_grad[3 * pos + 1] = a1;
+                inst_grad[3 * pos + 2] = a2;
+            }
+            __syncthreads();   // before the next batch zeroes s_part
+        }
     }
     cp_async_wait<0>();
 }
+
+// Deterministic mode, second half: Gaussian `id` owns tiles_touched[id] instances whose point-list positions
+// sit, ascending, at inst_sorted[seg[id] ...]; their 48-byte partial gradient records are added in that order.
+__global__ void __launch_bounds__(256)
+det_gather_kernel(int P, const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ seg,
+                  const uint32_t* __restrict__ inst_sorted, const float4* __restrict__ inst_grad,
+                  float4* __restrict__ grad_rec) {
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= P) return;
+    const uint32_t n = tiles_touched[id];
+    if (n == 0) return;   // grad_rec was zero-filled
+    const uint32_t first = seg[id];
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+    for (uint32_t k = 0; k < n; ++k) {
+        const size_t i = inst_sorted[first + k];
+        const float4 x = inst_grad[3 * i], y = inst_grad[3 * i + 1], z = inst_grad[3 * i + 2];
+        a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
+        a1.x += y.x; a1.y += y.y; a1.z += y.z; a1.w += y.w;
+        a2.x += z.x; a2.y += z.y; a2.z += z.z; a2.w += z.w;
+    }
+    grad_rec[3 * (size_t)id + 0] = a0;
+    grad_rec[3 * (size_t)id + 1] = a1;
+    grad_rec[3 * (size_t)id + 2] = a2;
+}
+
 
 
 // ------------------------------------------------------------------ K8 + K9 ---------------
@@ -985,13 +1057,69 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
         ProfScope ps(PS_BWD_ZERO, s);
         W3D_CUDA_TRY(cudaMemsetAsync(g.grad_rec, 0, 3 * (size_t)P * sizeof(float4), s));
     }
-    if (num_rendered > 0) {
+    if (num_rendered > 0 && deterministic_mode() != 0) {
+        // test mode: fixed summation order, no float atomics (see render_backward_direct_kernel<.., true>)
+        ProfScope ps(PS_RENDER_BWD, s);
+        const size_t R = (size_t)num_rendered;
+        const uint32_t* plist = point_list_ptr(bn, num_tiles);
+        const size_t hist_words = rs_hist_words(R), hist_scr = scan_scratch_words(hist_words);
+        Carver sizer(nullptr);
+        sizer.take<float4>(3 * R); sizer.take<uint32_t>(R); sizer.take<uint32_t>(R); sizer.take<uint32_t>(R);
+        sizer.take<uint32_t>(R); sizer.take<uint32_t>(hist_words + hist_scr + 64); sizer.take<uint32_t>(P);
+        sizer.take<uint32_t>(scan_scratch_words(P) + 64);
+        void* chunk = nullptr;
+        W3D_CUDA_TRY(cudaMallocAsync(&chunk, sizer.bytes(), s));
+        Carver c(chunk);
+        float4* inst_grad = c.take<float4>(3 * R);
+        uint32_t* ka = c.take<uint32_t>(R);
+        uint32_t* va = c.take<uint32_t>(R);
+        uint32_t* kb = c.take<uint32_t>(R);
+        uint32_t* vb = c.take<uint32_t>(R);
+        uint32_t* hist = c.take<uint32_t>(hist_words + hist_scr + 64);
+        uint32_t* seg = c.take<uint32_t>(P);
+        uint32_t* scan_scr = c.take<uint32_t>(scan_scratch_words(P) + 64);
+        int st = WAST3D_OK;
+        do {
+            if (cudaMemsetAsync(inst_grad, 0, 3 * R * sizeof(float4), s) != cudaSuccess) { st = WAST3D_ERR_CUDA; break; }
+            render_backward_direct_kernel<64, true><<<grid, TILE_PIX, 0, s>>>(
+                im.ranges, plist, W, H, prm->background, g.rec, prm->sampling_offsets, im.final_T, im.n_contrib,
+                dL_dpix, dL_ddepth, g.grad_rec, inst_grad);
+            count_launch();
+            if (cudaGetLastError() != cudaSuccess) { st = WAST3D_ERR_CUDA; break; }
+            // instance positions grouped by Gaussian id, ascending inside a group (stable LSD sort on the id)
+            const int bits = bits_for((uint32_t)P);
+            const int passes = (bits + 7) / 8;
+            const uint32_t *kin = plist, *vin = nullptr;
+            uint32_t *kout = ka, *vout = va;
+            for (int p = 0; p < passes && st == WAST3D_OK; ++p) {
+                const int nb = (p == passes - 1) ? bits - 8 * p : 8;
+                st = radix_pass_u32(kin, vin, kout, vout, R, 8 * p, nb, hist, hist + hist_words, s, debug);
+                kin = kout; vin = vout;
+                kout = (kout == ka) ? kb : ka;
+                vout = (vout == va) ? vb : va;
+            }
+            if (st != WAST3D_OK) break;
+            st = scan_exclusive_u32(g.tiles_touched, nullptr, seg, P, scan_scr, nullptr, s, debug);
+            if (st != WAST3D_OK) break;
+            det_gather_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.tiles_touched, seg, vin, inst_grad, g.grad_rec);
+            count_launch();
+            if (cudaGetLastError() != cudaSuccess) st = WAST3D_ERR_CUDA;
+        } while (0);
+        cudaFreeAsync(chunk, s);
+        if (st == WAST3D_ERR_CUDA) set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
+        if (st != WAST3D_OK) return st;
+        if (debug) W3D_CUDA_TRY(cudaStreamSynchronize(s));
+    } else if (num_rendered > 0) {
         ProfScope ps(PS_RENDER_BWD, s);
         static const int variant = getenv("WAST3D_K7_VARIANT") ? atoi(getenv("WAST3D_K7_VARIANT")) : 1;
-        auto k7 = variant == 1 ? render_backward_direct_kernel : render_backward_kernel;
-        k7<<<grid, TILE_PIX, 0, s>>>(
-            im.ranges, point_list_ptr(bn, num_tiles), W, H, prm->background, g.rec,
-            prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec);
+        if (variant == 1)
+            render_backward_direct_kernel<BWD_BATCH, false><<<grid, TILE_PIX, 0, s>>>(
+                im.ranges, point_list_ptr(bn, num_tiles), W, H, prm->background, g.rec,
+                prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec, nullptr);
+        else
+            render_backward_kernel<<<grid, TILE_PIX, 0, s>>>(
+                im.ranges, point_list_ptr(bn, num_tiles), W, H, prm->background, g.rec,
+                prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec);
         W3D_AFTER_LAUNCH(s, debug);
     }
     ProfScope ps_gb(PS_GAUSS_BWD, s);
@@ -1010,6 +1138,12 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
         dL_dcamViewDepth, af);
     W3D_AFTER_LAUNCH(s, debug);
     return WAST3D_OK;
+}
+
+extern "C" int wast3d_set_deterministic(int mode) {
+    const int prev = deterministic_mode();
+    if (mode == 0 || mode == 1) g_deterministic.store(mode);
+    return prev;
 }
 
 extern "C" int wast3d_raster_backward(const wast3d_raster_params* prm, int num_rendered,

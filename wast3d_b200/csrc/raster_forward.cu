@@ -782,12 +782,8 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         ProfScope ps(PS_EMIT, s);
         const bool smem_hist = num_tiles <= (uint32_t)EMIT_MAX_SMEM_TILES;
         const size_t smem = smem_hist ? num_tiles * sizeof(uint32_t) : 0;
-        static bool attr_set = false;
-        if (!attr_set) {
-            W3D_CUDA_TRY(cudaFuncSetAttribute(emit_instances_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              EMIT_MAX_SMEM_TILES * (int)sizeof(uint32_t)));
-            attr_set = true;
-        }
+        static_assert(EMIT_MAX_SMEM_TILES * sizeof(uint32_t) <= 48 * 1024,
+                      "emit_instances_kernel's counters must fit the default dynamic shared-memory limit");
         const int n_chunks = (P + 31) / 32;
         int blocks = 148 * 4;
         if (blocks > (n_chunks + 7) / 8) blocks = (n_chunks + 7) / 8;

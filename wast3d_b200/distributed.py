@@ -40,13 +40,14 @@ def _grad_chunks(params, chunk_bytes: int, small_bytes: int):
     large gradients are reduced IN PLACE as contiguous slices of at most chunk_bytes (no pack /
     unpack copies); gradients smaller than small_bytes are packed together into one buffer so
     that tiny tensors do not each pay a collective launch."""
+    # The work list must be IDENTICAL on every rank (the sequence and sizes of the collectives): it is derived from
+    # the parameters' shapes only.  A missing gradient becomes zeros and a non-contiguous one a contiguous copy
+    # (allreduce_gradients materialises both before calling this).
     work, small, small_n = [], [], 0
     for p in params:
         g = p.grad
-        if g is None:
-            continue
         nbytes = g.numel() * g.element_size()
-        if nbytes < small_bytes or not g.is_contiguous():
+        if nbytes < small_bytes:
             small.append(p)
             small_n += nbytes
             continue
@@ -70,9 +71,14 @@ def allreduce_gradients(params: Iterable[torch.Tensor], group=None, average: boo
     is taken inside the collective (ReduceOp.AVG).  Returns the list of pending chunks when
     async_op=True (pass it to `finish_allreduce`, or use `allreduce_and_step`)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    params = [p for p in params if p.grad is not None]
+    params = [p for p in params if p.numel()]
     if world == 1 or not params:
         return []
+    for p in params:  # same collectives on every rank, whatever the local autograd graph produced
+        if p.grad is None:
+            p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+        elif not p.grad.is_contiguous():
+            p.grad = p.grad.contiguous()
     use_avg = average and _avg_supported(group)
     op = dist.ReduceOp.AVG if use_avg else dist.ReduceOp.SUM
     pending = []
@@ -94,7 +100,7 @@ def _finish_one(entry):
         off = 0
         for p, s0, e0 in owners:
             n = e0 - s0
-            p.grad.view(-1)[s0:e0].copy_(flat[off:off + n])
+            p.grad.reshape(-1)[s0:e0].copy_(flat[off:off + n])  # contiguous by construction: a view
             off += n
 
 

@@ -17,6 +17,22 @@ import torch
 from . import _lib
 
 
+# (device index) -> reusable scratch tensor of the match kernels.  Calls on one device are stream-ordered on
+# torch's current stream; a caller that matches concurrently on several streams passes its own `scratch`.
+_SCRATCH: dict = {}
+
+
+def match_scratch(dev: torch.device, Kc: int, Ks: int) -> torch.Tensor:
+    """Caller scratch of wast3d_w2_match / wast3d_nn_match (wast3d_match_scratch_bytes), cached per device."""
+    need = int(_lib.load().wast3d_match_scratch_bytes(int(Kc), int(Ks)))
+    key = torch.device(dev).index
+    t = _SCRATCH.get(key)
+    if t is None or t.numel() < need:
+        t = torch.empty(_lib.bucket_bytes(need), dtype=torch.uint8, device=dev)
+        _SCRATCH[key] = t
+    return t
+
+
 def _check3(t, name, cols):
     if t.dim() != 2 or t.size(1) != cols:
         raise RuntimeError(f"{name} must have dimensions (n, {cols})")
@@ -55,9 +71,10 @@ def nn_match(a: torch.Tensor, b: torch.Tensor):
     dist = torch.empty((Na,), dtype=torch.float32, device=a.device)
     keep: list = []
     with torch.cuda.device(a.device):
+        ws = match_scratch(a.device, Na, Nb)
         st = lib.wast3d_nn_match(Na, Nb, _lib.fptr(a, keep), _lib.fptr(b, keep),
                                  idx.data_ptr() if Na else None, dist.data_ptr() if Na else None,
-                                 _lib.stream_ptr())
+                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr())
     _lib.check(st, "nn_match")
     return idx.long(), dist
 
@@ -137,12 +154,17 @@ def emd2_uniform(xa: torch.Tensor, xb: torch.Tensor, return_plan: bool = False):
     return (cost, perm.long()) if return_plan else cost
 
 
-def w2_match(mean_c, cov_c, mean_s, cov_s, return_stats: bool = False, _lb_dump: bool = False):
+def w2_match(mean_c, cov_c, mean_s, cov_s, return_stats: bool = False, _lb_dump: bool = False,
+             stats_out: torch.Tensor | None = None, int32_out: tuple | None = None):
     """Nearest style cluster per content cluster under squared Gaussian W2.
 
     Returns (idx int64 [Kc], cost float32 [Kc]) and, with return_stats, a dict
     {pairs, exact_evals, gemm_tiles}: how many of the Kc*Ks pairs needed the exact Bures term
-    after the tensor-core lower bound.
+    after the tensor-core lower bound (reading it synchronises; pass `stats_out`, a device int64[4]
+    tensor, to collect the counters without a host round trip).  The call itself never synchronises:
+    a (never expected) tensor-core barrier time-out shows as idx == -2 / cost NaN.
+    `int32_out` = (idx int32 [Kc], cost [Kc]) preallocated outputs: nothing is allocated or converted
+    (steady-state loops, bench.py).
     """
     _check3(mean_c, "mean_c", 3)
     _check3(cov_c, "cov_c", 6)
@@ -154,23 +176,34 @@ def w2_match(mean_c, cov_c, mean_s, cov_s, return_stats: bool = False, _lb_dump:
     Kc, Ks = int(mean_c.size(0)), int(mean_s.size(0))
     if Ks == 0:
         raise RuntimeError("w2_match: no style clusters")
-    idx = torch.empty((Kc,), dtype=torch.int32, device=dev)
-    cost = torch.empty((Kc,), dtype=torch.float32, device=dev)
-    stats = torch.zeros((4,), dtype=torch.int64, device=dev)
+    if int32_out is not None:
+        idx, cost = int32_out
+        if idx.dtype != torch.int32 or cost.dtype != torch.float32 or idx.numel() != Kc or cost.numel() != Kc:
+            raise RuntimeError("w2_match: int32_out must be (int32 [Kc], float32 [Kc])")
+    else:
+        idx = torch.empty((Kc,), dtype=torch.int32, device=dev)
+        cost = torch.empty((Kc,), dtype=torch.float32, device=dev)
+    want_stats = return_stats or stats_out is not None
+    stats = stats_out if stats_out is not None else (torch.empty((4,), dtype=torch.int64, device=dev) if want_stats else None)
     lb = torch.full((Kc, Ks), float("nan"), dtype=torch.float32, device=dev) if _lb_dump else None
     keep: list = []
     args = (Kc, Ks, _lib.fptr(mean_c, keep), _lib.fptr(cov_c, keep), _lib.fptr(mean_s, keep),
             _lib.fptr(cov_s, keep), idx.data_ptr() if Kc else None, cost.data_ptr() if Kc else None,
-            stats.data_ptr())
+            stats.data_ptr() if stats is not None else None)
     with torch.cuda.device(dev):
         if _lb_dump:
             st = lib.wast3d_w2_match_debug(*args, lb.data_ptr(), _lib.stream_ptr())
         else:
-            st = lib.wast3d_w2_match(*args, _lib.stream_ptr())
+            ws = match_scratch(dev, Kc, Ks)
+            st = lib.wast3d_w2_match(*args, ws.data_ptr(), ws.numel(), _lib.stream_ptr())
     _lib.check(st, "w2_match")
+    if int32_out is not None:
+        return idx, cost
     out = (idx.long(), cost)
     if return_stats:
         s = stats.tolist()
+        if s[3]:
+            raise RuntimeError("w2_match: tensor-core barrier timed out on the device")
         out = out + ({"pairs": s[0], "exact_evals": s[1], "gemm_tiles": s[2]},)
     if _lb_dump:
         out = out + (lb,)

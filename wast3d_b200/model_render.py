@@ -110,8 +110,16 @@ class _RasterizeModel(torch.autograd.Function):
                 _lib.check(st, "rasterize_model_backward_adam")
             fused_opt._applied = True
             sink.fresh = False
+            # the parameters changed in place outside autograd's view: any other graph branch that saved them
+            # must fail loudly instead of silently using post-update values
+            for p_ in ctx.sink_params:
+                if p_.numel():
+                    torch.autograd.graph.increment_version(p_)
             return None, d_m2d, None, None, None, None, None, None, None, None, None
-        if sink is not None and sink.fresh:
+        # arena path only when nothing else has produced a gradient for these leaves in this step: re-pointing
+        # .grad at the arena view would drop an earlier regulariser's gradient (it is accumulated by autograd
+        # instead, and the optimizer copies .grad into the arena)
+        if sink is not None and sink.fresh and all(p_.grad is None for p_ in ctx.sink_params):
             sunk = [sink.view_for(p) for p in ctx.sink_params]
             if any(v is None for v in sunk):
                 sunk = None

@@ -129,6 +129,16 @@ class BackwardFusedAdam(FusedAdam):
         if closure is not None:
             raise RuntimeError("BackwardFusedAdam: closures are not supported")
         if self._applied:
+            # the update already happened inside the rasteriser's backward, from the render gradient alone: a
+            # gradient that autograd left in .grad (a regulariser on the leaves in the same loss.backward())
+            # was not part of it
+            stray = [i for i, g in enumerate(self.param_groups) if g["params"][0].grad is not None]
+            if stray:
+                self._applied = False
+                raise RuntimeError(
+                    "BackwardFusedAdam: parameter group(s) %s received a gradient outside the rasteriser's backward; "
+                    "the in-backward update only sees the render gradient. Use training_setup(fused=True) when the "
+                    "loss has terms that reach the leaves without passing through render()." % stray)
             self._applied = False
             return None
         return super().step()

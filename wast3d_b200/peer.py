@@ -386,6 +386,33 @@ class PeerShardedAdam(torch.optim.Optimizer):
         super().zero_grad(set_to_none=True)  # the arena views are overwritten by the next backward
         self.grad_sink.fresh = True
 
+    # -- checkpointing (the reference's GaussianModel.capture / restore go through optimizer.state_dict(),
+    #    scene/gaussian_model.py:58-77).  The moments live in flat per-rank shards, not in self.state: expose them
+    #    so a resume restores them instead of silently resetting Adam.
+    def state_dict(self):
+        d = super().state_dict()
+        d["peer_sharded"] = {"world": self.world, "rank": self.rank, "shards": [tuple(s) for s in self.shards],
+                             "exp_avg": self.exp_avg.detach().clone(), "exp_avg_sq": self.exp_avg_sq.detach().clone(),
+                             "steps": list(self._steps), "epoch": int(self._epoch)}
+        return d
+
+    def load_state_dict(self, state_dict):
+        sd = dict(state_dict)
+        mine = sd.pop("peer_sharded", None)
+        if mine is None:
+            raise RuntimeError("PeerShardedAdam.load_state_dict: not a PeerShardedAdam checkpoint (the sharded "
+                               "moments are missing); resuming would silently reset Adam's state")
+        if mine["world"] != self.world or mine["rank"] != self.rank or \
+                [tuple(s) for s in mine["shards"]] != [tuple(s) for s in self.shards]:
+            raise RuntimeError("PeerShardedAdam.load_state_dict: checkpoint was written with a different world size, "
+                               "rank or arena layout")
+        super().load_state_dict(sd)
+        with torch.no_grad():
+            self.exp_avg.copy_(mine["exp_avg"].to(self.device))
+            self.exp_avg_sq.copy_(mine["exp_avg_sq"].to(self.device))
+        self._steps = list(mine["steps"])
+        self._epoch = int(mine["epoch"])
+
     def check_peers(self):
         """Raise if a step timed out waiting for a peer (sticky flag set by the kernel)."""
         e = int(_lib.load().wast3d_peer_error(0))
