@@ -235,23 +235,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // ---------------------------------------------------------------- match -------------------------
-// grid = (row blocks, column splits); block = 256 threads.  Thread t serves content row (t & 127) of the
-// block (TMEM lane t & 127); warps 0-3 read columns [0,64) of a tile's accumulator, warps 4-7 columns
-// [64,128) (a warp can only address the TMEM lane quarter warp_id % 4).
+// grid = (row blocks, column splits); block = 512 threads.  Thread t serves content row (t & 127) of the
+// block (TMEM lane t & 127) and the 32 accumulator columns [32 (t >> 7), +32) of a tile (a warp can only
+// address the TMEM lane quarter warp_id % 4, so the four warps that share a quarter split the columns).
+// Two CTAs (2 x 256 TMEM columns) per SM = 32 resident warps to hide the exact evaluation's sqrt chain.
 //
 // Per 128 x 128 tile:
 //   MMA      one tcgen05.mma into one of two TMEM buffers, issued one tile AHEAD of its epilogue, operands and
 //            exact style descriptors staged with cp.async two tiles ahead (double buffered);
-//   phase A  every thread compares its 64 lower bounds with the row's threshold and appends the survivors
-//            (row, column) to a shared candidate list (warp-aggregated append);
-//   phase B  the 256 threads evaluate the candidates' exact costs — one candidate per thread and round, so
+//   phase A  every thread compares its 32 lower bounds with the row's threshold and appends the survivors
+//            (row, column) to a shared candidate list (warp-aggregated append; what does not fit the list is
+//            evaluated on the spot by its owner);
+//   phase B  the 512 threads evaluate the candidates' exact costs — one candidate per thread and round, so
 //            the long exact evaluation (20 dependent square roots for W2) never runs with 1/32 of a warp
 //            active — and merge (cost, column) into the row's packed best with a shared 64-bit atomicMin
 //            (cost bits high, column low: ties go to the lowest column in any evaluation order).
 // The first tile of a CTA starts best-first: every row evaluates the column with the smallest bound, which
 // makes the thresholds tight before the first candidate list is built.  Column splits of the same rows share
 // their progress through the global packed word (read before, published after every tile).
-constexpr int MT_THREADS = 256;
+constexpr int MT_THREADS = 512;
+constexpr int MT_COLS = MT_N / (MT_THREADS / MT_M);   // accumulator columns per thread and tile (32)
+constexpr int MT_CAND = 8192;                          // candidate list entries (typical tile: < 100)
 constexpr int DESC_STRIDE = 20;   // floats per descriptor row in shared memory (80 B: conflict-free float4 rows)
 
 struct MatchSmem {
@@ -260,7 +264,7 @@ struct MatchSmem {
     float desc_s[2][MT_N * DESC_STRIDE];
     float desc_c[MT_M * DESC_STRIDE];
     unsigned long long best[MT_M];
-    uint16_t cand[MT_M * MT_N];
+    uint16_t cand[MT_CAND];
     uint64_t bar[2];
     uint32_t tmem;
     uint32_t n_cand;
@@ -296,7 +300,7 @@ __device__ __forceinline__ unsigned long long exact_packed(const float* dc, cons
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(MT_THREADS)
+__global__ void __launch_bounds__(MT_THREADS, 2)
 match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __restrict__ desc_s,
              const __nv_bfloat16* __restrict__ oper_c, const __nv_bfloat16* __restrict__ oper_s,
              int tiles_per_split, unsigned long long* __restrict__ best_packed,
@@ -306,7 +310,7 @@ match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __re
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rl = tid & (MT_M - 1);          // row within the block == TMEM lane
-    const int half = tid >> 7;                // which 64 columns of a tile this thread reads
+    const int cgrp = tid >> 7;                // which MT_COLS columns of a tile this thread reads
     const int row = blockIdx.x * MT_M + rl;
     const bool row_ok = row < Kc;
     const int n_tiles = (Ks + MT_N - 1) / MT_N;
@@ -344,13 +348,9 @@ match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __re
             cp_async16(sm.B[b] + tile_off(tid, 0), src);
             cp_async16(sm.B[b] + tile_off(tid, 8), src + 8);
         }
-        const int c = tid >> 1, h = tid & 1;
-        if (col0 + c < Ks) {
-            const float* src = desc_s + 16 * (size_t)(col0 + c) + 8 * h;
-            float* dst = sm.desc_s[b] + DESC_STRIDE * c + 8 * h;
-            cp_async16(dst, src);
-            cp_async16(dst + 4, src + 4);
-        }
+        const int c = tid >> 2, h = tid & 3;   // 512 threads x 16 bytes = 128 descriptors of 64 bytes
+        if (col0 + c < Ks)
+            cp_async16(sm.desc_s[b] + DESC_STRIDE * c + 4 * h, desc_s + 16 * (size_t)(col0 + c) + 4 * h);
         cp_async_commit();
     };
     stage(0);
@@ -404,28 +404,25 @@ match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __re
             const unsigned long long g = ld_relaxed_u64(best_packed + row);
             if (g < sm.best[tid]) sm.best[tid] = g;
         }
-        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(b * MT_N + half * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(b * MT_N + cgrp * MT_COLS);
         const float* dsb = sm.desc_s[b];
+        static_assert(MT_COLS == 32, "one tcgen05.ld.32x32b.x32 per thread and tile");
+        const int cbase = cgrp * MT_COLS;
+        int kmin = -1;
         if (i == 0) {
-            // best-first: exact cost of the column with the smallest bound in this thread's 64 columns
+            // best-first: exact cost of the column with the smallest bound among this thread's columns
+            // (its own TMEM read: the 32 bounds are not kept in registers across the exact evaluation)
             float vmin = __int_as_float(0x7f800000);
-            int kmin = -1;
-#pragma unroll 1
-            for (int c = 0; c < 64; c += 32) {
-                float v[32];
-                tmem_ld32(taddr + (uint32_t)c, v);
+            {
+                float v0[MT_COLS];
+                tmem_ld32(taddr, v0);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) {
-                    const int cl = half * 64 + c + k;
-                    if (col0 + cl < Ks && v[k] < vmin) { vmin = v[k]; kmin = cl; }
-                }
+                for (int k = 0; k < MT_COLS; ++k)
+                    if (col0 + cbase + k < Ks && v0[k] < vmin) { vmin = v0[k]; kmin = k; }
             }
             __syncthreads();   // the reads of best_packed above are merged before anybody min()s into best[]
             if (row_ok && kmin >= 0) {
-                float dc[16], ds[16];
-                load_desc(my_dc, dc);
-                load_desc(dsb + DESC_STRIDE * kmin, ds);
-                atomicMin(&sm.best[rl], exact_packed<MODE>(dc, ds, col0 + kmin));
+                atomicMin(&sm.best[rl], exact_packed<MODE>(my_dc, dsb + DESC_STRIDE * (cbase + kmin), col0 + cbase + kmin));
                 ++n_exact;
             }
         }
@@ -433,20 +430,18 @@ match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __re
         const float thresh = thresh_of<MODE>(sm.best[rl]);
 
         // ---- phase A: candidates whose (margin-adjusted) lower bound can still beat the row's best
-#pragma unroll 1
-        for (int c = 0; c < 64; c += 32) {
-            float v[32];
-            tmem_ld32(taddr + (uint32_t)c, v);
-            const int cbase = half * 64 + c;
+        {
+            float v[MT_COLS];
+            tmem_ld32(taddr, v);
             if (lb_dump != nullptr && row_ok) {
 #pragma unroll
-                for (int k = 0; k < 32; ++k)
+                for (int k = 0; k < MT_COLS; ++k)
                     if (col0 + cbase + k < Ks) lb_dump[(size_t)row * Ks + col0 + cbase + k] = v[k];
             }
             unsigned mask = 0;
 #pragma unroll
-            for (int k = 0; k < 32; ++k)
-                if (row_ok && col0 + cbase + k < Ks && !(v[k] > thresh)) mask |= 1u << k;
+            for (int k = 0; k < MT_COLS; ++k)
+                if (row_ok && col0 + cbase + k < Ks && k != kmin && !(v[k] > thresh)) mask |= 1u << k;
             const int cnt = __popc(mask);
             int incl = cnt;
 #pragma unroll
@@ -462,21 +457,24 @@ match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __re
             while (mask) {
                 const int k = __ffs(mask) - 1;
                 mask &= mask - 1;
-                sm.cand[pos++] = (uint16_t)((rl << 7) | (cbase + k));
+                if (pos < MT_CAND) {
+                    sm.cand[pos] = (uint16_t)((rl << 7) | (cbase + k));
+                } else {   // list full (degenerate data: thousands of near-ties in one tile): evaluate here
+                    atomicMin(&sm.best[rl], exact_packed<MODE>(my_dc, dsb + DESC_STRIDE * (cbase + k), col0 + cbase + k));
+                    ++n_exact;
+                }
+                ++pos;
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
 
         // ---- phase B: exact costs, one candidate per thread and round
-        const int n = (int)sm.n_cand;
+        const int n = min((int)sm.n_cand, MT_CAND);
         for (int k = tid; k < n; k += MT_THREADS) {
             const int cd = sm.cand[k];
             const int r = cd >> 7, cl = cd & 127;
-            float dc[16], ds[16];
-            load_desc(sm.desc_c + DESC_STRIDE * r, dc);
-            load_desc(dsb + DESC_STRIDE * cl, ds);
-            atomicMin(&sm.best[r], exact_packed<MODE>(dc, ds, col0 + cl));
+            atomicMin(&sm.best[r], exact_packed<MODE>(sm.desc_c + DESC_STRIDE * r, dsb + DESC_STRIDE * cl, col0 + cl));
         }
         if (tid == 0) n_exact += (unsigned long long)n;
         __syncthreads();
@@ -708,7 +706,8 @@ static int run_match(int Kc, int Ks, const float* mean_c, const float* cov_c, co
         if (Ks > 0) {
             const int row_blocks = Kc_pad / MT_M;
             const int n_tiles = Ks_pad / MT_N;
-            int splits = (2 * 148 + row_blocks - 1) / row_blocks;   // two CTAs (of 8 warps) per SM
+            // two CTAs (2 x 256 TMEM columns, 16 warps each) per SM: as many column splits as still fit ONE wave
+            int splits = (2 * 148) / row_blocks;
             if (splits > n_tiles) splits = n_tiles;
             if (splits < 1) splits = 1;
             const int tiles_per_split = (n_tiles + splits - 1) / splits;
