@@ -206,6 +206,18 @@ int wast3d_knn_dist2(int P, const float* points, float* mean_dist2, int32_t* nn_
 int wast3d_cluster_stats(int n, int K, const float* points, const int32_t* labels,
                          float* mean, float* cov6, int32_t* count, void* stream);
 
+/* The two accumulation passes of wast3d_cluster_stats on caller-owned accumulators (ABI v6), for statistics over
+ * points that are sharded across GPUs ("segmented mean/covariance over 6 M points shard by point with a
+ * reduce of 10 floats x Kc"): every rank adds its points, the host all-reduces the accumulators in between.
+ *   wast3d_cluster_sums:    sum3 [K,3] double += member xyz, count [K] int32 += members        (zero them first)
+ *   wast3d_cluster_scatter: acc6 [K,6] double += (x - mean)(x - mean)^T upper triangle, mean3 [K,3] double = sum / count
+ * Then mean = (float) mean3, cov6 = (float)(acc6 / count): bit-identical to wast3d_cluster_stats on the union
+ * of the points up to the (double) summation order. */
+int wast3d_cluster_sums(int n, int K, const float* points, const int32_t* labels, double* sum3, int32_t* count,
+                        void* stream);
+int wast3d_cluster_scatter(int n, int K, const float* points, const int32_t* labels, const double* mean3,
+                           double* acc6, void* stream);
+
 /* wast3d_nn_match: for each query row a[i] ([Na,3]) the index of the nearest b[j] ([Nb,3])
  * = argmin_j cdist(a,b)[i,j] with ties to the lowest j; out_dist = that Euclidean distance.
  * Decided on fp32 values computed in torch.cdist's operation order (oracle/match_oracle.c).
@@ -336,6 +348,24 @@ int wast3d_pixel_loss_forward(int C, int H, int W, const float* img, const float
 int wast3d_pixel_loss_backward(int C, int H, int W, const float* img, const float* gt, const float* depth,
                                const float* depth_gt, float w_l1, float w_tv, float w_depth,
                                const float* grad_out, float* d_img, float* d_depth, void* stream);
+
+/* Depth -> normal map of the train_st_normals variant (BASELINE.json configs[4]); replaces the kornia / torch
+ * expression of train_st_normals.py:113-123:
+ *   normals = kornia.geometry.depth.depth_to_normals(depth[None,None], K, normalize_points=False)   (unit normals)
+ *   image_normals = (normals - amin(normals)) / (amax(normals) - amin(normals) + 1e-6)
+ * with K = [[fx,0,cx],[0,fy,cy],[0,0,1]] (the reference hard-codes 1111, 1111, 400, 400 for its 800x800 images).
+ * kornia is an un-vendored, unpinned dependency: its published algorithm (unproject with the pixel grid, 3x3 Sobel / 8
+ * with replicate padding on the point image, cross product, F.normalize with eps 1e-12) is restated in
+ * oracle/normals.py.  depth [H,W] -> normals_unit [3,H,W], normals01 [3,H,W], minmax [2] (amin, amax), all DEVICE.
+ * backward: grad01 [3,H,W] -> grad_depth [H,W] (every element written), including the gradient that flows through
+ * amin / amax (shared evenly among ties like torch); grad_ab is a [6,H,W] scratch image.  scratch:
+ * wast3d_depth_normals_scratch_bytes() bytes, reusable on the same stream.  Deterministic (no float atomics). */
+size_t wast3d_depth_normals_scratch_bytes(void);
+int wast3d_depth_normals_forward(int H, int W, const float* depth, float fx, float fy, float cx, float cy,
+                                 float* normals_unit, float* normals01, float* minmax, void* scratch, void* stream);
+int wast3d_depth_normals_backward(int H, int W, const float* depth, float fx, float fy, float cx, float cy,
+                                  const float* normals_unit, const float* minmax, const float* grad01,
+                                  float* grad_ab, float* grad_depth, void* scratch, void* stream);
 
 /* ---- view-parallel optimizer step over NVLink peer memory (ABI v3) ------------------
  * The reference is single-GPU: torch.optim.Adam over six groups (scene/gaussian_model.py:149-167).

@@ -149,6 +149,37 @@ def test_sharded_matching_equals_unsharded():
     assert _run(_match_job) == [True, True]
 
 
+def _stats_job(rank, world):
+    """C4 host logic: statistics of points sharded BY POINT over two ranks == the oracle's statistics of the union
+    (two all-reduces of 4 + 6 numbers per cluster; numpy stand-ins for the CUDA accumulation kernels)."""
+    from oracle import cpu
+    rng = np.random.default_rng(9)
+    n, K = 5003, 37
+    pts = (rng.normal(size=(n, 3)) * 2.0 + 5.0).astype(np.float32)
+    lab = rng.integers(0, K - 3, size=n).astype(np.int32)          # clusters K-3..K-1 stay empty
+    s, e = wd.shard_bounds(n, rank, world)
+
+    def sums(p, l, K_, sum3, count):
+        np.add.at(sum3.numpy(), l.numpy(), p.numpy().astype(np.float64))
+        np.add.at(count.numpy(), l.numpy(), 1)
+
+    def scatter(p, l, K_, mean3, acc6):
+        d = p.numpy().astype(np.float64) - mean3.numpy()[l.numpy()]
+        m = np.stack([d[:, 0] * d[:, 0], d[:, 0] * d[:, 1], d[:, 0] * d[:, 2], d[:, 1] * d[:, 1], d[:, 1] * d[:, 2],
+                      d[:, 2] * d[:, 2]], 1)
+        np.add.at(acc6.numpy(), l.numpy(), m)
+
+    mean, cov, count = wd.sharded_cluster_stats(torch.from_numpy(pts[s:e]), torch.from_numpy(lab[s:e]), K,
+                                                sums_fn=sums, scatter_fn=scatter)
+    om, oc, on = cpu.cluster_stats(pts, lab, K)
+    return bool((count.numpy() == on).all() and np.abs(mean.numpy() - om).max() <= 1e-6 and
+                np.abs(cov.numpy() - oc).max() <= 1e-6 and (cov.numpy()[K - 3:] == 0).all())
+
+
+def test_point_sharded_cluster_stats_equal_unsharded():
+    assert _run(_stats_job) == [True, True]
+
+
 def test_view_assignment():
     cams = list(range(8))
     seen = [wd.view_for_rank(cams, step, r, 4) for step in range(2) for r in range(4)]

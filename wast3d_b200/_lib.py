@@ -78,6 +78,8 @@ SIGNATURES = {
     "wast3d_knn_scratch_bytes": (_sz, [_i]),
     "wast3d_knn_dist2": (_i, [_i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wast3d_cluster_stats": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_cluster_sums": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_cluster_scatter": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_match_scratch_bytes": (_sz, [_i, _i]),
     "wast3d_nn_match": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "wast3d_cdist_topk": (_i, [_i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
@@ -95,6 +97,9 @@ SIGNATURES = {
     "wast3d_pixel_loss_scratch_bytes": (_sz, []),
     "wast3d_pixel_loss_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp]),
     "wast3d_pixel_loss_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _f, _f, _f, _vp, _vp, _vp, _vp]),
+    "wast3d_depth_normals_scratch_bytes": (_sz, []),
+    "wast3d_depth_normals_forward": (_i, [_i, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp]),
+    "wast3d_depth_normals_backward": (_i, [_i, _i, _vp, _f, _f, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_kmeans_lloyd": (_i, [_i, _i, _vp, _vp, _vp, _i, C.c_double, C.POINTER(C.c_double), C.POINTER(_i),
                                  C.POINTER(C.c_double), _vp]),
     "wast3d_pair_dist_forward": (_i, [C.POINTER(PairArgs), _vp, _vp]),

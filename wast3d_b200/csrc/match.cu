@@ -438,10 +438,14 @@ match_kernel(int Kc, int Ks, const float* __restrict__ desc_c, const float* __re
                 for (int k = 0; k < MT_COLS; ++k)
                     if (col0 + cbase + k < Ks) lb_dump[(size_t)row * Ks + col0 + cbase + k] = v[k];
             }
+            // one compare + one bit insert per bound; validity (row, column range, the best-first column) as masks
             unsigned mask = 0;
 #pragma unroll
-            for (int k = 0; k < MT_COLS; ++k)
-                if (row_ok && col0 + cbase + k < Ks && k != kmin && !(v[k] > thresh)) mask |= 1u << k;
+            for (int k = 0; k < MT_COLS; ++k) mask |= (v[k] > thresh ? 0u : 1u) << k;
+            const int n_valid = Ks - (col0 + cbase);
+            if (n_valid < MT_COLS) mask &= n_valid > 0 ? ((1u << n_valid) - 1u) : 0u;
+            if (kmin >= 0) mask &= ~(1u << kmin);
+            if (!row_ok) mask = 0;
             const int cnt = __popc(mask);
             int incl = cnt;
 #pragma unroll
@@ -788,6 +792,28 @@ extern "C" int wast3d_cluster_stats(int n, int K, const float* points, const int
     if (rc == WAST3D_ERR_CUDA) set_last_cuda_error(cudaGetLastError(), __FILE__, __LINE__);
     cudaFreeAsync(buf, s);
     return rc;
+}
+
+// Point-sharded statistics (BASELINE.json configs[3]): the two accumulation passes of
+// wast3d_cluster_stats on caller-owned accumulators, so that N ranks can each add their share of the points and
+// all-reduce 4 + 6 numbers per cluster in between (wast3d_b200/distributed.py sharded_cluster_stats).
+extern "C" int wast3d_cluster_sums(int n, int K, const float* points, const int32_t* labels, double* sum3,
+                                   int32_t* count, void* stream_v) {
+    if (n < 0 || K < 0 || (K > 0 && (!sum3 || !count)) || (n > 0 && (!points || !labels))) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return WAST3D_OK;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    cluster_sum_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, K, points, labels, sum3, count);
+    W3D_AFTER_LAUNCH(s, false);
+    return WAST3D_OK;
+}
+extern "C" int wast3d_cluster_scatter(int n, int K, const float* points, const int32_t* labels, const double* mean3,
+                                      double* acc6, void* stream_v) {
+    if (n < 0 || K < 0 || (K > 0 && (!mean3 || !acc6)) || (n > 0 && (!points || !labels))) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (n == 0 || K == 0) return WAST3D_OK;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    cluster_cov_kernel<<<(n + 255) / 256, 256, 0, s>>>(n, K, points, labels, mean3, acc6);
+    W3D_AFTER_LAUNCH(s, false);
+    return WAST3D_OK;
 }
 
 // Lloyd's K-Means on 3-D points (replaces sklearn.cluster.KMeans(...).fit_predict as called by

@@ -162,6 +162,38 @@ def sharded_match(match_fn: Callable[..., Sequence[torch.Tensor]], row_tensors: 
     return idx_full, cost_full
 
 
+def sharded_cluster_stats(points_shard: torch.Tensor, labels_shard: torch.Tensor, K: int, group=None,
+                          sums_fn: Callable = None, scatter_fn: Callable = None):
+    """Per-cluster (mean [K,3], cov6 [K,6], count [K]) of points that are sharded BY POINT across the ranks
+    (BASELINE.json configs[3]: 6 M Gaussians, 16 384 content clusters).  Every rank adds its
+    points into [K,3] + [K] accumulators, one all-reduce; the means are then identical everywhere, every rank adds its
+    centred second moments, second all-reduce of [K,6] doubles.  Two collectives of 10 numbers per cluster in total;
+    the points never move.  Same two passes as the single-GPU `matching.cluster_stats`.
+
+    `sums_fn(points, labels, K, sum3, count)` / `scatter_fn(points, labels, K, mean3, acc6)` accumulate in place;
+    they default to the library kernels (wast3d_cluster_sums / wast3d_cluster_scatter) — the CPU tests pass
+    stand-ins to exercise the collectives with gloo."""
+    if sums_fn is None or scatter_fn is None:
+        from . import matching
+        sums_fn, scatter_fn = matching.cluster_sums, matching.cluster_scatter
+    dev = points_shard.device
+    sum3 = torch.zeros((K, 3), dtype=torch.float64, device=dev)
+    count = torch.zeros((K,), dtype=torch.int32, device=dev)
+    sums_fn(points_shard, labels_shard, K, sum3, count)
+    multi = dist.is_initialized() and dist.get_world_size(group) > 1
+    if multi:
+        dist.all_reduce(sum3, group=group)
+        dist.all_reduce(count, group=group)
+    c = count.to(torch.float64).unsqueeze(1)
+    mean3 = torch.where(c > 0, sum3 / c.clamp_min(1.0), torch.zeros_like(sum3))
+    acc6 = torch.zeros((K, 6), dtype=torch.float64, device=dev)
+    scatter_fn(points_shard, labels_shard, K, mean3, acc6)
+    if multi:
+        dist.all_reduce(acc6, group=group)
+    cov6 = torch.where(c > 0, acc6 / c.clamp_min(1.0), torch.zeros_like(acc6))
+    return mean3.to(torch.float32), cov6.to(torch.float32), count
+
+
 def view_for_rank(cameras: Sequence, step: int, rank: int, world: int):
     """Camera of `rank` in the `step`-th view batch (k ranks render k different cameras)."""
     return cameras[(step * world + rank) % len(cameras)]

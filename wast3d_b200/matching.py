@@ -57,6 +57,32 @@ def cluster_stats(points: torch.Tensor, labels: torch.Tensor, K: int):
     return mean, cov, count
 
 
+def cluster_sums(points: torch.Tensor, labels: torch.Tensor, K: int, sum3: torch.Tensor, count: torch.Tensor):
+    """Pass 1 of the statistics on caller accumulators: sum3 [K,3] float64 += member xyz, count [K] int32 += 1."""
+    _check3(points, "points", 3)
+    _lib.require_device(points)
+    keep: list = []
+    lab = labels.to(device=points.device, dtype=torch.int32)
+    with torch.cuda.device(points.device):
+        st = _lib.load().wast3d_cluster_sums(int(points.size(0)), int(K), _lib.fptr(points, keep),
+                                             _lib.fptr(lab, keep, torch.int32), sum3.data_ptr(), count.data_ptr(),
+                                             _lib.stream_ptr())
+    _lib.check(st, "cluster_sums")
+
+
+def cluster_scatter(points: torch.Tensor, labels: torch.Tensor, K: int, mean3: torch.Tensor, acc6: torch.Tensor):
+    """Pass 2: acc6 [K,6] float64 += (x - mean)(x - mean)^T (upper triangle) with mean3 [K,3] float64."""
+    _check3(points, "points", 3)
+    _lib.require_device(points)
+    keep: list = []
+    lab = labels.to(device=points.device, dtype=torch.int32)
+    with torch.cuda.device(points.device):
+        st = _lib.load().wast3d_cluster_scatter(int(points.size(0)), int(K), _lib.fptr(points, keep),
+                                                _lib.fptr(lab, keep, torch.int32), mean3.data_ptr(), acc6.data_ptr(),
+                                                _lib.stream_ptr())
+    _lib.check(st, "cluster_scatter")
+
+
 def nn_match(a: torch.Tensor, b: torch.Tensor):
     """(argmin_j |a_i - b_j|, that distance): what `torch.min(torch.cdist(a, b), 1)` returns
     (values, indices swapped into (idx, dist) order); ties go to the lowest index."""
