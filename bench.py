@@ -71,6 +71,10 @@ def parse():
                     help="peer arm: 1 = the SH features (81%% of the parameter bytes) are reduced / updated / all-gathered by "
                          "a second launch on a side stream that overlaps the next view's projection, sorting and binning "
                          "(the rasteriser's colour kernel waits for it); 0 = one launch, the step waits for all of it")
+    ap.add_argument("--async-forward", type=int, default=1, choices=[0, 1],
+                    help="1 = graph-safe forward (wast3d_raster_forward_async): the instance count is never read back by the "
+                         "host, the binning buffer is sized from the largest count seen; 0 = the reference's protocol "
+                         "(one blocking read of num_rendered per forward, rasterizer_impl.cu:283)")
     ap.add_argument("--tile-cut", type=int, default=1, choices=[0, 1],
                     help="1 = instantiate Gaussians only in tiles that can see alpha >= 1/255 (default), "
                          "0 = the reference's radius rectangles")
@@ -383,9 +387,12 @@ def workload_config(spec, n):
             "l2_policy": "inputs_larger_than_L2 (parameters+state ~2.8 GB per step vs 126 MB L2)"}
 
 
+ASYNC_FWD = [True]
+
+
 def implementation_info(sync):
     return {"grad_sync": sync, "peer_backend": PEER_BACKEND[0] if sync in ("peer", "records") else None,
-            "loss": LOSS_KIND[0]}
+            "loss": LOSS_KIND[0], "graph_safe_forward": ASYNC_FWD[0]}
 
 
 def c1_case(dev, n_content=50_000, n_style=10_000):
@@ -465,6 +472,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
     _lib.set_tile_cut(args.tile_cut)
+    from wast3d_b200 import model_render
+    model_render.set_async_forward(bool(args.async_forward))
+    ASYNC_FWD[0] = bool(args.async_forward)
     if args.sync == "auto":
         args.sync = "peer" if world > 1 else "backward"
     if args.sync == "backward" and world > 1:
@@ -1012,6 +1022,7 @@ def main():
                         "sample": f"oracle/ CPU restatement (OpenMP), every {stride}th Gaussian ({inp.P}, R={Rs}) at "
                                   f"{W}x{H}, fwd+bwd {dt:.2f} s/step, scaled x{stride}; no Adam"}
 
+    model_render.async_forward_check()   # raises if any graph-safe forward of the run overflowed its capacity
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": n_warm, "ms_per_step": ms_step, "higher_is_better": True,

@@ -104,6 +104,23 @@ int wast3d_raster_forward(const wast3d_raster_params* prm,
                           float* out_color, float* out_depth, int* radii,
                           int* num_rendered_host, void* stream);
 
+/* Graph-safe forward (ABI v6): wast3d_raster_forward without its blocking read — no cudaStreamSynchronize, no
+ * device->host copy, so a whole optimisation step can be enqueued ahead of the GPU (or captured in a CUDA graph).
+ * The reference sizes its binning buffer from num_rendered read back on the host (rasterizer_impl.cu:283-289); here the
+ * caller states an upper bound: binning_alloc is called once for `instance_capacity` instances, the instance-sized
+ * kernels take the actual count from device memory, and status_dev (DEVICE uint32[4]) receives
+ *   {num_rendered, prefiltered-violated flag, look-back time-out flag, overflow flag}.
+ * overflow != 0: the view needed more than instance_capacity instances; nothing was written out of bounds but the
+ * image of THIS call is incomplete — the caller must discard the step and retry with a larger capacity (the host
+ * layer polls the status one call later and raises).  Pass instance_capacity as `num_rendered` to the backward
+ * entry points (the binning buffer is carved for it).  Results are bit-identical to wast3d_raster_forward. */
+int wast3d_raster_forward_async(const wast3d_raster_params* prm,
+                                wast3d_alloc_fn geom_alloc, void* geom_user,
+                                wast3d_alloc_fn binning_alloc, void* binning_user,
+                                wast3d_alloc_fn img_alloc, void* img_user,
+                                float* out_color, float* out_depth, int* radii,
+                                int instance_capacity, unsigned int* status_dev, void* stream);
+
 /* Replaces RasterizeGaussiansBackwardCUDA -> Rasterizer::backward
  * (rasterize_points.cu:121-206, rasterizer_impl.cu:345-446).
  * Gradient outputs need NOT be zero-initialised: every element is written.

@@ -732,3 +732,55 @@ def test_notebook_loop_two_renders_and_leaf_regulariser(built):
     m_b, opt_b, g_b, _ = step(True, "in_backward")
     with pytest.raises(RuntimeError, match="outside the rasteriser"):
         opt_b.step()
+
+
+def test_graph_safe_forward_is_bit_identical_and_reports_overflow(built):
+    """wast3d_raster_forward_async through render(): no host read of num_rendered, instance capacity from the largest
+    count seen.  Same image / depth / radii bits as the synchronous protocol, same gradients (deterministic backward),
+    and a capacity that is too small is reported (one call late, or at async_forward_check) instead of corrupting
+    memory or passing silently."""
+    from wast3d_b200 import _lib, model_render
+    from wast3d_b200.gaussian_renderer import render
+    from wast3d_b200.scene import GaussianModel, PipelineParams, orbit_cameras, synthetic_gaussians
+    arrs = synthetic_gaussians(60000, seed=21, log_scale_mu=-3.4)
+    cams = orbit_cameras(4, 4.03, 0.0, 0.6911, 320, 240, device="cuda", sphere=True)
+    bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
+    torch.manual_seed(1)
+    offs = -torch.rand(240, 320, 2, device="cuda")
+
+    def run(cam):
+        m = GaussianModel.from_arrays(arrs, device="cuda")
+        out = render(cam, m, PipelineParams(), bg, sampling_offsets=offs)
+        (out["render"].square().mean() + 0.1 * out["depth"].mean()).backward()
+        return out["render"].detach().clone(), out["depth"].detach().clone(), out["radii"].clone(), \
+            [p.grad.clone() for p in m.parameters()]
+
+    prev_det = _lib.set_deterministic(1)
+    prev = model_render.set_async_forward(False)
+    try:
+        want = [run(c) for c in cams]
+        model_render._ASYNC_STATE.clear()
+        model_render.set_async_forward(True)
+        got = [run(c) for c in cams]                 # first call synchronous (learns R), the rest graph-safe
+        got2 = [run(c) for c in cams]
+        model_render.async_forward_check()
+        key = (torch.cuda.current_device(), 320, 240)
+        assert model_render._ASYNC_STATE[key]["seen"] > 100000
+        for res in (got, got2):
+            for a, b in zip(res, want):
+                assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+                for ga, gb in zip(a[3], b[3]):
+                    assert torch.equal(ga, gb)
+        # a capacity below the view's instance count: detected, never silent
+        model_render._ASYNC_STATE[key]["seen"] = 10
+        bad = run(cams[1])
+        with pytest.raises(RuntimeError, match="binning buffer held"):
+            model_render.async_forward_check()
+        again = run(cams[1])                          # capacity was raised from the reported count
+        model_render.async_forward_check()
+        assert torch.equal(again[0], want[1][0]) and torch.equal(again[2], want[1][2])
+        del bad
+    finally:
+        model_render.set_async_forward(prev)
+        _lib.set_deterministic(prev_det)
+        model_render._ASYNC_STATE.clear()

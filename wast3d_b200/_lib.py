@@ -64,6 +64,8 @@ SIGNATURES = {
     "wast3d_device_check": (_i, [_i]),
     "wast3d_raster_forward": (_i, [C.POINTER(RasterParams), ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp,
                                    _vp, _vp, _vp, C.POINTER(_i), _vp]),
+    "wast3d_raster_forward_async": (_i, [C.POINTER(RasterParams), ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp,
+                                         _vp, _vp, _vp, _i, _vp, _vp]),
     "wast3d_raster_backward": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_raster_backward_raw": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -184,6 +184,7 @@ struct GeomState {
     uint32_t* scan_ws;       // [scan_lookback_workspace_words(P)]
     uint32_t* totals;        // [4]  {num_rendered, num_visible, ...}
     float4* grad_rec;        // [3P] backward accumulators (see raster_backward.cu)
+    uint2* rect;             // [P]  instantiated tile rectangle {x0 | y0 << 16, width | height << 16}; 0 = none
 
     static GeomState carve(void* chunk, size_t P, size_t* bytes) {
         Carver c(chunk);
@@ -201,6 +202,7 @@ struct GeomState {
         g.scan_ws = c.take<uint32_t>(scan_lookback_workspace_words(P) + scan_scratch_words(P));
         g.totals = c.take<uint32_t>(32);
         g.grad_rec = c.take<float4>(3 * P);
+        g.rect = c.take<uint2>(P);
         if (bytes) *bytes = c.bytes();
         return g;
     }
@@ -255,9 +257,10 @@ int scan_exclusive_u32(const uint32_t* in, const uint32_t* perm, uint32_t* out, 
                        uint32_t* scratch, uint32_t* total, cudaStream_t s, bool debug);
 // One stable LSD pass on bits [shift, shift+bits) (bits <= 8).  vals_in == NULL means iota.
 // keys_out == NULL means "do not write keys" (last pass).
+// n_dev (optional, device): process min(*n_dev, n) elements; n is then the capacity the launch is sized for.
 int radix_pass_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                    uint32_t* vals_out, size_t n, int shift, int bits, uint32_t* hist,
-                   uint32_t* scan_scratch, cudaStream_t s, bool debug);
+                   uint32_t* scan_scratch, cudaStream_t s, bool debug, const uint32_t* n_dev = nullptr);
 
 // Single-pass (decoupled look-back) variants — see scan_sort.cu.  The workspace `ws` of
 // onesweep_workspace_words(n, passes) words is zeroed by onesweep_prepare() once per sort;

@@ -46,16 +46,86 @@ static int deterministic_mode() {
 }
 
 constexpr int BWD_BATCH = 256;
-constexpr int ACC_STRIDE = 12;
-// gradient record slots
-//  0 dmean2D.x  1 dmean2D.y  2 dconic.x  3 dconic.y | 4 dconic.w  5 dopacity  6 dviewdepth  7 - |
-//  8 dcolor.r   9 dcolor.g  10 dcolor.b  11 -
+// gradient record (48 bytes per Gaussian), accumulated by K7, consumed by K8+K9:
+//  0 M_x   1 M_y   2 M_xx  3 M_xy | 4 M_yy  5 M_0  6 dviewdepth  7 - | 8 dcolor.r  9 dcolor.g  10 dcolor.b  11 -
+// K7 sums MOMENTS of t = G * dL/dalpha over the pixels (M_0 = sum t, M_x = sum t dx, M_y = sum t dy, M_xx = sum t dx^2,
+// M_xy = sum t dx dy, M_yy = sum t dy^2; dx, dy as in backward.cu:497): with the Gaussian's conic (A, B, C) and
+// opacity o, which are constant over the pixels, the reference's per-pixel gradients (backward.cu:567-583) sum to
+//   dL/dmean2D.x = -o (W/2) (A M_x + B M_y)      dL/dmean2D.y = -o (H/2) (C M_y + B M_x)
+//   dL/dconic    = -o/2 (M_xx, M_xy, M_yy)       dL/dopacity  = M_0
+// which K8+K9 evaluates once per Gaussian (moments_to_gradients) instead of K7 once per pixel: 6 multiplies per
+// (pixel, Gaussian) pair instead of 18.
 
 __device__ __forceinline__ float rcp_approx(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+
+// Per-pixel state of the back-to-front replay (backward.cu:463-478,529-563).
+struct ReplayPixel {
+    float2 pixf;
+    float T, T_final;
+    float accum0, accum1, accum2;
+    float last_alpha, last_c0, last_c1, last_c2;
+    float dpix0, dpix1, dpix2, ddepth, bg_dot_dpixel;
+    uint32_t last_contributor;
+};
+
+// One (pixel, Gaussian) pair of the replay.  Returns false when the reference skips the pair (behind the pixel's
+// last contributor, power > 0, alpha < 1/255); otherwise advances the pixel state and writes the ten partials
+// v = {t dx, t dy, t dx^2, t dx dy, t dy^2, t, dviewdepth, dcolor.rgb}.
+__device__ __forceinline__ bool replay_pair(ReplayPixel& px, uint32_t pos, const float4 a, const float4 con_o,
+                                            const float4* __restrict__ c_ptr, float (&v)[10]) {
+    // backward.cu:512-514: skip Gaussians behind this pixel's last contributor
+    if (!(pos < px.last_contributor)) return false;
+    const float dx = __fsub_rn(a.x, px.pixf.x);
+    const float dy = __fsub_rn(a.y, px.pixf.y);
+    const float sy = __fmul_rn(__fmul_rn(con_o.z, dy), dy);
+    const float sq = __fmaf_rn(dx, __fmul_rn(con_o.x, dx), sy);
+    const float cr = __fmul_rn(__fmul_rn(con_o.y, dx), dy);
+    const float power = __fmaf_rn(sq, -0.5f, -cr);
+    if (power > 0.0f) return false;
+    const float G = expf(power);
+    const float alpha = fminf(0.99f, __fmul_rn(con_o.w, G));
+    if (alpha < 1.0f / 255.0f) return false;
+    const float4 c = *c_ptr;
+    // backward.cu:529-563.  One approximate reciprocal (MUFU.RCP, <= 1 ulp; 1 - alpha is in [0.01, 1]) serves both
+    // divisions of backward.cu:530,562.
+    const float inv_1ma = rcp_approx(1.f - alpha);
+    px.T = px.T * inv_1ma;
+    const float dchannel_dcolor = alpha * px.T;
+    float dL_dalpha = 0.0f;
+    px.accum0 = px.last_alpha * px.last_c0 + (1.f - px.last_alpha) * px.accum0;
+    px.last_c0 = c.x;
+    dL_dalpha += (c.x - px.accum0) * px.dpix0;
+    v[7] = dchannel_dcolor * px.dpix0;
+    px.accum1 = px.last_alpha * px.last_c1 + (1.f - px.last_alpha) * px.accum1;
+    px.last_c1 = c.y;
+    dL_dalpha += (c.y - px.accum1) * px.dpix1;
+    v[8] = dchannel_dcolor * px.dpix1;
+    px.accum2 = px.last_alpha * px.last_c2 + (1.f - px.last_alpha) * px.accum2;
+    px.last_c2 = c.z;
+    dL_dalpha += (c.z - px.accum2) * px.dpix2;
+    v[9] = dchannel_dcolor * px.dpix2;
+    v[6] = dchannel_dcolor * px.ddepth;  // backward.cu:552
+    dL_dalpha *= px.T;
+    px.last_alpha = alpha;
+    dL_dalpha += (-px.T_final * inv_1ma) * px.bg_dot_dpixel;
+    // moments of t = G dL/dalpha (see the record layout above; backward.cu:567-583 is applied per Gaussian in K8)
+    const float t = G * dL_dalpha;
+    const float tdx = t * dx, tdy = t * dy;
+    v[0] = tdx;
+    v[1] = tdy;
+    v[2] = tdx * dx;
+    v[3] = tdx * dy;
+    v[4] = tdy * dy;
+    v[5] = t;
+    return true;
+}
+
+// record float index of partial i
+__device__ __forceinline__ int record_index(int i) { return i < 7 ? i : i + 1; }
 
 // Sum v[0..11] over the warp.  On return lane L holds in the result the total of slot
 //   slot(L) = 6*b4 + 3*b3 + 2*b2 + b1   (b_k = bit k of L), valid when (2*b2+b1) < 3;
@@ -93,260 +163,59 @@ __device__ __forceinline__ float warp_reduce12(const float (&v)[12], int lane) {
     return y;
 }
 
-__global__ void __launch_bounds__(TILE_PIX)
+// ---- K7 ---------------------------------------------------------------------------------------------------
+// Pixel-parallel back-to-front replay of a 16x16 tile (one warp = 8x4 pixels), 256-record batches staged with
+// cp.async (double buffered), one barrier per batch.  Per (warp, Gaussian) hit the ten partials of the 32 pixels
+// have to be summed.  Two reduction schemes:
+//  ROWS = 0  value-halving butterfly: 13 shuffles + 21 selects + 13 adds, result lanes issue one 4-byte RED each;
+//  ROWS = H  (default, H = 3) transposed through shared memory: every lane stores its ten partials into ten rows of a
+//            per-warp [10 H][32 + 4] array as soon as they are computed (no register pressure, nothing to select);
+//            after H hits, lanes 0 .. 10 H - 1 each read one row with eight 16-byte loads, add the 32 values in a
+//            fixed order and issue the RED for (hit, slot).  About 20 issue slots per hit instead of 60, the rest
+//            of the cost moves to the (idle) shared-memory pipe.
+// DET (tests, wast3d_set_deterministic): no float atomics; the warps park their sums in shared memory, one thread per
+// instance adds them in warp order and writes inst_grad[position in the point list] (see det_gather_kernel).
+constexpr int RED_STRIDE = 36;   // floats per row: 32 pixels + 4 (conflict-free 16-byte row reads by 8 lanes at a time)
+
+template <int BATCH, int ROWS, bool DET>
+struct K7Smem {
+    float4 r0[2][BATCH];
+    float4 r1[2][BATCH];
+    float4 r2[2][BATCH];
+    uint32_t id[2][BATCH];
+    uint32_t warp_max[TILE_PIX / 32];
+    float red[ROWS > 0 ? TILE_PIX / 32 : 1][ROWS > 0 ? 10 * ROWS : 1][RED_STRIDE];
+    float part[DET ? TILE_PIX / 32 : 1][DET ? BATCH : 1][12];
+};
+
+template <int BATCH, int ROWS, bool DET, int MINB>
+__global__ void __launch_bounds__(TILE_PIX, MINB)
 render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                        const int W, const int H, const float* __restrict__ bg_color,
                        const float4* __restrict__ rec, const float* __restrict__ sampling_offsets,
                        const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
                        const float* __restrict__ dL_dpixels, const float* __restrict__ dL_ddepths,
-                       float4* __restrict__ grad_rec) {
-    __shared__ float4 s_r0[2][BWD_BATCH];
-    __shared__ float4 s_r1[2][BWD_BATCH];
-    __shared__ float4 s_r2[2][BWD_BATCH];
-    __shared__ uint32_t s_id[2][BWD_BATCH];
-    __shared__ __align__(16) float s_acc[BWD_BATCH * ACC_STRIDE];
-    __shared__ uint32_t s_touched[BWD_BATCH];
-    __shared__ uint32_t s_warp_max[TILE_PIX / 32];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
-    const uint32_t pix_id = (uint32_t)W * py + px;
-
-    float2 pixf = make_float2((float)px, (float)py);
-    if (inside && sampling_offsets != nullptr) {
-        const float2 o = *reinterpret_cast<const float2*>(sampling_offsets + 2 * (size_t)pix_id);
-        pixf.x = (float)px + o.x;
-        pixf.y = (float)py + o.y;
-    }
-    const float inf = __int_as_float(0x7f800000);
-    float bx0 = inside ? pixf.x : inf, bx1 = inside ? pixf.x : -inf;
-    float by0 = inside ? pixf.y : inf, by1 = inside ? pixf.y : -inf;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
-        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
-        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
-        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
-    }
-
-    const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
-
-    // backward.cu:463-478
-    const float T_final = inside ? final_Ts[pix_id] : 0.f;
-    float T = T_final;
-    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
-    const size_t HW = (size_t)H * W;
-    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, ddepth = 0.f;
-    if (inside) {
-        dpix0 = dL_dpixels[pix_id];
-        dpix1 = dL_dpixels[HW + pix_id];
-        dpix2 = dL_dpixels[2 * HW + pix_id];
-        ddepth = dL_ddepths ? dL_ddepths[pix_id] : 0.f;
-    }
-    // backward.cu:560-563 (pixel constant)
-    float bg_dot_dpixel = 0.f;
-    bg_dot_dpixel += bg_color[0] * dpix0;
-    bg_dot_dpixel += bg_color[1] * dpix1;
-    bg_dot_dpixel += bg_color[2] * dpix2;
-
-    // Nothing behind the tile's deepest last contributor can receive gradient.
-    const uint32_t warp_max_last = __reduce_max_sync(0xffffffffu, last_contributor);
-    if (lane == 0) s_warp_max[warp] = warp_max_last;
-    __syncthreads();
-    uint32_t n_eff = 0;
-#pragma unroll
-    for (int w = 0; w < TILE_PIX / 32; ++w) n_eff = max(n_eff, s_warp_max[w]);
-    n_eff = min(n_eff, range.y - range.x);
-    const int n = (int)n_eff;
-    const int rounds = (n + BWD_BATCH - 1) / BWD_BATCH;
-
-    auto prefetch = [&](int b) {
-        const int p = b * BWD_BATCH + tid;
-        if (p < n) {
-            const uint32_t id = point_list[range.x + (uint32_t)(n - 1 - p)];
-            s_id[b & 1][tid] = id;
-            const float4* src = rec + 3 * (size_t)id;
-            cp_async16(&s_r0[b & 1][tid], src);
-            cp_async16(&s_r1[b & 1][tid], src + 1);
-            cp_async16(&s_r2[b & 1][tid], src + 2);
-        }
-        cp_async_commit();
-    };
-
-    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
-    float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
-    const float ddelx_dx = 0.5 * W;  // backward.cu:486-487
-    const float ddely_dy = 0.5 * H;
-
-    if (rounds > 0) prefetch(0);
-    for (int b = 0; b < rounds; ++b) {
-        // reset this batch's accumulators (nobody reads them until after the barrier below)
-        {
-            float4* z = reinterpret_cast<float4*>(s_acc + tid * ACC_STRIDE);
-            z[0] = z[1] = z[2] = make_float4(0.f, 0.f, 0.f, 0.f);
-            s_touched[tid] = 0;
-        }
-        if (b + 1 < rounds) {
-            prefetch(b + 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-
-        const int cnt = min(BWD_BATCH, n - b * BWD_BATCH);
-        const float4* r0 = s_r0[b & 1];
-        const float4* r1 = s_r1[b & 1];
-        const float4* r2 = s_r2[b & 1];
-        if (warp_max_last > 0) {
-            for (int j0 = 0; j0 < cnt; j0 += 32) {
-                const int jj = j0 + lane;
-                bool hit = false;
-                if (jj < cnt) {
-                    const uint32_t pos = (uint32_t)(n - 1 - (b * BWD_BATCH + jj));
-                    const float4 a = r0[jj];
-                    const float hy = r2[jj].w;
-                    hit = pos < warp_max_last &&
-                          !((a.x + a.w < bx0) || (a.x - a.w > bx1) || (a.y + hy < by0) ||
-                            (a.y - hy > by1));
-                    if (hit) {  // the box overlaps: decide exactly on the ellipse
-                        const float4 co = r1[jj];
-                        hit = !ellipse_misses_rect(a.x, a.y, co.x, co.y, co.z, co.w, bx0, bx1, by0, by1);
-                    }
-                }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int j = j0 + __ffs(m) - 1;
-                    m &= m - 1;
-                    const uint32_t pos = (uint32_t)(n - 1 - (b * BWD_BATCH + j));
-                    float v[12];
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) v[i] = 0.f;
-                    bool active = false;
-                    // backward.cu:512-514: skip Gaussians behind this pixel's last contributor
-                    if (pos < last_contributor) {
-                        const float4 a = r0[j];
-                        const float4 con_o = r1[j];
-                        const float dx = __fsub_rn(a.x, pixf.x);
-                        const float dy = __fsub_rn(a.y, pixf.y);
-                        const float sy = __fmul_rn(__fmul_rn(con_o.z, dy), dy);
-                        const float sq = __fmaf_rn(dx, __fmul_rn(con_o.x, dx), sy);
-                        const float cr = __fmul_rn(__fmul_rn(con_o.y, dx), dy);
-                        const float power = __fmaf_rn(sq, -0.5f, -cr);
-                        if (!(power > 0.0f)) {
-                            const float G = expf(power);
-                            const float alpha = fminf(0.99f, __fmul_rn(con_o.w, G));
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                active = true;
-                                const float4 c = r2[j];
-                                // backward.cu:529-563
-                                // one approximate reciprocal (MUFU.RCP, <= 1 ulp; 1 - alpha is in [0.01, 1]) serves both
-                                // divisions of backward.cu:530,562: two IEEE divisions were 30 of this loop's 187 instructions
-                                const float inv_1ma = rcp_approx(1.f - alpha);
-                                T = T * inv_1ma;
-                                const float dchannel_dcolor = alpha * T;
-                                float dL_dalpha = 0.0f;
-                                accum0 = last_alpha * last_c0 + (1.f - last_alpha) * accum0;
-                                last_c0 = c.x;
-                                dL_dalpha += (c.x - accum0) * dpix0;
-                                v[8] = dchannel_dcolor * dpix0;
-                                accum1 = last_alpha * last_c1 + (1.f - last_alpha) * accum1;
-                                last_c1 = c.y;
-                                dL_dalpha += (c.y - accum1) * dpix1;
-                                v[9] = dchannel_dcolor * dpix1;
-                                accum2 = last_alpha * last_c2 + (1.f - last_alpha) * accum2;
-                                last_c2 = c.z;
-                                dL_dalpha += (c.z - accum2) * dpix2;
-                                v[10] = dchannel_dcolor * dpix2;
-                                v[6] = dchannel_dcolor * ddepth;  // backward.cu:552
-
-                                dL_dalpha *= T;
-                                last_alpha = alpha;
-                                dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
-
-                                // backward.cu:567-583
-                                const float dL_dG = con_o.w * dL_dalpha;
-                                const float gdx = G * dx;
-                                const float gdy = G * dy;
-                                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-                                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                                v[1] = dL_dG * dG_ddely * ddely_dy;
-                                v[2] = -0.5f * gdx * dx * dL_dG;
-                                v[3] = -0.5f * gdx * dy * dL_dG;
-                                v[4] = -0.5f * gdy * dy * dL_dG;
-                                v[5] = G * dL_dalpha;
-                            }
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, active)) {
-                        const float tot = warp_reduce12(v, lane);
-                        const int sub = ((lane >> 1) & 3);  // 2*b2 + b1
-                        const int slot = 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1) + sub;
-                        if (!(lane & 1) && sub < 3 && slot != 7 && slot != 11)
-                            atomicAdd(&s_acc[j * ACC_STRIDE + slot], tot);
-                        if (lane == 0) s_touched[j] = 1u;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // flush: one thread per Gaussian of the batch, three 16-byte vector reductions
-        if (tid < cnt && s_touched[tid]) {
-            const float4* a = reinterpret_cast<const float4*>(s_acc + tid * ACC_STRIDE);
-            float4* dst = grad_rec + 3 * (size_t)s_id[b & 1][tid];
-            atomicAdd(dst + 0, a[0]);
-            atomicAdd(dst + 1, a[1]);
-            atomicAdd(dst + 2, a[2]);
-        }
-        // the next iteration zeroes s_acc and prefetches into the other buffer; the barrier at
-        // the top of the next iteration orders those against this flush only partially, so:
-        __syncthreads();
-    }
-    cp_async_wait<0>();
-}
-
-// Variant: the reduce lanes add straight into the global gradient record (one 4-byte RED per
-// slot and (warp, Gaussian) hit) — no shared accumulator, no flush, one barrier per batch.
-//
-// DET = true (wast3d_set_deterministic, tests): no float atomics at all.  The eight warps of the tile park
-// their reduced partials in shared memory, one thread per instance adds them in warp order and writes the
-// 48-byte sum to inst_grad[position in the point list]; raster_backward_impl then adds every Gaussian's
-// instances in point-list order (det_gather_kernel).  Same arithmetic per pixel, a fixed summation order:
-// the gradients are bit-reproducible from run to run (and agree with the atomic path to fp32 rounding).
-template <int BWD_BATCH, bool DET>
-__global__ void __launch_bounds__(TILE_PIX)
-render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                       const int W, const int H, const float* __restrict__ bg_color,
-                       const float4* __restrict__ rec, const float* __restrict__ sampling_offsets,
-                       const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
-                       const float* __restrict__ dL_dpixels, const float* __restrict__ dL_ddepths,
                        float4* __restrict__ grad_rec, float4* __restrict__ inst_grad) {
-    __shared__ float4 s_r0[2][BWD_BATCH];
-    __shared__ float4 s_r1[2][BWD_BATCH];
-    __shared__ float4 s_r2[2][BWD_BATCH];
-    __shared__ uint32_t s_id[2][BWD_BATCH];
-    __shared__ uint32_t s_warp_max[TILE_PIX / 32];
-    __shared__ __align__(16) float s_part[DET ? TILE_PIX / 32 : 1][DET ? BWD_BATCH : 1][12];
+    extern __shared__ __align__(16) uint8_t k7_smem_raw[];
+    K7Smem<BATCH, ROWS, DET>& sm = *reinterpret_cast<K7Smem<BATCH, ROWS, DET>*>(k7_smem_raw);
 
     float* grad_f = reinterpret_cast<float*>(grad_rec);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t px = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
-    const uint32_t py = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
-    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
-    const uint32_t pix_id = (uint32_t)W * py + px;
+    const uint32_t pxi = blockIdx.x * TILE_X + (warp & 1) * 8 + (lane & 7);
+    const uint32_t pyi = blockIdx.y * TILE_Y + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * pyi + pxi;
 
-    float2 pixf = make_float2((float)px, (float)py);
+    ReplayPixel px;
+    px.pixf = make_float2((float)pxi, (float)pyi);
     if (inside && sampling_offsets != nullptr) {
         const float2 o = *reinterpret_cast<const float2*>(sampling_offsets + 2 * (size_t)pix_id);
-        pixf.x = (float)px + o.x;
-        pixf.y = (float)py + o.y;
+        px.pixf.x = (float)pxi + o.x;
+        px.pixf.y = (float)pyi + o.y;
     }
     const float inf = __int_as_float(0x7f800000);
-    float bx0 = inside ? pixf.x : inf, bx1 = inside ? pixf.x : -inf;
-    float by0 = inside ? pixf.y : inf, by1 = inside ? pixf.y : -inf;
+    float bx0 = inside ? px.pixf.x : inf, bx1 = inside ? px.pixf.x : -inf;
+    float by0 = inside ? px.pixf.y : inf, by1 = inside ? px.pixf.y : -inf;
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
         bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
@@ -358,57 +227,85 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
     const uint2 range = ranges[blockIdx.y * gridDim.x + blockIdx.x];
 
     // backward.cu:463-478
-    const float T_final = inside ? final_Ts[pix_id] : 0.f;
-    float T = T_final;
-    const uint32_t last_contributor = inside ? n_contrib[pix_id] : 0u;
+    px.T_final = inside ? final_Ts[pix_id] : 0.f;
+    px.T = px.T_final;
+    px.last_contributor = inside ? n_contrib[pix_id] : 0u;
     const size_t HW = (size_t)H * W;
-    float dpix0 = 0.f, dpix1 = 0.f, dpix2 = 0.f, ddepth = 0.f;
+    px.dpix0 = px.dpix1 = px.dpix2 = px.ddepth = 0.f;
     if (inside) {
-        dpix0 = dL_dpixels[pix_id];
-        dpix1 = dL_dpixels[HW + pix_id];
-        dpix2 = dL_dpixels[2 * HW + pix_id];
-        ddepth = dL_ddepths ? dL_ddepths[pix_id] : 0.f;
+        px.dpix0 = dL_dpixels[pix_id];
+        px.dpix1 = dL_dpixels[HW + pix_id];
+        px.dpix2 = dL_dpixels[2 * HW + pix_id];
+        px.ddepth = dL_ddepths ? dL_ddepths[pix_id] : 0.f;
     }
     // backward.cu:560-563 (pixel constant)
-    float bg_dot_dpixel = 0.f;
-    bg_dot_dpixel += bg_color[0] * dpix0;
-    bg_dot_dpixel += bg_color[1] * dpix1;
-    bg_dot_dpixel += bg_color[2] * dpix2;
+    px.bg_dot_dpixel = 0.f;
+    px.bg_dot_dpixel += bg_color[0] * px.dpix0;
+    px.bg_dot_dpixel += bg_color[1] * px.dpix1;
+    px.bg_dot_dpixel += bg_color[2] * px.dpix2;
+    px.accum0 = px.accum1 = px.accum2 = 0.f;
+    px.last_alpha = px.last_c0 = px.last_c1 = px.last_c2 = 0.f;
 
     // Nothing behind the tile's deepest last contributor can receive gradient.
-    const uint32_t warp_max_last = __reduce_max_sync(0xffffffffu, last_contributor);
-    if (lane == 0) s_warp_max[warp] = warp_max_last;
+    const uint32_t warp_max_last = __reduce_max_sync(0xffffffffu, px.last_contributor);
+    if (lane == 0) sm.warp_max[warp] = warp_max_last;
     __syncthreads();
     uint32_t n_eff = 0;
 #pragma unroll
-    for (int w = 0; w < TILE_PIX / 32; ++w) n_eff = max(n_eff, s_warp_max[w]);
+    for (int w = 0; w < TILE_PIX / 32; ++w) n_eff = max(n_eff, sm.warp_max[w]);
     n_eff = min(n_eff, range.y - range.x);
     const int n = (int)n_eff;
-    const int rounds = (n + BWD_BATCH - 1) / BWD_BATCH;
+    const int rounds = (n + BATCH - 1) / BATCH;
 
     auto prefetch = [&](int b) {
-        const int p = b * BWD_BATCH + tid;
-        if (tid < BWD_BATCH && p < n) {
-            const uint32_t id = point_list[range.x + (uint32_t)(n - 1 - p)];
-            s_id[b & 1][tid] = id;
-            const float4* src = rec + 3 * (size_t)id;
-            cp_async16(&s_r0[b & 1][tid], src);
-            cp_async16(&s_r1[b & 1][tid], src + 1);
-            cp_async16(&s_r2[b & 1][tid], src + 2);
+#pragma unroll
+        for (int q = tid; q < BATCH; q += TILE_PIX) {
+            const int p = b * BATCH + q;
+            if (p < n) {
+                const uint32_t id = point_list[range.x + (uint32_t)(n - 1 - p)];
+                sm.id[b & 1][q] = id;
+                const float4* src = rec + 3 * (size_t)id;
+                cp_async16(&sm.r0[b & 1][q], src);
+                cp_async16(&sm.r1[b & 1][q], src + 1);
+                cp_async16(&sm.r2[b & 1][q], src + 2);
+            }
         }
         cp_async_commit();
     };
 
-    float accum0 = 0.f, accum1 = 0.f, accum2 = 0.f;
-    float last_alpha = 0.f, last_c0 = 0.f, last_c1 = 0.f, last_c2 = 0.f;
-    const float ddelx_dx = 0.5 * W;  // backward.cu:486-487
-    const float ddely_dy = 0.5 * H;
+    // transposed reduction state: hits parked in this warp's rows, and where their sums go
+    int parked = 0;
+    uint32_t dst0 = 0, dst1 = 0, dst2 = 0, dst3 = 0;   // ROWS <= 4
+    float* red_w = &sm.red[ROWS > 0 ? warp : 0][0][0];
+    auto flush = [&]() {
+        if (ROWS == 0 || parked == 0) return;
+        __syncwarp();
+        if (lane < 10 * parked) {
+            const float4* row = reinterpret_cast<const float4*>(red_w + lane * RED_STRIDE);
+            float4 q[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] = row[k];
+            float sum = 0.f;
+            {   // fixed order: pairwise over the eight 16-byte pieces
+                float p4[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p4[k] = (q[k].x + q[k].y) + (q[k].z + q[k].w);
+                sum = ((p4[0] + p4[1]) + (p4[2] + p4[3])) + ((p4[4] + p4[5]) + (p4[6] + p4[7]));
+            }
+            const int h = lane / 10, i = lane - 10 * h;
+            const uint32_t dst = h == 0 ? dst0 : h == 1 ? dst1 : h == 2 ? dst2 : dst3;
+            if (DET) sm.part[DET ? warp : 0][DET ? dst : 0][record_index(i)] = sum;   // dst = index in the batch
+            else atomicAdd(grad_f + 12 * (size_t)dst + record_index(i), sum);         // dst = Gaussian id
+        }
+        __syncwarp();
+        parked = 0;
+    };
 
     if (rounds > 0) prefetch(0);
     for (int b = 0; b < rounds; ++b) {
         if (DET) {   // this warp's partials of the batch start at zero (a warp that skips a Gaussian adds 0)
-            float* z = &s_part[warp][0][0];
-            for (int q = lane; q < BWD_BATCH * 12; q += 32) z[q] = 0.f;
+            float* z = &sm.part[DET ? warp : 0][0][0];
+            for (int q = lane; q < BATCH * 12; q += 32) z[q] = 0.f;
         }
         // one barrier per batch: batch b has landed, and every warp is done with batch b-1 whose
         // buffer the prefetch of b+1 overwrites
@@ -416,16 +313,16 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
         __syncthreads();
         if (b + 1 < rounds) prefetch(b + 1);
 
-        const int cnt = min(BWD_BATCH, n - b * BWD_BATCH);
-        const float4* r0 = s_r0[b & 1];
-        const float4* r1 = s_r1[b & 1];
-        const float4* r2 = s_r2[b & 1];
+        const int cnt = min(BATCH, n - b * BATCH);
+        const float4* r0 = sm.r0[b & 1];
+        const float4* r1 = sm.r1[b & 1];
+        const float4* r2 = sm.r2[b & 1];
         if (warp_max_last > 0) {
             for (int j0 = 0; j0 < cnt; j0 += 32) {
                 const int jj = j0 + lane;
                 bool hit = false;
                 if (jj < cnt) {
-                    const uint32_t pos = (uint32_t)(n - 1 - (b * BWD_BATCH + jj));
+                    const uint32_t pos = (uint32_t)(n - 1 - (b * BATCH + jj));
                     const float4 a = r0[jj];
                     const float hy = r2[jj].w;
                     hit = pos < warp_max_last &&
@@ -440,99 +337,55 @@ render_backward_direct_kernel(const uint2* __restrict__ ranges, const uint32_t* 
                 while (m) {
                     const int j = j0 + __ffs(m) - 1;
                     m &= m - 1;
-                    const uint32_t pos = (uint32_t)(n - 1 - (b * BWD_BATCH + j));
-                    float v[12];
+                    const uint32_t pos = (uint32_t)(n - 1 - (b * BATCH + j));
+                    float v[10];
+                    const bool active = replay_pair(px, pos, r0[j], r1[j], r2 + j, v);
+                    if (!__any_sync(0xffffffffu, active)) continue;
+                    if (ROWS > 0) {
+                        float* rowp = red_w + parked * (10 * RED_STRIDE) + lane;
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) v[i] = 0.f;
-                    bool active = false;
-                    // backward.cu:512-514: skip Gaussians behind this pixel's last contributor
-                    if (pos < last_contributor) {
-                        const float4 a = r0[j];
-                        const float4 con_o = r1[j];
-                        const float dx = __fsub_rn(a.x, pixf.x);
-                        const float dy = __fsub_rn(a.y, pixf.y);
-                        const float sy = __fmul_rn(__fmul_rn(con_o.z, dy), dy);
-                        const float sq = __fmaf_rn(dx, __fmul_rn(con_o.x, dx), sy);
-                        const float cr = __fmul_rn(__fmul_rn(con_o.y, dx), dy);
-                        const float power = __fmaf_rn(sq, -0.5f, -cr);
-                        if (!(power > 0.0f)) {
-                            const float G = expf(power);
-                            const float alpha = fminf(0.99f, __fmul_rn(con_o.w, G));
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                active = true;
-                                const float4 c = r2[j];
-                                // backward.cu:529-563
-                                // one approximate reciprocal (MUFU.RCP, <= 1 ulp; 1 - alpha is in [0.01, 1]) serves both
-                                // divisions of backward.cu:530,562: two IEEE divisions were 30 of this loop's 187 instructions
-                                const float inv_1ma = rcp_approx(1.f - alpha);
-                                T = T * inv_1ma;
-                                const float dchannel_dcolor = alpha * T;
-                                float dL_dalpha = 0.0f;
-                                accum0 = last_alpha * last_c0 + (1.f - last_alpha) * accum0;
-                                last_c0 = c.x;
-                                dL_dalpha += (c.x - accum0) * dpix0;
-                                v[8] = dchannel_dcolor * dpix0;
-                                accum1 = last_alpha * last_c1 + (1.f - last_alpha) * accum1;
-                                last_c1 = c.y;
-                                dL_dalpha += (c.y - accum1) * dpix1;
-                                v[9] = dchannel_dcolor * dpix1;
-                                accum2 = last_alpha * last_c2 + (1.f - last_alpha) * accum2;
-                                last_c2 = c.z;
-                                dL_dalpha += (c.z - accum2) * dpix2;
-                                v[10] = dchannel_dcolor * dpix2;
-                                v[6] = dchannel_dcolor * ddepth;  // backward.cu:552
-
-                                dL_dalpha *= T;
-                                last_alpha = alpha;
-                                dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
-
-                                // backward.cu:567-583
-                                const float dL_dG = con_o.w * dL_dalpha;
-                                const float gdx = G * dx;
-                                const float gdy = G * dy;
-                                const float dG_ddelx = -gdx * con_o.x - gdy * con_o.y;
-                                const float dG_ddely = -gdy * con_o.z - gdx * con_o.y;
-                                v[0] = dL_dG * dG_ddelx * ddelx_dx;
-                                v[1] = dL_dG * dG_ddely * ddely_dy;
-                                v[2] = -0.5f * gdx * dx * dL_dG;
-                                v[3] = -0.5f * gdx * dy * dL_dG;
-                                v[4] = -0.5f * gdy * dy * dL_dG;
-                                v[5] = G * dL_dalpha;
-                            }
-                        }
-                    }
-                    if (__any_sync(0xffffffffu, active)) {
-                        const float tot = warp_reduce12(v, lane);
+                        for (int i = 0; i < 10; ++i) rowp[i * RED_STRIDE] = active ? v[i] : 0.f;
+                        const uint32_t dst = DET ? (uint32_t)j : sm.id[b & 1][j];
+                        if (parked == 0) dst0 = dst; else if (parked == 1) dst1 = dst; else if (parked == 2) dst2 = dst; else dst3 = dst;
+                        if (++parked == ROWS) flush();
+                    } else {
+                        float v12[12];
+#pragma unroll
+                        for (int i = 0; i < 10; ++i) v12[record_index(i)] = active ? v[i] : 0.f;
+                        v12[7] = v12[11] = 0.f;
+                        const float tot = warp_reduce12(v12, lane);
                         const int sub = ((lane >> 1) & 3);  // 2*b2 + b1
                         const int slot = 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1) + sub;
                         if (!(lane & 1) && sub < 3 && slot != 7 && slot != 11) {
-                            if (DET) s_part[warp][j][slot] = tot;
-                            else atomicAdd(grad_f + 12 * (size_t)s_id[b & 1][j] + slot, tot);
+                            if (DET) sm.part[DET ? warp : 0][DET ? j : 0][slot] = tot;
+                            else atomicAdd(grad_f + 12 * (size_t)sm.id[b & 1][j] + slot, tot);
                         }
                     }
                 }
             }
         }
         if (DET) {
+            flush();   // parked sums refer to positions in THIS batch
             __syncthreads();
             if (tid < cnt) {
                 float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
 #pragma unroll
                 for (int w = 0; w < TILE_PIX / 32; ++w) {   // fixed order
-                    const float4* q = reinterpret_cast<const float4*>(&s_part[w][tid][0]);
+                    const float4* q = reinterpret_cast<const float4*>(&sm.part[DET ? w : 0][DET ? tid : 0][0]);
                     const float4 x = q[0], y = q[1], z = q[2];
                     a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
                     a1.x += y.x; a1.y += y.y; a1.z += y.z; a1.w += y.w;
                     a2.x += z.x; a2.y += z.y; a2.z += z.z; a2.w += z.w;
                 }
-                const size_t pos = (size_t)range.x + (size_t)(n - 1 - (b * BWD_BATCH + tid));
+                const size_t pos = (size_t)range.x + (size_t)(n - 1 - (b * BATCH + tid));
                 inst_grad[3 * pos + 0] = a0;
                 inst_grad[3 * pos + 1] = a1;
                 inst_grad[3 * pos + 2] = a2;
             }
-            __syncthreads();   // before the next batch zeroes s_part
+            __syncthreads();   // before the next batch zeroes the partials
         }
     }
+    flush();   // Gaussian ids were copied when the hits were parked: sums may outlive their batch
     cp_async_wait<0>();
 }
 
@@ -559,7 +412,6 @@ det_gather_kernel(int P, const uint32_t* __restrict__ tiles_touched, const uint3
     grad_rec[3 * (size_t)id + 1] = a1;
     grad_rec[3 * (size_t)id + 2] = a2;
 }
-
 
 
 // ------------------------------------------------------------------ K8 + K9 ---------------
@@ -665,6 +517,7 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                          const float* __restrict__ cov3D_precomp, const float* __restrict__ view,
                          const float* __restrict__ proj, const float* __restrict__ campos,
                          const float h_x, const float h_y, const float tan_fovx, const float tan_fovy,
+                         const float half_w, const float half_h,
                          const float4* __restrict__ grad_rec, float* __restrict__ dL_dmean2D,
                          float* __restrict__ dL_dconic_out, float* __restrict__ dL_dopacity,
                          float* __restrict__ dL_dcolor, float* __restrict__ dL_dmean3D,
@@ -709,6 +562,17 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         g0 = grad_rec[3 * (size_t)idx + 0];
         g1 = grad_rec[3 * (size_t)idx + 1];
         g2 = grad_rec[3 * (size_t)idx + 2];
+        {
+            // K7 accumulated moments (see the record layout at the top): backward.cu:567-583 once per Gaussian.
+            // half_w, half_h = ddelx_dx, ddely_dy (backward.cu:486-487)
+            const float4 co = rec[3 * (size_t)idx + 1];   // conic (A, B, C), opacity
+            const float Mx = g0.x, My = g0.y, Mxx = g0.z, Mxy = g0.w, Myy = g1.x;
+            g0.x = -(co.w * half_w) * (co.x * Mx + co.y * My);
+            g0.y = -(co.w * half_h) * (co.z * My + co.y * Mx);
+            g0.z = -0.5f * co.w * Mxx;
+            g0.w = -0.5f * co.w * Mxy;
+            g1.x = -0.5f * co.w * Myy;
+        }
         mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
 
         float cov6[6];
@@ -1033,6 +897,17 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
 
 using namespace w3d;
 
+template <int BATCH, int ROWS, bool DET, int MINB, typename... Args>
+static cudaError_t launch_k7(dim3 grid, cudaStream_t s, Args... args) {
+    auto kern = render_backward_kernel<BATCH, ROWS, DET, MINB>;
+    const size_t smem = sizeof(K7Smem<BATCH, ROWS, DET>);
+    // per device and cheap: no process-wide "already set" flag (several devices per process)
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, TILE_PIX, smem, s>>>(args...);
+    return cudaGetLastError();
+}
+
 static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendered, const int* radii,
                                 void* geom_buffer, void* binning_buffer, void* img_buffer,
                                 const float* dL_dpix, const float* dL_ddepth, float* dL_dmean2D,
@@ -1060,7 +935,12 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
     if (num_rendered > 0 && deterministic_mode() != 0) {
         // test mode: fixed summation order, no float atomics (see render_backward_direct_kernel<.., true>)
         ProfScope ps(PS_RENDER_BWD, s);
-        const size_t R = (size_t)num_rendered;
+        // the buffers below are sized by the ACTUAL instance count; after a graph-safe forward `num_rendered` is only
+        // the capacity the binning buffer was carved for, so read the count (a test mode may synchronise)
+        uint32_t r_dev = 0;
+        W3D_CUDA_TRY(cudaMemcpyAsync(&r_dev, g.totals, sizeof(r_dev), cudaMemcpyDeviceToHost, s));
+        W3D_CUDA_TRY(cudaStreamSynchronize(s));
+        const size_t R = r_dev < (uint32_t)num_rendered ? r_dev : (size_t)num_rendered;
         const uint32_t* plist = point_list_ptr(bn, num_tiles);
         const size_t hist_words = rs_hist_words(R), hist_scr = scan_scratch_words(hist_words);
         Carver sizer(nullptr);
@@ -1081,9 +961,11 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
         int st = WAST3D_OK;
         do {
             if (cudaMemsetAsync(inst_grad, 0, 3 * R * sizeof(float4), s) != cudaSuccess) { st = WAST3D_ERR_CUDA; break; }
-            render_backward_direct_kernel<64, true><<<grid, TILE_PIX, 0, s>>>(
-                im.ranges, plist, W, H, prm->background, g.rec, prm->sampling_offsets, im.final_T, im.n_contrib,
-                dL_dpix, dL_ddepth, g.grad_rec, inst_grad);
+            if (launch_k7<64, 3, true, 1>(grid, s, im.ranges, plist, W, H, prm->background, g.rec, prm->sampling_offsets,
+                                       im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec, inst_grad) != cudaSuccess) {
+                st = WAST3D_ERR_CUDA;
+                break;
+            }
             count_launch();
             if (cudaGetLastError() != cudaSuccess) { st = WAST3D_ERR_CUDA; break; }
             // instance positions grouped by Gaussian id, ascending inside a group (stable LSD sort on the id)
@@ -1111,15 +993,23 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
         if (debug) W3D_CUDA_TRY(cudaStreamSynchronize(s));
     } else if (num_rendered > 0) {
         ProfScope ps(PS_RENDER_BWD, s);
-        static const int variant = getenv("WAST3D_K7_VARIANT") ? atoi(getenv("WAST3D_K7_VARIANT")) : 1;
-        if (variant == 1)
-            render_backward_direct_kernel<BWD_BATCH, false><<<grid, TILE_PIX, 0, s>>>(
-                im.ranges, point_list_ptr(bn, num_tiles), W, H, prm->background, g.rec,
-                prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec, nullptr);
-        else
-            render_backward_kernel<<<grid, TILE_PIX, 0, s>>>(
-                im.ranges, point_list_ptr(bn, num_tiles), W, H, prm->background, g.rec,
-                prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec);
+        // A/B switches (measurements): WAST3D_K7_ROWS = hits parked per transposed reduction (0 = shuffle butterfly),
+        // WAST3D_K7_BATCH = records staged per barrier, WAST3D_K7_MINB = resident CTAs per SM the registers are cut for
+        static const int rows = getenv("WAST3D_K7_ROWS") ? atoi(getenv("WAST3D_K7_ROWS")) : 0;
+        static const int batch = getenv("WAST3D_K7_BATCH") ? atoi(getenv("WAST3D_K7_BATCH")) : 256;
+        static const int minb = getenv("WAST3D_K7_MINB") ? atoi(getenv("WAST3D_K7_MINB")) : 4;
+        const uint32_t* plist = point_list_ptr(bn, num_tiles);
+#define W3D_K7(B, R, M)                                                                                         \
+    launch_k7<B, R, false, M>(grid, s, im.ranges, plist, W, H, prm->background, g.rec, prm->sampling_offsets,  \
+                              im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec, nullptr)
+        cudaError_t e;
+        if (rows == 2) e = batch == 512 ? W3D_K7(512, 2, 4) : W3D_K7(256, 2, 4);
+        else if (rows == 3) e = W3D_K7(256, 3, 3);
+        else if (batch == 512) e = minb == 5 ? W3D_K7(512, 0, 5) : W3D_K7(512, 0, 4);
+        else if (batch == 128) e = minb == 5 ? W3D_K7(128, 0, 5) : W3D_K7(128, 0, 4);
+        else e = minb == 5 ? W3D_K7(256, 0, 5) : minb == 6 ? W3D_K7(256, 0, 6) : W3D_K7(256, 0, 4);
+#undef W3D_K7
+        W3D_CUDA_TRY(e);
         W3D_AFTER_LAUNCH(s, debug);
     }
     ProfScope ps_gb(PS_GAUSS_BWD, s);
@@ -1133,7 +1023,8 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
     gb<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, radii, prm->shs, prm->shs_rest, g.rec, g.clamped, prm->scales,
         prm->rotations, prm->scale_modifier, prm->cov3D_precomp, prm->viewmatrix, prm->projmatrix,
-        prm->campos, focal_x, focal_y, prm->tan_fovx, prm->tan_fovy, g.grad_rec, dL_dmean2D, dL_dconic,
+        prm->campos, focal_x, focal_y, prm->tan_fovx, prm->tan_fovy, (float)(0.5 * W), (float)(0.5 * H), g.grad_rec,
+        dL_dmean2D, dL_dconic,
         dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dsh_rest, dL_dscale, dL_drot,
         dL_dcamViewDepth, af);
     W3D_AFTER_LAUNCH(s, debug);

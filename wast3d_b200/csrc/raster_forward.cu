@@ -113,7 +113,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   const float focal_x, const float focal_y, const dim3 grid,
                   const bool prefiltered, int* __restrict__ radii, float4* __restrict__ rec,
                   uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
-                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ flags,
+                  uint8_t* __restrict__ clamped, uint2* __restrict__ rect_out, uint32_t* __restrict__ flags,
                   const uint32_t* __restrict__ sample_bound_words, const bool cut_tiles) {
     __shared__ __align__(16) float s_sh[PRE_WARPS][32 * SH_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -124,6 +124,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     bool visible = false;
     int my_radius_i = 0;
     uint32_t n_tiles = 0;
+    uint2 my_rect = make_uint2(0u, 0u);
     float3 p_orig = make_float3(0.f, 0.f, 0.f);
     float3 p_view = make_float3(0.f, 0.f, 0.f);
     float2 point_image = make_float2(0.f, 0.f);
@@ -131,8 +132,13 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     float opac = 0.f;
     float2 ext = make_float2(0.f, 0.f);
 
+    // means3D / scales: [P,3] AoS read with coalesced 16-byte loads (load_rows3)
+    __shared__ __align__(16) float s_v3[PRE_WARPS][96];
+    const int rows_valid_w = max(0, min(32, P - warp_first));
+    p_orig = load_rows3(means3D, warp_first, rows_valid_w, lane, s_v3[warp]);
+    float3 sc_in = make_float3(0.f, 0.f, 0.f);
+    if (cov3D_precomp == nullptr) sc_in = load_rows3(scales, warp_first, rows_valid_w, lane, s_v3[warp]);
     if (live) {
-        p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
         // in_frustum (auxiliary.h:139-164): near plane only
         p_view = xform_point_4x3(p_orig, viewmatrix);
         if (p_view.z <= 0.2f) {
@@ -147,7 +153,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
 #pragma unroll
                 for (int k = 0; k < 6; ++k) cov6[k] = cov3D_precomp[6 * idx + k];
             } else {
-                float3 sc = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+                float3 sc = sc_in;
                 float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
                 if (RAW) {
                     sc = act_exp3(sc);
@@ -181,6 +187,10 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                                       rect_min, rect_max, grid);
                         n_tiles = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
                     }
+                    // the rectangle the instance emitter expands (8 bytes instead of re-deriving it from the record)
+                    if (n_tiles != 0)
+                        my_rect = make_uint2(rect_min.x | (rect_min.y << 16),
+                                             (rect_max.x - rect_min.x) | ((rect_max.y - rect_min.y) << 16));
                 }
             }
         }
@@ -222,6 +232,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     if (!live) return;
     radii[idx] = my_radius_i;
     tiles_touched[idx] = visible ? n_tiles : 0u;
+    rect_out[idx] = my_rect;
     clamped[idx] = (uint8_t)(clamp_bits | (visible ? 8u : 0u));  // bit 3: render record written
     depth_key[idx] = visible ? __float_as_uint(p_view.z) : CULLED_KEY;
     if (visible) {
@@ -329,12 +340,14 @@ constexpr int EMIT_MAX_SMEM_TILES = 12288;  // 48 KB of counters; larger grids c
 
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
-                      const uint32_t* __restrict__ tiles_touched, const int* __restrict__ radii,
-                      const float4* __restrict__ rec, uint32_t* __restrict__ keys,
+                      const uint2* __restrict__ rect, uint32_t* __restrict__ keys,
                       uint32_t* __restrict__ vals, uint32_t* __restrict__ tile_count, const dim3 grid,
-                      const int num_tiles, const bool smem_hist,
-                      const uint32_t* __restrict__ sample_bound_words, const bool cut_tiles) {
+                      const int num_tiles, const bool smem_hist, const uint32_t capacity,
+                      uint32_t* __restrict__ totals) {
     extern __shared__ uint32_t s_count[];
+    // graph-safe forward: the pair arrays hold `capacity` instances; a view that needs more raises totals[3]
+    // (nothing is written out of bounds; the image of that call is incomplete and the host layer reports it)
+    if (blockIdx.x == 0 && threadIdx.x == 0 && totals[0] > capacity) totals[3] = 1u;
     if (smem_hist) {
         for (int t = threadIdx.x; t < num_tiles; t += EMIT_THREADS) s_count[t] = 0;
         __syncthreads();
@@ -348,19 +361,12 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
         uint32_t id = 0, n = 0, off = 0xFFFFFFFFu, xy0 = 0, w = 1;
         if (k < P) {
             id = order[k];
-            n = tiles_touched[id];
             off = offsets[k];
-            if (n != 0) {
-                const float4 r0 = rec[3 * (size_t)id];
-                uint2 rect_min, rect_max;
-                if (cut_tiles)  // the same rectangle K1 counted (same inputs, same arithmetic)
-                    tile_rect_cut(make_float2(r0.x, r0.y), radii[id], r0.w, rec[3 * (size_t)id + 2].w,
-                                  load_sample_bounds(sample_bound_words), rect_min, rect_max, grid);
-                else
-                    tile_rect(make_float2(r0.x, r0.y), radii[id], rect_min, rect_max, grid);
-                xy0 = rect_min.x | (rect_min.y << 16);
-                w = rect_max.x - rect_min.x;
-            }
+            const uint2 rc = rect[id];   // the rectangle K1 counted: one 8-byte gather per Gaussian
+            xy0 = rc.x;
+            w = rc.y & 0xFFFFu;
+            n = w * (rc.y >> 16);
+            if (n == 0) w = 1;
         }
         const uint32_t begin = __shfl_sync(0xffffffffu, off, 0);
         const uint32_t end = __reduce_max_sync(0xffffffffu, k < P ? off + n : 0u);
@@ -377,7 +383,7 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
             const uint32_t src_xy0 = __shfl_sync(0xffffffffu, xy0, l);
             const uint32_t src_w = __shfl_sync(0xffffffffu, w, l);
             const uint32_t src_id = __shfl_sync(0xffffffffu, id, l);
-            if (p < end) {
+            if (p < end && p < capacity) {
                 const uint32_t t = p - o;
                 const uint32_t ty = t / src_w, tx = t - ty * src_w;
                 const uint32_t tile = ((src_xy0 >> 16) + ty) * grid.x + (src_xy0 & 0xFFFFu) + tx;
@@ -449,6 +455,10 @@ tile_digit_hist_kernel(int num_tiles, const uint32_t* __restrict__ tile_count, i
 
 __global__ void tile_copy_flags_kernel(const uint32_t* a, const uint32_t* b, uint32_t* out) {
     if (threadIdx.x == 0) *out = (a ? *a : 0u) | (b ? *b : 0u);
+}
+// status_dev[0..3] = {num_rendered, prefiltered violated, look-back time-out, capacity overflow}
+__global__ void copy_status_kernel(const uint32_t* __restrict__ totals, uint32_t* __restrict__ status) {
+    if (threadIdx.x < 4) status[threadIdx.x] = totals[threadIdx.x];
 }
 
 // ------------------------------------------------------------------ K6 -------------------
@@ -659,16 +669,21 @@ int validate_params(const wast3d_raster_params* p, bool forward) {
 
 using namespace w3d;
 
-extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_alloc_fn geom_alloc,
-                                     void* geom_user, wast3d_alloc_fn binning_alloc,
-                                     void* binning_user, wast3d_alloc_fn img_alloc, void* img_user,
-                                     float* out_color, float* out_depth, int* radii,
-                                     int* num_rendered_host, void* stream_v) {
+// capacity < 0: the reference's protocol (one blocking read of num_rendered sizes the binning buffer).
+// capacity >= 1: graph-safe — nothing is read back; the binning buffer holds `capacity` instances, the R-dependent
+// kernels take the instance count from device memory, status_dev receives {R, flags, time-out, overflow}.
+static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn geom_alloc,
+                               void* geom_user, wast3d_alloc_fn binning_alloc,
+                               void* binning_user, wast3d_alloc_fn img_alloc, void* img_user,
+                               float* out_color, float* out_depth, int* radii,
+                               int* num_rendered_host, long long capacity, uint32_t* status_dev, void* stream_v) {
     cudaStream_t s = (cudaStream_t)stream_v;
     int st = validate_params(prm, true);
     if (st != WAST3D_OK) return st;
     if (!geom_alloc || !binning_alloc || !img_alloc || !out_color || !out_depth || !num_rendered_host)
         return WAST3D_ERR_INVALID_ARGUMENT;
+    const bool async = capacity >= 0;
+    if (async && (capacity < 1 || capacity > 0x7FFFFFFFll)) return WAST3D_ERR_INVALID_ARGUMENT;
     const int P = prm->P, W = prm->width, H = prm->height;
     const bool debug = prm->debug != 0;
     const size_t N = (size_t)W * H;
@@ -677,6 +692,7 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         // rasterize_points.cu:69-70,83: outputs stay at their zero fill, buffers stay empty
         W3D_CUDA_TRY(cudaMemsetAsync(out_color, 0, 3 * N * sizeof(float), s));
         W3D_CUDA_TRY(cudaMemsetAsync(out_depth, 0, N * sizeof(float), s));
+        if (async && status_dev) W3D_CUDA_TRY(cudaMemsetAsync(status_dev, 0, 4 * sizeof(uint32_t), s));
         return WAST3D_OK;
     }
     const dim3 grid((W + TILE_X - 1) / TILE_X, (H + TILE_Y - 1) / TILE_Y, 1);
@@ -713,7 +729,7 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         P, prm->D, prm->M, prm->means3D, prm->scales, prm->scale_modifier, prm->rotations,
         prm->opacities, prm->shs, prm->shs_rest, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
         prm->projmatrix, prm->campos, W, H, prm->tan_fovx, prm->tan_fovy, focal_x, focal_y, grid,
-        prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.totals + 1,
+        prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.rect, g.totals + 1,
         sample_bound_words, cut_tiles);
     W3D_AFTER_LAUNCH(s, debug);
     }
@@ -757,18 +773,24 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
     }
     }
 
-    // the one blocking read the reference also has (rasterizer_impl.cu:283)
-    uint32_t host_totals[3] = {0, 0, 0};
-    W3D_CUDA_TRY(cudaMemcpyAsync(host_totals, g.totals, sizeof(host_totals), cudaMemcpyDeviceToHost, s));
-    W3D_CUDA_TRY(cudaStreamSynchronize(s));
-    if (host_totals[1] & 1u) return WAST3D_ERR_INVALID_ARGUMENT;  // prefiltered violated
-    if (host_totals[2]) {
-        set_last_cuda_error(cudaErrorLaunchTimeout, __FILE__, __LINE__);
-        return WAST3D_ERR_CUDA;
+    uint32_t R;   // instances the binning buffer is carved for (== num_rendered in the synchronous protocol)
+    if (!async) {
+        // the one blocking read the reference also has (rasterizer_impl.cu:283)
+        uint32_t host_totals[3] = {0, 0, 0};
+        W3D_CUDA_TRY(cudaMemcpyAsync(host_totals, g.totals, sizeof(host_totals), cudaMemcpyDeviceToHost, s));
+        W3D_CUDA_TRY(cudaStreamSynchronize(s));
+        if (host_totals[1] & 1u) return WAST3D_ERR_INVALID_ARGUMENT;  // prefiltered violated
+        if (host_totals[2]) {
+            set_last_cuda_error(cudaErrorLaunchTimeout, __FILE__, __LINE__);
+            return WAST3D_ERR_CUDA;
+        }
+        if (host_totals[0] > 0x7FFFFFFFu) return WAST3D_ERR_OVERFLOW;
+        R = host_totals[0];
+    } else {
+        R = (uint32_t)capacity;
     }
-    if (host_totals[0] > 0x7FFFFFFFu) return WAST3D_ERR_OVERFLOW;
-    const uint32_t R = host_totals[0];
     *num_rendered_host = (int)R;
+    const uint32_t* n_dev = async ? g.totals : nullptr;   // device-side instance count for the R-sized kernels
 
     size_t bin_bytes;
     BinningState::carve(nullptr, R, &bin_bytes);
@@ -787,16 +809,16 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         const int n_chunks = (P + 31) / 32;
         int blocks = 148 * 4;
         if (blocks > (n_chunks + 7) / 8) blocks = (n_chunks + 7) / 8;
-        emit_instances_kernel<<<blocks, EMIT_THREADS, smem, s>>>(P, g.order_a, g.offsets, g.tiles_touched, radii,
-                                                               g.rec, bn.keys_a, bn.vals_a, im.tile_count, grid,
-                                                               (int)num_tiles, smem_hist, sample_bound_words, cut_tiles);
+        emit_instances_kernel<<<blocks, EMIT_THREADS, smem, s>>>(P, g.order_a, g.offsets, g.rect, bn.keys_a, bn.vals_a,
+                                                               im.tile_count, grid, (int)num_tiles, smem_hist, R, g.totals);
         W3D_AFTER_LAUNCH(s, debug);
         }
         ProfScope* pts = new ProfScope(PS_TILE_SORT, s);
         int bpp;
         const int passes = tile_sort_passes(num_tiles, &bpp);
         if (passes > TILE_SORT_MAX_PASSES) { delete pts; return WAST3D_ERR_OVERFLOW; }
-        if (sort_mode(STAGE_TILE) == 1) {
+        const bool tile_lookback = sort_mode(STAGE_TILE) == 1 && !async;   // look-back passes need the host-side count
+        if (tile_lookback) {
             st = onesweep_prepare(bn.sort_ws, R, passes, s);
             if (st) { delete pts; return st; }
             // the per-pass global digit histograms follow from the per-tile counts: no read of the keys
@@ -807,12 +829,12 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
         uint32_t *kin = bn.keys_a, *vin = bn.vals_a, *kout = bn.keys_b, *vout = bn.vals_b;
         for (int p = 0; p < passes; ++p) {
             // the last pass does not need to write the sorted tile ids: ranges come from the counts
-            if (sort_mode(STAGE_TILE) == 1)
+            if (tile_lookback)
                 st = onesweep_pass(kin, vin, p + 1 < passes ? kout : nullptr, vout, R, p * bpp, bpp, bn.sort_ws,
                                    passes, p, s, debug);
             else
                 st = radix_pass_u32(kin, vin, p + 1 < passes ? kout : nullptr, vout, R, p * bpp, bpp, bn.sort_ws,
-                                    bn.sort_ws + rs_hist_words(R), s, debug);
+                                    bn.sort_ws + rs_hist_words(R), s, debug, n_dev);
             if (st) { delete pts; return st; }
             uint32_t* t;
             t = kin; kin = kout; kout = t;
@@ -837,12 +859,38 @@ extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_all
             W3D_AFTER_LAUNCH(s, debug);
         }
     }
+    {
     ProfScope ps_render(PS_RENDER_FWD, s);
     render_forward_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, point_list_ptr(bn, num_tiles), W, H, g.rec,
                                                     prm->background, prm->sampling_offsets, im.final_T,
                                                     im.n_contrib, out_color, out_depth);
     W3D_AFTER_LAUNCH(s, debug);
+    }
+    if (async && status_dev) {
+        copy_status_kernel<<<1, 32, 0, s>>>(g.totals, status_dev);
+        W3D_AFTER_LAUNCH(s, debug);
+    }
     return WAST3D_OK;
+}
+
+extern "C" int wast3d_raster_forward(const wast3d_raster_params* prm, wast3d_alloc_fn geom_alloc,
+                                     void* geom_user, wast3d_alloc_fn binning_alloc,
+                                     void* binning_user, wast3d_alloc_fn img_alloc, void* img_user,
+                                     float* out_color, float* out_depth, int* radii,
+                                     int* num_rendered_host, void* stream_v) {
+    return raster_forward_impl(prm, geom_alloc, geom_user, binning_alloc, binning_user, img_alloc, img_user, out_color,
+                               out_depth, radii, num_rendered_host, -1, nullptr, stream_v);
+}
+
+extern "C" int wast3d_raster_forward_async(const wast3d_raster_params* prm, wast3d_alloc_fn geom_alloc,
+                                           void* geom_user, wast3d_alloc_fn binning_alloc,
+                                           void* binning_user, wast3d_alloc_fn img_alloc, void* img_user,
+                                           float* out_color, float* out_depth, int* radii,
+                                           int instance_capacity, unsigned int* status_dev, void* stream_v) {
+    if (instance_capacity < 1 || !status_dev) return WAST3D_ERR_INVALID_ARGUMENT;
+    int carved = 0;
+    return raster_forward_impl(prm, geom_alloc, geom_user, binning_alloc, binning_user, img_alloc, img_user, out_color,
+                               out_depth, radii, &carved, instance_capacity, status_dev, stream_v);
 }
 
 extern "C" int wast3d_set_tile_cut(int mode) {

@@ -312,6 +312,26 @@ __device__ __forceinline__ void unstage_rows(float* __restrict__ g_rows, int row
     }
 }
 
+// ---- [P,3] arrays (means3D, scales) with 16-byte loads -----------------------------------------
+// The caller's tensors are AoS [P,3] (12 bytes per Gaussian): a warp's 32 rows are 384 contiguous bytes = 24
+// float4.  Lanes 0-23 fetch one float4 each (coalesced 16-byte loads: 12 sector requests instead of the 36 of
+// three strided 4-byte loads per lane), the warp transposes through 96 floats of shared memory (stride-3 reads
+// are bank-conflict free) and lane l gets row l.  s_tmp: this warp's 96-float scratch.
+__device__ __forceinline__ float3 load_rows3(const float* __restrict__ base, int warp_first, int rows_valid,
+                                             int lane, float* s_tmp) {
+    const float* g = base + 3 * (size_t)warp_first;
+    if (rows_valid == 32 && (((size_t)g) & 15) == 0) {
+        if (lane < 24) reinterpret_cast<float4*>(s_tmp)[lane] = __ldg(reinterpret_cast<const float4*>(g) + lane);
+    } else {
+        for (int i = lane; i < 3 * rows_valid; i += 32) s_tmp[i] = __ldg(g + i);
+    }
+    __syncwarp();
+    float3 v = make_float3(0.f, 0.f, 0.f);
+    if (lane < rows_valid) v = make_float3(s_tmp[3 * lane], s_tmp[3 * lane + 1], s_tmp[3 * lane + 2]);
+    __syncwarp();
+    return v;
+}
+
 // ---- model-space activations (raw_params mode; scene/gaussian_model.py:26-41) ----------------
 // Same expressions as the torch kernels the reference runs for the GaussianModel getters:
 // sigmoid = 1 / (1 + exp(-x)), exp, F.normalize = x / max(||x||_2, 1e-12).

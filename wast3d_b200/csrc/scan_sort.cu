@@ -121,10 +121,13 @@ int scan_exclusive_u32(const uint32_t* in, const uint32_t* perm, uint32_t* out, 
 // [w*32*ITEMS, (w+1)*32*ITEMS) of the tile and its j-th load covers 32 consecutive keys, so
 // loads are coalesced and the memory order is (w, j, lane) — ranking in that order is stable.
 
+// n_dev (optional): the element count lives on the device (graph-safe forward: the instance count is never read by
+// the host); `n` is then the capacity the grid was sized for and the kernel processes min(*n_dev, n) elements.
 __global__ void __launch_bounds__(RS_THREADS)
 radix_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint32_t mask,
-                  uint32_t* __restrict__ hist, unsigned nblocks) {
+                  uint32_t* __restrict__ hist, unsigned nblocks, const uint32_t* __restrict__ n_dev) {
     __shared__ uint32_t h[RS_RADIX];
+    if (n_dev != nullptr) n = min(n, (size_t)*n_dev);
     h[threadIdx.x] = 0;
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * RS_TILE;
@@ -144,24 +147,24 @@ __global__ void onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const
                                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                                      int shift, uint32_t mask, const uint32_t* __restrict__ digit_hist,
                                      uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                                     uint32_t* __restrict__ err, unsigned nblocks);
+                                     uint32_t* __restrict__ err, unsigned nblocks, const uint32_t* __restrict__ n_dev);
 
 int radix_pass_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                    uint32_t* vals_out, size_t n, int shift, int bits, uint32_t* hist,
-                   uint32_t* scan_scratch, cudaStream_t s, bool debug) {
+                   uint32_t* scan_scratch, cudaStream_t s, bool debug, const uint32_t* n_dev) {
     if (n == 0) return WAST3D_OK;
     if (bits < 1 || bits > 8) return WAST3D_ERR_INVALID_ARGUMENT;
     if (n > 0xFFFFFFFFull - RS_TILE) return WAST3D_ERR_OVERFLOW;
     const unsigned nb = (unsigned)rs_num_blocks(n);
     const uint32_t mask = (1u << bits) - 1u;
-    radix_hist_kernel<<<nb, RS_THREADS, 0, s>>>(keys_in, n, shift, mask, hist, nb);
+    radix_hist_kernel<<<nb, RS_THREADS, 0, s>>>(keys_in, n, shift, mask, hist, nb, n_dev);
     W3D_AFTER_LAUNCH(s, debug);
     int st = scan_exclusive_u32(hist, nullptr, hist, (size_t)nb * RS_RADIX, scan_scratch, nullptr,
                                 s, debug);
     if (st != WAST3D_OK) return st;
 #define W3D_SCATTER(HV, WK)                                                                          \
     onesweep_pass_kernel<HV, WK, false><<<nb, OS_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n, \
-                                                                  shift, mask, hist, nullptr, nullptr, nullptr, nb)
+                                                                  shift, mask, hist, nullptr, nullptr, nullptr, nb, n_dev)
     if (vals_in) {
         if (keys_out) W3D_SCATTER(true, true); else W3D_SCATTER(true, false);
     } else {
@@ -228,8 +231,12 @@ onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __res
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
                      int shift, uint32_t mask, const uint32_t* __restrict__ digit_hist,
                      uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                     uint32_t* __restrict__ err, unsigned nblocks) {
+                     uint32_t* __restrict__ err, unsigned nblocks, const uint32_t* __restrict__ n_dev) {
     constexpr int WARPS = OS_THREADS / 32;
+    if (!LOOKBACK && n_dev != nullptr) {   // device-side element count (see radix_hist_kernel)
+        n = min(n, (size_t)*n_dev);
+        if ((size_t)blockIdx.x * OS_TILE >= n) return;   // whole block past the end (uniform)
+    }
     __shared__ uint16_t warp_hist[WARPS][RS_RADIX];  // <= OS_TILE, fits 16 bits
     __shared__ uint32_t bin_start[RS_RADIX];
     __shared__ uint32_t bin_base[RS_RADIX];
@@ -393,7 +400,7 @@ int onesweep_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* ke
 #define W3D_OS(HV, WK)                                                                                   \
     onesweep_pass_kernel<HV, WK, true><<<nb, OS_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n, shift, \
                                                                  mask, w.digit_hist + (size_t)pass * RS_RADIX,   \
-                                                                 w.status(pass), w.ticket(pass), w.err, nb)
+                                                                 w.status(pass), w.ticket(pass), w.err, nb, nullptr)
     if (vals_in) {
         if (keys_out) W3D_OS(true, true); else W3D_OS(true, false);
     } else {
@@ -534,7 +541,7 @@ extern "C" int wast3d_test_sort_pairs(size_t n, const uint32_t* keys_in, const u
         const bool to_out = ((passes - 1 - p) & 1) == 0;
         uint32_t* ko = to_out ? keys_out : ka;
         uint32_t* vo = to_out ? vals_out : va;
-        if (mode == 0) st = radix_pass_u32(kin, vin, ko, vo, n, shifts[p], bits[p], hist, scr, s, false);
+        if (mode == 0) st = radix_pass_u32(kin, vin, ko, vo, n, shifts[p], bits[p], hist, scr, s, false, nullptr);
         else st = onesweep_pass(kin, vin, ko, vo, n, shifts[p], bits[p], ws, passes, p, s, false);
         kin = ko;
         vin = vo;

@@ -33,6 +33,55 @@ def _prm(keep, rs: GaussianRasterizationSettings, xyz, f_dc, f_rest, opacity, sc
         sampling_offsets=offsets, raw_params=True, sh_rest=f_rest, colour_wait_event=colour_wait_event)
 
 
+# ---- graph-safe forward (wast3d_raster_forward_async): no host synchronisation in the step -------------------
+# The reference reads num_rendered back on the host in every forward to size the binning buffer
+# (rasterizer_impl.cu:283-289), which stalls the stream once per step and rules out CUDA-graph capture.  In async
+# mode the buffer is sized from the largest instance count SEEN so far for this (device, image size) plus headroom;
+# the count of every call lands in pinned host memory through an asynchronous copy and is looked at one call later:
+# no wait in steady state.  The first call for a size uses the synchronous protocol (there is no estimate yet).  An
+# overflow (the view needed more instances than the capacity: the image of that call was incomplete) raises
+# RuntimeError at the next call / at async_forward_check(), after the capacity has been raised.
+_ASYNC = {"on": bool(int(__import__("os").environ.get("WAST3D_ASYNC_FORWARD", "0")))}
+_ASYNC_STATE: dict = {}   # (device index, W, H) -> {"seen": max R, "pending": [(event, pinned, capacity)]}
+
+
+def set_async_forward(on: bool) -> bool:
+    """Enable / disable the graph-safe forward for rasterize_model(); returns the previous setting."""
+    prev, _ASYNC["on"] = _ASYNC["on"], bool(on)
+    return prev
+
+
+def _async_poll(st, wait=False):
+    keep = []
+    err = None
+    for ev, pinned, cap in st["pending"]:
+        if wait:
+            ev.synchronize()
+        if not ev.query():
+            keep.append((ev, pinned, cap))
+            continue
+        r, prefilt, timeout, overflow = (int(v) for v in pinned.tolist())
+        st["seen"] = max(st["seen"], r)
+        if overflow:
+            err = RuntimeError(f"wast3d_b200: a graph-safe forward needed {r} tile instances but its binning buffer held "
+                               f"{cap}; that step's image and gradients are incomplete (capacity raised for the next call)")
+        elif prefilt & 1:
+            err = RuntimeError("wast3d_b200: rasterize_model: invalid argument (prefiltered set but a culled point was seen)")
+        elif timeout:
+            err = RuntimeError("wast3d_b200: look-back time-out in the binning stage")
+    st["pending"] = keep
+    if err is not None:
+        raise err
+
+
+def async_forward_check(device=None):
+    """Wait for the status words of all graph-safe forwards issued so far and raise if one of them overflowed its
+    instance capacity (call at a point where synchronising is acceptable: end of training, checkpoints, tests)."""
+    for key, st in _ASYNC_STATE.items():
+        if device is None or key[0] == torch.device(device).index:
+            _async_poll(st, wait=True)
+
+
 class _RasterizeModel(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xyz, means2D, f_dc, f_rest, opacity, scaling, rotation, raster_settings,
@@ -56,10 +105,31 @@ class _RasterizeModel(torch.autograd.Function):
         ev = int(colour_wait_event.cuda_event) if colour_wait_event is not None else None
         prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation, sampling_offsets, ev)
         rendered = C.c_int(0)
+        ast = None
+        if _ASYNC["on"] and P:
+            ast = _ASYNC_STATE.setdefault((dev.index, W, H), {"seen": 0, "pending": []})
+            _async_poll(ast)   # raises if an earlier call of this size overflowed
         with torch.cuda.device(dev):
-            st = lib.wast3d_raster_forward(
-                C.byref(prm), geom.cb, None, binning.cb, None, img.cb, None, color.data_ptr(),
-                depth.data_ptr(), radii.data_ptr() if P else None, C.byref(rendered), _lib.stream_ptr())
+            if ast is not None and ast["seen"] > 0:
+                # capacity: 25% + 64k above the largest count seen, bucketed so that it (and the buffer size) is stable
+                cap = min(_lib.bucket_bytes(ast["seen"] + ast["seen"] // 4 + 65536), 0x7FFFFFFF)
+                status = torch.empty(4, dtype=torch.int32, device=dev)
+                st = lib.wast3d_raster_forward_async(
+                    C.byref(prm), geom.cb, None, binning.cb, None, img.cb, None, color.data_ptr(), depth.data_ptr(),
+                    radii.data_ptr(), int(cap), status.data_ptr(), _lib.stream_ptr())
+                rendered.value = int(cap)
+                if st == 0:
+                    pinned = torch.empty(4, dtype=torch.int32, pin_memory=True)
+                    pinned.copy_(status, non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    ast["pending"].append((ev, pinned, int(cap)))
+            else:
+                st = lib.wast3d_raster_forward(
+                    C.byref(prm), geom.cb, None, binning.cb, None, img.cb, None, color.data_ptr(),
+                    depth.data_ptr(), radii.data_ptr() if P else None, C.byref(rendered), _lib.stream_ptr())
+                if ast is not None and st == 0:
+                    ast["seen"] = max(ast["seen"], int(rendered.value), 1)
         geom_t, binning_t, img_t = geom.take(), binning.take(), img.take()
         for b in (geom, binning, img):
             if b.error is not None:
