@@ -141,7 +141,9 @@ int wast3d_raster_backward(const wast3d_raster_params* prm, int num_rendered, co
  * autograd backward of sigmoid / exp / normalize / cat that the reference runs as separate
  * torch kernels.  dL_dxyz [P,3], dL_dfeatures_dc [P,1,3], dL_dfeatures_rest [P,M-1,3],
  * dL_dopacity_logit [P,1], dL_dlog_scale [P,3], dL_drotation [P,4]; every element is written.
- * dL_dmean2D [P,3] (the viewspace_points gradient) is optional (NULL = not needed). */
+ * dL_dmean2D [P,3] (the viewspace_points gradient) is optional (NULL = not needed).
+ * dL_dfeatures_dc and dL_dfeatures_rest may BOTH be NULL: the SH gradients are then not written (the view-parallel
+ * colour-record exchange rebuilds them on every rank, include/wast3d_b200_staged.h). */
 int wast3d_raster_backward_raw(const wast3d_raster_params* prm, int num_rendered, const int* radii,
                                void* geom_buffer, void* binning_buffer, void* img_buffer,
                                const float* dL_dpix, const float* dL_ddepth, float* dL_dxyz,

@@ -834,8 +834,9 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                     adam_rows_linear<ADAM_U>(af.g[2], (size_t)warp_first * rest_floats, rows_valid * rest_floats, s_sh[warp],
                                      dL_dsh_rest, lane);
             } else if (RAW) {
-                if (live) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
-                if (rest_floats > 0)
+                // NULL feature outputs: the caller rebuilds the SH gradient elsewhere (colour-record exchange)
+                if (live && dL_dsh) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
+                if (rest_floats > 0 && dL_dsh_rest)
                     unstage_rows_linear(dL_dsh_rest + (size_t)warp_first * rest_floats, rest_floats, rows_valid,
                                         s_sh[warp], lane);
             } else {
@@ -996,7 +997,7 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
         // A/B switches (measurements): WAST3D_K7_ROWS = hits parked per transposed reduction (0 = shuffle butterfly),
         // WAST3D_K7_BATCH = records staged per barrier, WAST3D_K7_MINB = resident CTAs per SM the registers are cut for
         static const int rows = getenv("WAST3D_K7_ROWS") ? atoi(getenv("WAST3D_K7_ROWS")) : 0;
-        static const int batch = getenv("WAST3D_K7_BATCH") ? atoi(getenv("WAST3D_K7_BATCH")) : 256;
+        static const int batch = getenv("WAST3D_K7_BATCH") ? atoi(getenv("WAST3D_K7_BATCH")) : 512;   // measured: 512
         static const int minb = getenv("WAST3D_K7_MINB") ? atoi(getenv("WAST3D_K7_MINB")) : 4;
         const uint32_t* plist = point_list_ptr(bn, num_tiles);
 #define W3D_K7(B, R, M)                                                                                         \
@@ -1068,9 +1069,12 @@ extern "C" int wast3d_raster_backward_raw(const wast3d_raster_params* prm, int n
     if (st != WAST3D_OK) return st;
     if (!prm->raw_params) return WAST3D_ERR_INVALID_ARGUMENT;
     if (prm->P == 0) return WAST3D_OK;
+    // dL_dfeatures_dc / dL_dfeatures_rest may both be NULL: the SH gradients are then not written (view-parallel
+    // colour-record exchange: every rank rebuilds them from 16-byte records, wast3d_b200_staged.h)
+    const bool feats_all = dL_dfeatures_dc != nullptr && (prm->M <= 1 || dL_dfeatures_rest != nullptr);
+    const bool feats_none = dL_dfeatures_dc == nullptr && dL_dfeatures_rest == nullptr;
     if (num_rendered < 0 || !geom_buffer || !img_buffer || !binning_buffer || !dL_dpix || !dL_dxyz ||
-        !dL_dfeatures_dc || (prm->M > 1 && !dL_dfeatures_rest) || !dL_dopacity_logit || !dL_dlog_scale ||
-        !dL_drotation)
+        !(feats_all || feats_none) || !dL_dopacity_logit || !dL_dlog_scale || !dL_drotation)
         return WAST3D_ERR_INVALID_ARGUMENT;
     return raster_backward_impl(prm, num_rendered, radii, geom_buffer, binning_buffer, img_buffer, dL_dpix,
                                 dL_ddepth, dL_dmean2D, nullptr, dL_dopacity_logit, nullptr, dL_dxyz, nullptr,

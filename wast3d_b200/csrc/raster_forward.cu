@@ -404,9 +404,11 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
 }
 
 // ranges[t] = [sum of counts before t, + count) — one block, replaces identifyTileRanges.
+// `capacity`: the pair arrays hold that many instances; after an overflowing graph-safe forward (flagged, the caller
+// discards the step) the ranges are clamped so that the render kernels still only read initialised list entries.
 __global__ void __launch_bounds__(1024)
 tile_ranges_from_counts_kernel(int num_tiles, const uint32_t* __restrict__ tile_count,
-                               uint2* __restrict__ ranges) {
+                               uint2* __restrict__ ranges, const uint32_t capacity) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -434,7 +436,10 @@ tile_ranges_from_counts_kernel(int num_tiles, const uint32_t* __restrict__ tile_
         }
         __syncthreads();
         const uint32_t start = s_carry + s_warp[warp] + incl - c;
-        if (t < num_tiles) ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+        if (t < num_tiles) {
+            const uint32_t lo = min(start, capacity), hi = min(start + c, capacity);
+            ranges[t] = hi > lo ? make_uint2(lo, hi) : make_uint2(0u, 0u);
+        }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = start + c;
         __syncthreads();
@@ -842,7 +847,7 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         }
         delete pts;
         ProfScope ps(PS_RANGES, s);
-        tile_ranges_from_counts_kernel<<<1, 1024, 0, s>>>((int)num_tiles, im.tile_count, im.ranges);
+        tile_ranges_from_counts_kernel<<<1, 1024, 0, s>>>((int)num_tiles, im.tile_count, im.ranges, R);
         W3D_AFTER_LAUNCH(s, debug);
     } else {
         W3D_CUDA_TRY(cudaMemsetAsync(im.ranges, 0, num_tiles * sizeof(uint2), s));

@@ -205,6 +205,8 @@ class _RasterizeModel(torch.autograd.Function):
             d_sc = torch.empty_like(scaling)
             d_rot = torch.empty_like(rotation)
         d_m2d = torch.empty((P, 3), **opt) if ctx.needs_input_grad[1] else None
+        if sunk is not None and getattr(sink, "record_out", None) is not None:
+            d_dc = d_rest = None   # colour-record exchange: the SH gradients are rebuilt from the records, never written
         if P:
             keep: list = []
             prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation,
@@ -226,6 +228,8 @@ class _RasterizeModel(torch.autograd.Function):
             for v in sunk:
                 v.zero_()
         if sunk is not None:
+            if getattr(sink, "record_out", None) is not None:
+                sunk = [None if p_ is f_dc or p_ is f_rest else v for p_, v in zip(ctx.sink_params, sunk)]
             for p_, v in zip(ctx.sink_params, sunk):
                 p_.grad = v
             sink.fresh = False

@@ -1,4 +1,4 @@
-"""STAGED FOR ROUND 2 — not used by any default path; has not run on a GPU yet (DESIGN.md §6, round-2 plan).
+"""Colour-record exchange of the SH features for the view-parallel optimizer (bench.py --sync records).
 
 View-parallel optimizer in which the SH features never cross NVLink as gradients or parameters:
 
@@ -72,8 +72,9 @@ class PeerRecordAdam(torch.optim.Optimizer):
         self.records = PeerBuffer(max(16, 16 * P), dev, group=group, backend=backend)
         self.record_view = self.records.local[:16 * P].view(torch.float32).view(P, 4)
         self._record_ptrs = (C.c_void_p * self.world)(*self.records.ptrs)
-        # K8+K9 still writes the SH gradients (first version): into a local scratch nobody reads
-        self._scratch = {id(features_dc): torch.empty_like(features_dc), id(features_rest): torch.empty_like(features_rest)}
+        # K8+K9 does not write the SH gradients on this path (NULL outputs, wast3d_raster_backward_raw): the sink only
+        # needs placeholder views so that the rasteriser's backward takes its arena route for the other leaves
+        self._scratch = {id(features_dc): torch.empty(0, device=dev), id(features_rest): torch.empty(0, device=dev)}
         self.grad_sink = self.early.grad_sink
         self.grad_sink.views.update(self._scratch)
         self.grad_sink.record_out = self.record_view  # model_render._RasterizeModel.backward fills it
