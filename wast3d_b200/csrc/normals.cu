@@ -44,7 +44,9 @@ __device__ __forceinline__ float3 point_at(const float* __restrict__ depth, int 
     const float d = depth[(size_t)y * W + x];
     const float px = ((float)x - k.cx) / k.fx;
     const float py = ((float)y - k.cy) / k.fy;
-    return make_float3(px * d, py * d, d);
+    // explicit multiplies: the differences of neighbouring points below must not be contracted into
+    // fma(px, d, -other) — that would turn "the same point twice" (replicate padding) into its rounding residue
+    return make_float3(__fmul_rn(px, d), __fmul_rn(py, d), d);
 }
 
 // Sobel gradients of the point image at (x, y): a = d/dx, b = d/dy (kernels / 8).  Differences of the two

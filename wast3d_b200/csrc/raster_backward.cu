@@ -394,7 +394,7 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
 __global__ void __launch_bounds__(256)
 det_gather_kernel(int P, const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ seg,
                   const uint32_t* __restrict__ inst_sorted, const float4* __restrict__ inst_grad,
-                  float4* __restrict__ grad_rec) {
+                  float4* __restrict__ grad_rec, const uint32_t R) {
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= P) return;
     const uint32_t n = tiles_touched[id];
@@ -402,6 +402,7 @@ det_gather_kernel(int P, const uint32_t* __restrict__ tiles_touched, const uint3
     const uint32_t first = seg[id];
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
     for (uint32_t k = 0; k < n; ++k) {
+        if (first + k >= R) break;   // only after an overflowing graph-safe forward (flagged; the step is discarded)
         const size_t i = inst_sorted[first + k];
         const float4 x = inst_grad[3 * i], y = inst_grad[3 * i + 1], z = inst_grad[3 * i + 2];
         a0.x += x.x; a0.y += x.y; a0.z += x.z; a0.w += x.w;
@@ -984,7 +985,8 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
             if (st != WAST3D_OK) break;
             st = scan_exclusive_u32(g.tiles_touched, nullptr, seg, P, scan_scr, nullptr, s, debug);
             if (st != WAST3D_OK) break;
-            det_gather_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.tiles_touched, seg, vin, inst_grad, g.grad_rec);
+            det_gather_kernel<<<(P + 255) / 256, 256, 0, s>>>(P, g.tiles_touched, seg, vin, inst_grad, g.grad_rec,
+                                                              (uint32_t)R);
             count_launch();
             if (cudaGetLastError() != cudaSuccess) st = WAST3D_ERR_CUDA;
         } while (0);
