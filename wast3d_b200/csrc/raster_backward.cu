@@ -389,6 +389,136 @@ render_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restr
     cp_async_wait<0>();
 }
 
+// ---- K7, one warp per CTA (see render_forward_warp_kernel for the rationale) ------------------------------------
+// Every 8x4 pixel block replays the tile's list for itself, back to front from ITS deepest last contributor, three
+// 32-record rounds in flight, no block barrier; the ten moment sums of a hit go through the value-halving butterfly
+// and one RED per slot, exactly like the tile kernel.  Per-pixel arithmetic is identical (replay_pair).
+constexpr int K7W_STAGES = 3;
+
+__global__ void __launch_bounds__(32)
+render_backward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                            const int W, const int H, const int tiles_x, const float* __restrict__ bg_color,
+                            const float4* __restrict__ rec, const float* __restrict__ sampling_offsets,
+                            const float* __restrict__ final_Ts, const uint32_t* __restrict__ n_contrib,
+                            const float* __restrict__ dL_dpixels, const float* __restrict__ dL_ddepths,
+                            float4* __restrict__ grad_rec) {
+    __shared__ float4 s_r0[K7W_STAGES][32];
+    __shared__ float4 s_r1[K7W_STAGES][32];
+    __shared__ float4 s_r2[K7W_STAGES][32];
+    __shared__ uint32_t s_id[K7W_STAGES][32];
+
+    float* grad_f = reinterpret_cast<float*>(grad_rec);
+    const int lane = threadIdx.x;
+    const uint32_t pxi = blockIdx.x * 8 + (lane & 7);
+    const uint32_t pyi = blockIdx.y * 4 + (lane >> 3);
+    const bool inside = pxi < (uint32_t)W && pyi < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * pyi + pxi;
+
+    ReplayPixel px;
+    px.last_contributor = inside ? n_contrib[pix_id] : 0u;
+    // Nothing behind this block's deepest last contributor can receive gradient.
+    const uint32_t warp_max_last = __reduce_max_sync(0xffffffffu, px.last_contributor);
+    if (warp_max_last == 0) return;
+
+    px.pixf = make_float2((float)pxi, (float)pyi);
+    if (inside && sampling_offsets != nullptr) {
+        const float2 o = *reinterpret_cast<const float2*>(sampling_offsets + 2 * (size_t)pix_id);
+        px.pixf.x = (float)pxi + o.x;
+        px.pixf.y = (float)pyi + o.y;
+    }
+    const float inf = __int_as_float(0x7f800000);
+    float bx0 = inside ? px.pixf.x : inf, bx1 = inside ? px.pixf.x : -inf;
+    float by0 = inside ? px.pixf.y : inf, by1 = inside ? px.pixf.y : -inf;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
+        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
+        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
+    }
+
+    const uint2 range = ranges[(blockIdx.y >> 2) * tiles_x + (blockIdx.x >> 1)];
+
+    // backward.cu:463-478
+    px.T_final = inside ? final_Ts[pix_id] : 0.f;
+    px.T = px.T_final;
+    const size_t HW = (size_t)H * W;
+    px.dpix0 = px.dpix1 = px.dpix2 = px.ddepth = 0.f;
+    if (inside) {
+        px.dpix0 = dL_dpixels[pix_id];
+        px.dpix1 = dL_dpixels[HW + pix_id];
+        px.dpix2 = dL_dpixels[2 * HW + pix_id];
+        px.ddepth = dL_ddepths ? dL_ddepths[pix_id] : 0.f;
+    }
+    // backward.cu:560-563 (pixel constant)
+    px.bg_dot_dpixel = 0.f;
+    px.bg_dot_dpixel += bg_color[0] * px.dpix0;
+    px.bg_dot_dpixel += bg_color[1] * px.dpix1;
+    px.bg_dot_dpixel += bg_color[2] * px.dpix2;
+    px.accum0 = px.accum1 = px.accum2 = 0.f;
+    px.last_alpha = px.last_c0 = px.last_c1 = px.last_c2 = 0.f;
+
+    const int n = (int)min(warp_max_last, range.y - range.x);
+    const int rounds = (n + 31) / 32;
+
+    auto prefetch = [&](int b) {
+        const int p = b * 32 + lane;
+        if (b < rounds && p < n) {
+            const uint32_t id = point_list[range.x + (uint32_t)(n - 1 - p)];
+            const int st = b % K7W_STAGES;
+            s_id[st][lane] = id;
+            const float4* src = rec + 3 * (size_t)id;
+            cp_async16(&s_r0[st][lane], src);
+            cp_async16(&s_r1[st][lane], src + 1);
+            cp_async16(&s_r2[st][lane], src + 2);
+        }
+        cp_async_commit();   // one group per round, empty or not
+    };
+
+    prefetch(0);
+    prefetch(1);
+    for (int b = 0; b < rounds; ++b) {
+        prefetch(b + 2);
+        cp_async_wait<2>();
+        __syncwarp();
+        const int st = b % K7W_STAGES;
+        const float4* r0 = s_r0[st];
+        const float4* r1 = s_r1[st];
+        const float4* r2 = s_r2[st];
+        const int cnt = min(32, n - b * 32);
+        bool hit = false;
+        if (lane < cnt) {
+            const float4 a = r0[lane];
+            const float hy = r2[lane].w;
+            hit = !((a.x + a.w < bx0) || (a.x - a.w > bx1) || (a.y + hy < by0) || (a.y - hy > by1));
+            if (hit) {  // the box overlaps: decide exactly on the ellipse
+                const float4 co = r1[lane];
+                hit = !ellipse_misses_rect(a.x, a.y, co.x, co.y, co.z, co.w, bx0, bx1, by0, by1);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t pos = (uint32_t)(n - 1 - (b * 32 + j));
+            float v[10];
+            const bool active = replay_pair(px, pos, r0[j], r1[j], r2 + j, v);
+            if (!__any_sync(0xffffffffu, active)) continue;
+            float v12[12];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) v12[record_index(i)] = active ? v[i] : 0.f;
+            v12[7] = v12[11] = 0.f;
+            const float tot = warp_reduce12(v12, lane);
+            const int sub = ((lane >> 1) & 3);  // 2*b2 + b1
+            const int slot = 6 * ((lane >> 4) & 1) + 3 * ((lane >> 3) & 1) + sub;
+            if (!(lane & 1) && sub < 3 && slot != 7 && slot != 11)
+                atomicAdd(grad_f + 12 * (size_t)s_id[st][j] + slot, tot);
+        }
+        __syncwarp();   // everybody is done with stage st before round b + 3 overwrites it
+    }
+    cp_async_wait<0>();
+}
+
 // Deterministic mode, second half: Gaussian `id` owns tiles_touched[id] instances whose point-list positions
 // sit, ascending, at inst_sorted[seg[id] ...]; their 48-byte partial gradient records are added in that order.
 __global__ void __launch_bounds__(256)
@@ -1005,8 +1135,16 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
 #define W3D_K7(B, R, M)                                                                                         \
     launch_k7<B, R, false, M>(grid, s, im.ranges, plist, W, H, prm->background, g.rec, prm->sampling_offsets,  \
                               im.final_T, im.n_contrib, dL_dpix, dL_ddepth, g.grad_rec, nullptr)
+        // WAST3D_K7_MODE: 1 (default) = one warp (8x4 pixels) per CTA, 0 = one 16x16 tile per CTA
+        static const int k7_mode = getenv("WAST3D_K7_MODE") ? atoi(getenv("WAST3D_K7_MODE")) : 1;
         cudaError_t e;
-        if (rows == 2) e = batch == 512 ? W3D_K7(512, 2, 4) : W3D_K7(256, 2, 4);
+        if (k7_mode == 1) {
+            const dim3 wgrid(2 * grid.x, 4 * grid.y, 1);
+            render_backward_warp_kernel<<<wgrid, 32, 0, s>>>(im.ranges, plist, W, H, (int)grid.x, prm->background, g.rec,
+                                                             prm->sampling_offsets, im.final_T, im.n_contrib, dL_dpix,
+                                                             dL_ddepth, g.grad_rec);
+            e = cudaGetLastError();
+        } else if (rows == 2) e = batch == 512 ? W3D_K7(512, 2, 4) : W3D_K7(256, 2, 4);
         else if (rows == 3) e = W3D_K7(256, 3, 3);
         else if (batch == 512) e = minb == 5 ? W3D_K7(512, 0, 5) : W3D_K7(512, 0, 4);
         else if (batch == 128) e = minb == 5 ? W3D_K7(128, 0, 5) : W3D_K7(128, 0, 4);

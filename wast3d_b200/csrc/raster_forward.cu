@@ -610,6 +610,149 @@ render_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     }
 }
 
+// ---- K6, one warp per CTA ---------------------------------------------------------------------------------
+// The tile kernel above stages a tile's list once for its eight warps and pays for it with a block barrier per
+// batch: a warp whose 8x4 pixels saturate early (or see few Gaussians) idles at every barrier until the slowest
+// warp of the tile is through, and its registers stay resident (ncu: ~40 % of the warp-time of K6 / K7 is spent at
+// that barrier, issue slots 73-81 % used).  Here every 8x4 pixel block is its own single-warp CTA: it stages the
+// tile's list for itself (3 x 32 records in flight, cp.async; the extra L2 -> SM traffic is ~2 GB per launch, a few
+// percent of the L2 bandwidth), synchronises with nobody, and leaves as soon as ITS pixels are done.  Same per-pixel
+// instruction sequence as render_forward_kernel: images, final_T and n_contrib are bit-identical.
+constexpr int WARP_STAGES = 3;
+
+__global__ void __launch_bounds__(32)
+render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                           const int W, const int H, const int tiles_x, const float4* __restrict__ rec,
+                           const float* __restrict__ bg_color, const float* __restrict__ sampling_offsets,
+                           float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+                           float* __restrict__ out_color, float* __restrict__ out_depth) {
+    __shared__ float4 s_r0[WARP_STAGES][32];
+    __shared__ float4 s_r1[WARP_STAGES][32];
+    __shared__ float4 s_r2[WARP_STAGES][32];
+
+    const int lane = threadIdx.x;
+    // blockIdx.x: 8-pixel column block, blockIdx.y: 4-pixel row block
+    const uint32_t px = blockIdx.x * 8 + (lane & 7);
+    const uint32_t py = blockIdx.y * 4 + (lane >> 3);
+    const bool inside = px < (uint32_t)W && py < (uint32_t)H;
+    const uint32_t pix_id = (uint32_t)W * py + px;
+
+    float2 pixf = make_float2((float)px, (float)py);
+    if (inside && sampling_offsets != nullptr) {
+        const float2 o = *reinterpret_cast<const float2*>(sampling_offsets + 2 * (size_t)pix_id);
+        pixf.x = (float)px + o.x;
+        pixf.y = (float)py + o.y;
+    }
+    const float inf = __int_as_float(0x7f800000);
+    float bx0 = inside ? pixf.x : inf, bx1 = inside ? pixf.x : -inf;
+    float by0 = inside ? pixf.y : inf, by1 = inside ? pixf.y : -inf;
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        bx0 = fminf(bx0, __shfl_xor_sync(0xffffffffu, bx0, d));
+        bx1 = fmaxf(bx1, __shfl_xor_sync(0xffffffffu, bx1, d));
+        by0 = fminf(by0, __shfl_xor_sync(0xffffffffu, by0, d));
+        by1 = fmaxf(by1, __shfl_xor_sync(0xffffffffu, by1, d));
+    }
+
+    const uint2 range = ranges[(blockIdx.y >> 2) * tiles_x + (blockIdx.x >> 1)];
+    // a block that lies entirely outside the image (W, H not multiples of 8 / 4) has nothing to blend or to write
+    const int n = __any_sync(0xffffffffu, inside) ? (int)(range.y - range.x) : 0;
+    const int rounds = (n + 31) / 32;
+
+    auto prefetch = [&](int b) {
+        const int p = b * 32 + lane;
+        if (b < rounds && p < n) {
+            const uint32_t id = point_list[range.x + p];
+            const float4* src = rec + 3 * (size_t)id;
+            const int st = b % WARP_STAGES;
+            cp_async16(&s_r0[st][lane], src);
+            cp_async16(&s_r1[st][lane], src + 1);
+            cp_async16(&s_r2[st][lane], src + 2);
+        }
+        cp_async_commit();   // one group per round, empty or not: the wait below counts groups
+    };
+
+    bool done = !inside;
+    float T = 1.0f;
+    uint32_t last_contributor = 0;
+    float C0 = 0.f, C1 = 0.f, C2 = 0.f, Dp = 0.f;
+
+    prefetch(0);
+    prefetch(1);
+    for (int b = 0; b < rounds; ++b) {
+        prefetch(b + 2);
+        cp_async_wait<2>();   // round b has landed (two younger groups may still be in flight)
+        __syncwarp();
+        const int st = b % WARP_STAGES;
+        const float4* r0 = s_r0[st];
+        const float4* r1 = s_r1[st];
+        const float4* r2 = s_r2[st];
+        const int cnt = min(32, n - b * 32);
+        bool hit = false;
+        if (lane < cnt) {
+            const float4 a = r0[lane];
+            const float hy = r2[lane].w;
+            // "not certainly outside" so that NaNs fall through to the exact test
+            hit = !((a.x + a.w < bx0) || (a.x - a.w > bx1) || (a.y + hy < by0) || (a.y - hy > by1));
+            if (hit) {  // the box overlaps: decide exactly on the ellipse
+                const float4 co = r1[lane];
+                hit = !ellipse_misses_rect(a.x, a.y, co.x, co.y, co.z, co.w, bx0, bx1, by0, by1);
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        bool warp_done = false;
+        while (m) {
+            const int j = __ffs(m) - 1;
+            m &= m - 1;
+            if (!done) {
+                const float4 a = r0[j];
+                const float4 con_o = r1[j];
+                // forward.cu:343-346, FMA structure pinned to the reference's SASS
+                const float dx = __fsub_rn(a.x, pixf.x);
+                const float dy = __fsub_rn(a.y, pixf.y);
+                const float sy = __fmul_rn(__fmul_rn(con_o.z, dy), dy);
+                const float sq = __fmaf_rn(dx, __fmul_rn(con_o.x, dx), sy);
+                const float cr = __fmul_rn(__fmul_rn(con_o.y, dx), dy);
+                const float power = __fmaf_rn(sq, -0.5f, -cr);
+                if (!(power > 0.0f)) {
+                    const float alpha = fminf(0.99f, __fmul_rn(con_o.w, expf(power)));
+                    if (!(alpha < 1.0f / 255.0f)) {
+                        const float test_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                        if (test_T < 0.0001f) {
+                            done = true;
+                        } else {
+                            const float4 c = r2[j];
+                            C0 = __fmaf_rn(T, __fmul_rn(alpha, c.x), C0);
+                            C1 = __fmaf_rn(T, __fmul_rn(alpha, c.y), C1);
+                            C2 = __fmaf_rn(T, __fmul_rn(alpha, c.z), C2);
+                            Dp = __fmaf_rn(T, __fmul_rn(alpha, a.z), Dp);
+                            T = test_T;
+                            last_contributor = (uint32_t)(b * 32 + j + 1);
+                        }
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) {
+                warp_done = true;
+                break;
+            }
+        }
+        if (warp_done) break;
+        __syncwarp();   // everybody is done reading stage st before round b + 3 overwrites it
+    }
+    cp_async_wait<0>();
+
+    if (inside) {
+        final_T[pix_id] = T;
+        n_contrib[pix_id] = last_contributor;
+        const size_t HW = (size_t)H * W;
+        out_color[pix_id] = __fmaf_rn(bg_color[0], T, C0);
+        out_color[HW + pix_id] = __fmaf_rn(bg_color[1], T, C1);
+        out_color[2 * HW + pix_id] = __fmaf_rn(bg_color[2], T, C2);
+        out_depth[pix_id] = Dp;
+    }
+}
+
 // ------------------------------------------------------------------ host -----------------
 // Which flavour of the sort / scan primitives each binning stage uses: 0 = multi-kernel (histogram,
 // table scan, scatter), 1 = single-kernel passes with decoupled look-back.  Measured on B200
@@ -866,9 +1009,18 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
     }
     {
     ProfScope ps_render(PS_RENDER_FWD, s);
-    render_forward_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, point_list_ptr(bn, num_tiles), W, H, g.rec,
-                                                    prm->background, prm->sampling_offsets, im.final_T,
-                                                    im.n_contrib, out_color, out_depth);
+    // WAST3D_K6_MODE: 1 (default) = one warp (8x4 pixels) per CTA, 0 = one 16x16 tile per CTA (A/B measurements)
+    static const int k6_mode = getenv("WAST3D_K6_MODE") ? atoi(getenv("WAST3D_K6_MODE")) : 1;
+    if (k6_mode == 1) {
+        const dim3 wgrid(2 * grid.x, 4 * grid.y, 1);   // the 8x4 blocks of whole tiles (out-of-image lanes are masked)
+        render_forward_warp_kernel<<<wgrid, 32, 0, s>>>(im.ranges, point_list_ptr(bn, num_tiles), W, H, (int)grid.x, g.rec,
+                                                        prm->background, prm->sampling_offsets, im.final_T,
+                                                        im.n_contrib, out_color, out_depth);
+    } else {
+        render_forward_kernel<<<grid, TILE_PIX, 0, s>>>(im.ranges, point_list_ptr(bn, num_tiles), W, H, g.rec,
+                                                        prm->background, prm->sampling_offsets, im.final_T,
+                                                        im.n_contrib, out_color, out_depth);
+    }
     W3D_AFTER_LAUNCH(s, debug);
     }
     if (async && status_dev) {

@@ -73,8 +73,18 @@ __host__ __device__ inline void accumulate_views(const ShAdamArgs& a, int idx, f
     for (int q = 0; q < rest_floats; ++q) mine[q] = 0.f;
     const float px = a.xyz[3 * (size_t)idx], py = a.xyz[3 * (size_t)idx + 1], pz = a.xyz[3 * (size_t)idx + 2];
     const int ncoef = M < (D + 1) * (D + 1) ? M : (D + 1) * (D + 1);
+    // all views' records first: up to SA_MAX_VIEWS independent 16-byte loads in flight per thread (seven of them
+    // cross NVLink at N = 8) instead of one load -> basis -> accumulate round trip per view
+    float4 recs[SA_MAX_VIEWS];
+#pragma unroll
+    for (int vw = 0; vw < SA_MAX_VIEWS; ++vw)
+        if (vw < a.views) recs[vw] = a.records[vw][idx];
+#pragma unroll 1
     for (int vw = 0; vw < a.views; ++vw) {
-        const float4 r = a.records[vw][idx];
+        float4 r = recs[0];
+#pragma unroll
+        for (int q = 1; q < SA_MAX_VIEWS; ++q)
+            if (q == vw) r = recs[q];
         if (r.w == 0.f) continue;  // culled in this view: contributes exactly zero
         // direction and basis as gaussian_backward_kernel / backward.cu:36-128 write them
         const float dx = px - a.campos[vw][0], dy = py - a.campos[vw][1], dz = pz - a.campos[vw][2];

@@ -306,10 +306,10 @@ class PeerShardedAdam(torch.optim.Optimizer):
         # persistent-grid cap of the late launch: it runs beside the next view's projection / sorting / binning;
         # its duration barely changes between 148 and 12-20 CTAs (NVLink/NVSwitch bound), the slowdown of the kernels
         # beside it does: every request it keeps in flight queues in front of theirs (profiles/r01_overlap.md)
-        # defaults = the measured configurations: multicast 12 at N <= 4 and 20 above (the N = 8 bench line; 12 is
-        # untested there and a shard of 1/8 with a longer switch round trip may become request-limited), plain peer
-        # loads / stores 37 at N = 2 and 20 at N = 4
-        default_ctas = (12 if W <= 4 else 20) if self.multicast else (37 if W <= 2 else 20)
+        # defaults = the measured configurations: multicast 12 (N = 4 and N = 8), plain peer loads / stores 37 at N = 2
+        # and 20 at N = 4
+        # round 2, N = 8 (8 x B200, multicast): 12 CTAs 3.50 ms per step, 20 CTAs 3.66 ms (profiles/r02_scaling_n8.md)
+        default_ctas = 12 if self.multicast else (37 if W <= 2 else 20)
         self.late_ctas = int(os.environ.get("WAST3D_PEER_LATE_CTAS", str(default_ctas)))
         if W > 1:  # replicas start identical: rank 0's values win (the reference has one copy)
             dist.broadcast(self._param_flat, src=dist.get_global_rank(group, 0) if group is not None else 0,
