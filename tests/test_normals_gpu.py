@@ -50,11 +50,11 @@ def test_normals_forward_backward_match_oracle(built, H, W, K):
     n64 = on.depth_to_normals(d64.detach(), *K)
     ok = (n64.norm(dim=0) > 0.5)[None].expand_as(o64)
     if H == 1 or W == 1:
-        # one of the two Sobel gradients vanishes identically: a x b == 0 everywhere, every normal is 0 / eps = 0 and the
-        # rescaled image is (0 - 0) / (0 + 1e-6) = 0; the gradient to the depth is zero as well
-        # (the gradient is 0 * (1 / eps) * (1 / 1e-6) terms that cancel analytically: ill-conditioned in any float32
-        # evaluation, the torch chain included — only finiteness is asserted)
-        assert out.abs().max().item() == 0.0 and o64.abs().max().item() == 0.0
+        # one of the two Sobel gradients vanishes identically, so a x b is 0 up to rounding residue: the direction of
+        # the "normal" is noise in EVERY evaluation (the float64 torch chain returns non-zero junk here as well, from
+        # the summation order of its convolution) and nothing downstream is comparable.  Ours is exactly zero (the
+        # kernel takes differences of identical points) and must stay finite.
+        assert out.abs().max().item() == 0.0
         assert torch.isfinite(d1.grad).all()
         return
     assert ok.float().mean().item() > 0.7

@@ -21,26 +21,35 @@ constexpr int LOSS_MAX_BLOCKS = 148 * 8;
 
 __device__ __forceinline__ float sgn(float x) { return (x > 0.f) - (x < 0.f); }
 
+// Row-based loops: a block walks whole image rows (row = c * H + y), threads stride over x.  All index arithmetic
+// is 32-bit with one modulo per ROW (the first version did two 64-bit divisions per ELEMENT and spent its time there).
 __global__ void __launch_bounds__(LOSS_THREADS)
 pixel_loss_forward_kernel(int C, int H, int W, const float* __restrict__ img, const float* __restrict__ gt,
                           const float* __restrict__ depth, const float* __restrict__ depth_gt, float w_l1,
                           float w_tv, float w_depth, double* __restrict__ partials, unsigned* __restrict__ counter,
                           float* __restrict__ out_loss) {
     const size_t HW = (size_t)H * W, n = (size_t)C * HW;
+    const int rows = C * H;
     float s_l1 = 0.f, s_ty = 0.f, s_tx = 0.f, s_d = 0.f;
-    for (size_t i = (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * LOSS_THREADS) {
-        const size_t pix = i % HW;
-        const int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
-        const float v = img[i];
-        if (gt) s_l1 += fabsf(v - gt[i]);
-        if (y + 1 < H) s_ty += fabsf(img[i + W] - v);
-        if (x + 1 < W) s_tx += fabsf(img[i + 1] - v);
-        if (depth && i < HW) {
-            const float d = depth[i] - depth_gt[i];
-            s_d += d * d;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int y = row % H;
+        const bool down = y + 1 < H;
+        const bool drow = depth != nullptr && row < H;   // channel 0's rows index the [H,W] depth image as well
+        const float* r = img + (size_t)row * W;
+        const float* g = gt ? gt + (size_t)row * W : nullptr;
+        for (int x = threadIdx.x; x < W; x += LOSS_THREADS) {
+            const float v = r[x];
+            if (g) s_l1 += fabsf(v - g[x]);
+            if (down) s_ty += fabsf(r[x + W] - v);
+            if (x + 1 < W) s_tx += fabsf(r[x + 1] - v);
+            if (drow) {
+                const float d = depth[(size_t)row * W + x] - depth_gt[(size_t)row * W + x];
+                s_d += d * d;
+            }
         }
     }
     __shared__ float red[4][LOSS_THREADS / 32];
+    __shared__ double sred[4][LOSS_THREADS];
     __shared__ bool last;
     float v4[4] = {s_l1, s_ty, s_tx, s_d};
 #pragma unroll
@@ -63,15 +72,25 @@ pixel_loss_forward_kernel(int C, int H, int W, const float* __restrict__ img, co
     }
     __syncthreads();
     if (!last) return;
-    // the last block sums the per-block partials in block order: the result does not depend on scheduling
-    __shared__ double tot[4];
-    if (threadIdx.x < 4) {
-        double t = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) t += ((volatile double*)partials)[4 * (size_t)b + threadIdx.x];
-        tot[threadIdx.x] = t;
+    // The last block adds the per-block partials in an order that depends only on the grid size (thread t takes blocks
+    // t, t + 256, ...; then a fixed tree): deterministic, and parallel instead of one thread walking ~1200 partials.
+    {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (unsigned b = threadIdx.x; b < gridDim.x; b += LOSS_THREADS)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] += ((volatile double*)partials)[4 * (size_t)b + k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sred[k][threadIdx.x] = acc[k];
+        __syncthreads();
+        for (int sft = LOSS_THREADS / 2; sft > 0; sft >>= 1) {
+            if ((int)threadIdx.x < sft)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) sred[k][threadIdx.x] += sred[k][threadIdx.x + sft];
+            __syncthreads();
+        }
     }
-    __syncthreads();
     if (threadIdx.x == 0) {
+        const double tot[4] = {sred[0][0], sred[1][0], sred[2][0], sred[3][0]};
         double loss = 0.0;
         if (gt) loss += (double)w_l1 * tot[0] / (double)n;
         double tv = 0.0;
@@ -90,29 +109,35 @@ pixel_loss_backward_kernel(int C, int H, int W, const float* __restrict__ img, c
                            float w_tv, float w_depth, const float* __restrict__ grad_out,
                            float* __restrict__ d_img, float* __restrict__ d_depth) {
     const size_t HW = (size_t)H * W, n = (size_t)C * HW;
+    const int rows = C * H;
     const float go = grad_out ? *grad_out : 1.0f;
     const float k_l1 = gt ? go * w_l1 / (float)n : 0.f;
     const float k_ty = H > 1 ? go * w_tv * 0.5f / ((float)C * (float)(H - 1) * (float)W) : 0.f;
     const float k_tx = W > 1 ? go * w_tv * 0.5f / ((float)C * (float)H * (float)(W - 1)) : 0.f;
     const float k_d = go * w_depth * 2.0f / (float)HW;
-    for (size_t i = (size_t)blockIdx.x * LOSS_THREADS + threadIdx.x; i < n; i += (size_t)gridDim.x * LOSS_THREADS) {
-        const size_t pix = i % HW;
-        const int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
-        const float v = img[i];
-        float g = 0.f;
-        if (gt) g += k_l1 * sgn(v - gt[i]);
-        // d/dv of |img[y+1]-v| is -sign(.), of |v-img[y-1]| is +sign(.)
-        if (y + 1 < H) g -= k_ty * sgn(img[i + W] - v);
-        if (y > 0) g += k_ty * sgn(v - img[i - W]);
-        if (x + 1 < W) g -= k_tx * sgn(img[i + 1] - v);
-        if (x > 0) g += k_tx * sgn(v - img[i - 1]);
-        d_img[i] = g;
-        if (d_depth && i < HW) d_depth[i] = depth ? k_d * (depth[i] - depth_gt[i]) : 0.f;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int y = row % H;
+        const bool down = y + 1 < H, up = y > 0;
+        const bool drow = d_depth != nullptr && row < H;
+        const size_t base = (size_t)row * W;
+        const float* r = img + base;
+        for (int x = threadIdx.x; x < W; x += LOSS_THREADS) {
+            const float v = r[x];
+            float g = 0.f;
+            if (gt) g += k_l1 * sgn(v - gt[base + x]);
+            // d/dv of |img[y+1]-v| is -sign(.), of |v-img[y-1]| is +sign(.)
+            if (down) g -= k_ty * sgn(r[x + W] - v);
+            if (up) g += k_ty * sgn(v - r[x - W]);
+            if (x + 1 < W) g -= k_tx * sgn(r[x + 1] - v);
+            if (x > 0) g += k_tx * sgn(v - r[x - 1]);
+            d_img[base + x] = g;
+            if (drow) d_depth[base + x] = depth ? k_d * (depth[base + x] - depth_gt[base + x]) : 0.f;
+        }
     }
 }
 
-static unsigned loss_blocks(size_t n) {
-    size_t b = (n + LOSS_THREADS - 1) / LOSS_THREADS;
+static unsigned loss_blocks(size_t rows) {   // one block per image row, capped at a few resident waves
+    size_t b = rows;
     if (b > LOSS_MAX_BLOCKS) b = LOSS_MAX_BLOCKS;
     return (unsigned)(b < 1 ? 1 : b);
 }
@@ -132,7 +157,7 @@ extern "C" int wast3d_pixel_loss_forward(int C, int H, int W, const float* img, 
     // scratch: [counter (zero between calls; the kernel resets it) | pad to 128 | partials]
     unsigned* counter = (unsigned*)scratch;
     double* partials = (double*)((char*)scratch + 128);
-    pixel_loss_forward_kernel<<<loss_blocks((size_t)C * H * W), LOSS_THREADS, 0, s>>>(
+    pixel_loss_forward_kernel<<<loss_blocks((size_t)C * H), LOSS_THREADS, 0, s>>>(
         C, H, W, img, gt, depth, depth_gt, w_l1, w_tv, w_depth, partials, counter, out_loss);
     W3D_AFTER_LAUNCH(s, false);
     return WAST3D_OK;
@@ -144,7 +169,7 @@ extern "C" int wast3d_pixel_loss_backward(int C, int H, int W, const float* img,
     if (C < 1 || H < 1 || W < 1 || !img || !d_img || ((depth == nullptr) != (depth_gt == nullptr)))
         return WAST3D_ERR_INVALID_ARGUMENT;
     cudaStream_t s = (cudaStream_t)stream_v;
-    pixel_loss_backward_kernel<<<loss_blocks((size_t)C * H * W), LOSS_THREADS, 0, s>>>(
+    pixel_loss_backward_kernel<<<loss_blocks((size_t)C * H), LOSS_THREADS, 0, s>>>(
         C, H, W, img, gt, depth, depth_gt, w_l1, w_tv, w_depth, grad_out, d_img, d_depth);
     W3D_AFTER_LAUNCH(s, false);
     return WAST3D_OK;

@@ -152,14 +152,27 @@ normals_bwd_reduce_kernel(size_t n, const float* __restrict__ unit, const float*
         __threadfence();
     }
     __syncthreads();
-    if (!last || threadIdx.x != 0) return;
+    if (!last) return;
+    // last block: partials added in an order fixed by the grid size (thread t takes blocks t, t + 256, ...; fixed tree)
+    __shared__ double sred[2][NRM_THREADS];
     double t0 = 0.0, t1 = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) {
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += NRM_THREADS) {
         t0 += ((volatile double*)partials)[2 * (size_t)b];
         t1 += ((volatile double*)partials)[2 * (size_t)b + 1];
     }
-    red[0] = t0;
-    red[1] = t1;
+    sred[0][threadIdx.x] = t0;
+    sred[1][threadIdx.x] = t1;
+    __syncthreads();
+    for (int sft = NRM_THREADS / 2; sft > 0; sft >>= 1) {
+        if ((int)threadIdx.x < sft) {
+            sred[0][threadIdx.x] += sred[0][threadIdx.x + sft];
+            sred[1][threadIdx.x] += sred[1][threadIdx.x + sft];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    red[0] = sred[0][0];
+    red[1] = sred[1][0];
     red[2] = (double)((volatile unsigned long long*)counts)[0];
     red[3] = (double)((volatile unsigned long long*)counts)[1];
     *counter = 0;

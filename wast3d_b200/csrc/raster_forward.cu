@@ -114,7 +114,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   const bool prefiltered, int* __restrict__ radii, float4* __restrict__ rec,
                   uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
                   uint8_t* __restrict__ clamped, uint2* __restrict__ rect_out, uint32_t* __restrict__ flags,
-                  const uint32_t* __restrict__ sample_bound_words, const bool cut_tiles) {
+                  const uint32_t* __restrict__ sample_bound_words, const bool cut_tiles, const bool vec3_loads) {
     __shared__ __align__(16) float s_sh[PRE_WARPS][32 * SH_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * PRE_THREADS + threadIdx.x;
@@ -133,11 +133,16 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     float2 ext = make_float2(0.f, 0.f);
 
     // means3D / scales: [P,3] AoS read with coalesced 16-byte loads (load_rows3)
-    __shared__ __align__(16) float s_v3[PRE_WARPS][96];
+    __shared__ __align__(16) float s_v3[PRE_WARPS][192];
     const int rows_valid_w = max(0, min(32, P - warp_first));
-    p_orig = load_rows3(means3D, warp_first, rows_valid_w, lane, s_v3[warp]);
     float3 sc_in = make_float3(0.f, 0.f, 0.f);
-    if (cov3D_precomp == nullptr) sc_in = load_rows3(scales, warp_first, rows_valid_w, lane, s_v3[warp]);
+    if (vec3_loads) {
+        load_rows3x2(means3D, cov3D_precomp == nullptr ? scales : nullptr, warp_first, rows_valid_w, lane, s_v3[warp],
+                     p_orig, sc_in);
+    } else if (live) {   // A/B: three strided 4-byte loads per array and lane
+        p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
+        if (cov3D_precomp == nullptr) sc_in = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
+    }
     if (live) {
         // in_frustum (auxiliary.h:139-164): near plane only
         p_view = xform_point_4x3(p_orig, viewmatrix);
@@ -869,6 +874,8 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         sample_bounds_kernel<<<148 * 2, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
         W3D_AFTER_LAUNCH(s, debug);
     }
+    // WAST3D_K1_VEC: 1 (default) = means3D / scales through coalesced 16-byte loads, 0 = strided scalar loads (A/B)
+    static const bool k1_vec = !(getenv("WAST3D_K1_VEC") && atoi(getenv("WAST3D_K1_VEC")) == 0);
     // colour_wait_event: SH -> RGB moves into its own kernel behind that event (see sh_colour_kernel)
     const bool defer_colour = prm->colour_wait_event != nullptr && prm->colors_precomp == nullptr;
     auto pre = prm->raw_params ? (defer_colour ? preprocess_kernel<true, false> : preprocess_kernel<true, true>)
@@ -878,7 +885,7 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         prm->opacities, prm->shs, prm->shs_rest, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
         prm->projmatrix, prm->campos, W, H, prm->tan_fovx, prm->tan_fovy, focal_x, focal_y, grid,
         prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.rect, g.totals + 1,
-        sample_bound_words, cut_tiles);
+        sample_bound_words, cut_tiles, k1_vec);
     W3D_AFTER_LAUNCH(s, debug);
     }
 

@@ -314,22 +314,35 @@ __device__ __forceinline__ void unstage_rows(float* __restrict__ g_rows, int row
 
 // ---- [P,3] arrays (means3D, scales) with 16-byte loads -----------------------------------------
 // The caller's tensors are AoS [P,3] (12 bytes per Gaussian): a warp's 32 rows are 384 contiguous bytes = 24
-// float4.  Lanes 0-23 fetch one float4 each (coalesced 16-byte loads: 12 sector requests instead of the 36 of
-// three strided 4-byte loads per lane), the warp transposes through 96 floats of shared memory (stride-3 reads
-// are bank-conflict free) and lane l gets row l.  s_tmp: this warp's 96-float scratch.
-__device__ __forceinline__ float3 load_rows3(const float* __restrict__ base, int warp_first, int rows_valid,
-                                             int lane, float* s_tmp) {
-    const float* g = base + 3 * (size_t)warp_first;
-    if (rows_valid == 32 && (((size_t)g) & 15) == 0) {
-        if (lane < 24) reinterpret_cast<float4*>(s_tmp)[lane] = __ldg(reinterpret_cast<const float4*>(g) + lane);
+// float4.  Lanes 0-23 fetch one float4 of each array (coalesced 16-byte loads: 12 sector requests per array
+// instead of the 36 of three strided 4-byte loads per lane; both arrays' loads are in flight together), the warp
+// transposes through shared memory (stride-3 reads are bank-conflict free) and lane l gets row l of both.
+// s_tmp: this warp's 192-float scratch, written once per kernel (no reuse, one __syncwarp).  b may be NULL.
+__device__ __forceinline__ void load_rows3x2(const float* __restrict__ a, const float* __restrict__ b, int warp_first,
+                                             int rows_valid, int lane, float* s_tmp, float3& va, float3& vb) {
+    const float* ga = a + 3 * (size_t)warp_first;
+    const float* gb = b ? b + 3 * (size_t)warp_first : nullptr;
+    const bool vec = rows_valid == 32 && (((size_t)ga) & 15) == 0 && (gb == nullptr || (((size_t)gb) & 15) == 0);
+    if (vec) {
+        if (lane < 24) {
+            const float4 x = __ldg(reinterpret_cast<const float4*>(ga) + lane);
+            float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gb) y = __ldg(reinterpret_cast<const float4*>(gb) + lane);
+            reinterpret_cast<float4*>(s_tmp)[lane] = x;
+            reinterpret_cast<float4*>(s_tmp + 96)[lane] = y;
+        }
     } else {
-        for (int i = lane; i < 3 * rows_valid; i += 32) s_tmp[i] = __ldg(g + i);
+        for (int i = lane; i < 3 * rows_valid; i += 32) {
+            s_tmp[i] = __ldg(ga + i);
+            s_tmp[96 + i] = gb ? __ldg(gb + i) : 0.f;
+        }
     }
     __syncwarp();
-    float3 v = make_float3(0.f, 0.f, 0.f);
-    if (lane < rows_valid) v = make_float3(s_tmp[3 * lane], s_tmp[3 * lane + 1], s_tmp[3 * lane + 2]);
-    __syncwarp();
-    return v;
+    va = vb = make_float3(0.f, 0.f, 0.f);
+    if (lane < rows_valid) {
+        va = make_float3(s_tmp[3 * lane], s_tmp[3 * lane + 1], s_tmp[3 * lane + 2]);
+        vb = make_float3(s_tmp[96 + 3 * lane], s_tmp[96 + 3 * lane + 1], s_tmp[96 + 3 * lane + 2]);
+    }
 }
 
 // ---- model-space activations (raw_params mode; scene/gaussian_model.py:26-41) ----------------

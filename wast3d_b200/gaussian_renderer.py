@@ -32,18 +32,27 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     """
     xyz = pc.get_xyz
     dev = xyz.device
-    # zero tensors that only exist to carry gradients out (reference :26-36)
-    screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
-    cam_view_depth = torch.zeros(xyz.shape[:-1] + (1,), dtype=xyz.dtype, device=dev,
-                                 requires_grad=True) + 0
     H, W = int(viewpoint_camera.image_height), int(viewpoint_camera.image_width)
     if sampling_offsets is None:
-        sampling_offsets = torch.rand(H, W, 2, device=dev) * -1
-    try:
-        screenspace_points.retain_grad()
-        cam_view_depth.retain_grad()
-    except Exception:
-        pass
+        sampling_offsets = torch.rand(H, W, 2, device=dev).mul_(-1)
+    fused = (override_color is None and not pipe.convert_SHs_python and not pipe.compute_cov3D_python
+             and getattr(pipe, "fused_activations", True) and model_supports_fusion(pc))
+    # zero tensors that only exist to carry gradients out (reference :26-36)
+    if fused:
+        # the model-space op never reads means2D: a stride-0 view of one zero row carries the gradient just as well
+        # (viewspace_points.grad is still the dense [P,3] tensor), without a 36 MB fill + add per render
+        screenspace_points = torch.zeros((1, xyz.shape[1]), dtype=xyz.dtype, device=dev).expand(xyz.shape[0], -1)
+        screenspace_points.requires_grad_(True)
+        cam_view_depth = None
+    else:
+        screenspace_points = torch.zeros_like(xyz, requires_grad=True) + 0
+        cam_view_depth = torch.zeros(xyz.shape[:-1] + (1,), dtype=xyz.dtype, device=dev,
+                                     requires_grad=True) + 0
+        try:
+            screenspace_points.retain_grad()
+            cam_view_depth.retain_grad()
+        except Exception:
+            pass
 
     settings = GaussianRasterizationSettings(
         image_height=H, image_width=W,
@@ -58,8 +67,7 @@ def render(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_modifier=
     # features of the last step() may still be in flight; only code behind this event may read them
     take = getattr(getattr(pc, "optimizer", None), "take_late_event", None)
     features_ready = take() if take is not None else None
-    if (override_color is None and not pipe.convert_SHs_python and not pipe.compute_cov3D_python
-            and getattr(pipe, "fused_activations", True) and model_supports_fusion(pc)):
+    if fused:
         image, depth, radii = rasterize_model(
             xyz, screenspace_points, pc._features_dc, pc._features_rest, pc._opacity, pc._scaling,
             pc._rotation, settings, sampling_offsets, getattr(pc, "grad_sink", None), features_ready)
