@@ -75,6 +75,10 @@ def parse():
                     help="1 = graph-safe forward (wast3d_raster_forward_async): the instance count is never read back by the "
                          "host, the binning buffer is sized from the largest count seen; 0 = the reference's protocol "
                          "(one blocking read of num_rendered per forward, rasterizer_impl.cu:283)")
+    ap.add_argument("--prefetch-projection", type=int, default=1, choices=[0, 1],
+                    help="single GPU, --sync backward: 1 = the backward kernel also projects every Gaussian for the NEXT step's "
+                         "camera from the parameters it has just updated (BackwardFusedAdam.prefetch_view); the next forward "
+                         "skips K1 and its re-read of all parameters; 0 = K1 in every forward")
     ap.add_argument("--tile-cut", type=int, default=1, choices=[0, 1],
                     help="1 = instantiate Gaussians only in tiles that can see alpha >= 1/255 (default), "
                          "0 = the reference's radius rectangles")
@@ -388,11 +392,13 @@ def workload_config(spec, n):
 
 
 ASYNC_FWD = [True]
+PREFETCH = [True]
 
 
 def implementation_info(sync):
     return {"grad_sync": sync, "peer_backend": PEER_BACKEND[0] if sync in ("peer", "records") else None,
-            "loss": LOSS_KIND[0], "graph_safe_forward": ASYNC_FWD[0]}
+            "loss": LOSS_KIND[0], "graph_safe_forward": ASYNC_FWD[0],
+            "projection_prefetch": bool(PREFETCH[0]) and sync == "backward"}
 
 
 def c1_case(dev, n_content=50_000, n_style=10_000):
@@ -475,6 +481,7 @@ def main():
     from wast3d_b200 import model_render
     model_render.set_async_forward(bool(args.async_forward))
     ASYNC_FWD[0] = bool(args.async_forward)
+    PREFETCH[0] = bool(args.prefetch_projection)
     if args.sync == "auto":
         args.sync = "peer" if world > 1 else "backward"
     if args.sync == "backward" and world > 1:
@@ -537,8 +544,26 @@ def main():
         while pending:
             read_loss(pending.pop(0))
 
-    def step(i, host_io):
+    prepared = {}   # step index -> camera object (host I/O arm: its matrices were copied from pinned memory)
+
+    def camera_for(i, host_io):
+        """The camera of step i.  Host I/O arm: a shallow copy whose matrices come from pinned host memory (copied on
+        the compute stream); prepared at most one step early so that the projection prefetch can announce it."""
         cam = wd.view_for_rank(cams, i, rank, world)
+        if not host_io:
+            return cam
+        if i not in prepared:
+            ci = cams.index(cam)
+            c2 = cam.to(dev)  # shallow copy
+            c2.world_view_transform = cam_host[ci][0].to(dev, non_blocking=True)
+            c2.full_proj_transform = cam_host[ci][1].to(dev, non_blocking=True)
+            c2.camera_center = cam_host[ci][2].to(dev, non_blocking=True)
+            prepared.clear()
+            prepared[i] = c2
+        return prepared[i]
+
+    def step(i, host_io):
+        cam = camera_for(i, host_io)
         k = i % 2
         if host_io:  # this step's inputs come from pinned host memory
             main = torch.cuda.current_stream(dev)
@@ -547,11 +572,6 @@ def main():
                 stage_tgt[k].copy_(tgt_host[k], non_blocking=True)
                 stage_dtgt[k].copy_(dtgt_host[k], non_blocking=True)
                 stage_full[k].record(copy_stream)
-            ci = cams.index(cam)
-            cam = cam.to(dev)  # shallow copy
-            cam.world_view_transform = cam_host[ci][0].to(dev, non_blocking=True)
-            cam.full_proj_transform = cam_host[ci][1].to(dev, non_blocking=True)
-            cam.camera_center = cam_host[ci][2].to(dev, non_blocking=True)
             tgt, dtgt = stage_tgt[k], stage_dtgt[k]
         else:
             tgt, dtgt = tgt_dev[k], dtgt_dev[k]
@@ -559,6 +579,13 @@ def main():
         if host_io:
             main.wait_event(stage_full[k])
         loss = style_loss(out, tgt, dtgt, fused=args.loss == "fused")
+        if args.sync == "backward" and args.prefetch_projection:
+            # the next step's camera is known (the loop draws it one iteration ahead): the per-Gaussian backward kernel
+            # projects for it from the parameters it has just updated, the next render() starts at the depth sort
+            nxt = camera_for(i + 1, host_io)
+            opt.prefetch_view(nxt)
+            if host_io:
+                prepared[i + 1] = nxt
         loss.backward()
         if host_io:
             stage_free[k].record(main)
@@ -750,13 +777,19 @@ def main():
         # reference's decomposition the same work is K8 92 + K9 535 + torch Adam 28 B/float x 59 = 2279 B.
         k_ms = avg["gaussian_backward"]
         alg_bytes = 1529.0 * spec.P
+        if args.prefetch_projection:
+            # + K1's outputs for the next view, written by the same kernel: radius 4 + depth key 4 + tile count 4 +
+            # rectangle 8 + clamp byte 1 per Gaussian, and the 48-byte render record of the visible ones
+            alg_bytes += 21.0 * spec.P + 48.0 * vis
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         traffic, traffic_src = traffic_of("gaussian_backward_adam_kernel")
-        roofline = {"bound": "hbm", "kernel": "gaussian_backward_kernel<RAW, ADAM> (K8+K9 + Adam in place)",
+        roofline = {"bound": "hbm", "kernel": "gaussian_backward_kernel<RAW, ADAM" + (", NEXT> (K8+K9 + Adam in place + K1 of the next view)"
+                                                                                  if args.prefetch_projection else "> (K8+K9 + Adam in place)"),
                     "achieved": round(achieved, 2), "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "traffic_source": traffic_src,
                     "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
-                    "units": "1529 B per Gaussian x P (every Gaussian's parameters and moments move, culled or not)",
+                    "units": "1529 B per Gaussian x P (every Gaussian's parameters and moments move, culled or not)"
+                             + (" + 21 B x P + 48 B x visible (next view's projection)" if args.prefetch_projection else ""),
                     "achieved_in_reference_units": round(2279.0 * spec.P / (k_ms * 1e-3) / 1e9, 2) if k_ms > 0 else 0.0}
     else:
         k_ms = avg["render_backward"]

@@ -28,7 +28,8 @@ enum wast3d_status {
     WAST3D_ERR_ALLOC = 3,            /* an allocation callback returned NULL                  */
     WAST3D_ERR_NO_DEVICE = 4,        /* no sm_100 device visible (there is no CPU fallback)   */
     WAST3D_ERR_OVERFLOW = 5,         /* instance count does not fit 31 bits                   */
-    WAST3D_ERR_NON_RGB = 6           /* reserved: non-RGB channels need precomputed colours   */
+    WAST3D_ERR_NON_RGB = 6,          /* reserved: non-RGB channels need precomputed colours   */
+    WAST3D_ERR_STALE_PROJECTION = 7  /* preprojected forward: sampling offsets outside the bounds the projection assumed */
 };
 
 const char* wast3d_strerror(int status);
@@ -87,6 +88,10 @@ typedef struct wast3d_raster_params {
      * side stream) while K1's geometry part and K2-K5 run; results are bit-identical.  The wait also
      * orders the render and everything after it on `stream` behind the event. */
     void* colour_wait_event;
+    /* ---- ABI v6: the geometry buffer returned by geom_alloc already holds K1's outputs for THIS view, written by
+     * wast3d_raster_backward_raw_adam_next (see there); `radii` must be the pointer given there.  wast3d_raster_forward*
+     * then starts at the depth sort. */
+    int preprojected;
 } wast3d_raster_params;
 
 /* Replaces RasterizeGaussiansCUDA -> CudaRasterizer::Rasterizer::forward
@@ -174,6 +179,35 @@ int wast3d_raster_backward_raw_adam(const wast3d_raster_params* prm, int num_ren
                                     const float* dL_dpix, const float* dL_ddepth,
                                     const wast3d_adam_group* groups, float* const* grads_out,
                                     float* dL_dmean2D, void* stream);
+
+/* wast3d_raster_backward_raw_adam that ALSO projects every Gaussian for the next view (ABI v6).  In an optimisation
+ * loop the next forward's K1 (preprocessCUDA, forward.cu:155-256) re-reads the parameters the optimizer has just
+ * written; here the per-Gaussian kernel evaluates it on the updated values while they are still in registers and writes
+ * K1's outputs into the NEXT call's geometry buffer: the next forward (wast3d_raster_params::preprojected = 1, same
+ * buffer returned by its geom_alloc callback, same radii pointer) skips K1 and its 236 B/Gaussian parameter read.
+ * Results are bit-identical to running K1 separately (one source, csrc/project.cuh).
+ * The tile cut needs bounds of the next call's sampling offsets before they exist: offset_min/max (the reference
+ * draws them in (-1, 0], gaussian_renderer/__init__.py:31); the next forward verifies its offsets against these
+ * bounds (status WAST3D_ERR_STALE_PROJECTION).  geom_buffer: wast3d_raster_geom_bytes(P) bytes, 128-byte aligned.
+ * The caller promises that nobody modifies the six parameter tensors between this call and that forward. */
+typedef struct wast3d_next_view {
+    int width, height;
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int D;                       /* active SH degree of the next view */
+    const float* viewmatrix;     /* DEVICE [16] */
+    const float* projmatrix;     /* DEVICE [16] */
+    const float* campos;         /* DEVICE [3]  */
+    void* geom_buffer;           /* DEVICE, the next forward's geometry buffer */
+    int* radii;                  /* DEVICE [P], the next forward's radii output (NULL -> internal) */
+    float offset_min_x, offset_max_x, offset_min_y, offset_max_y;
+} wast3d_next_view;
+size_t wast3d_raster_geom_bytes(int P);
+int wast3d_raster_backward_raw_adam_next(const wast3d_raster_params* prm, int num_rendered, const int* radii,
+                                         void* geom_buffer, void* binning_buffer, void* img_buffer,
+                                         const float* dL_dpix, const float* dL_ddepth,
+                                         const wast3d_adam_group* groups, float* const* grads_out,
+                                         float* dL_dmean2D, const wast3d_next_view* next, void* stream);
 
 /* Test/inspection hook (no reference equivalent is Python-visible; mirrors the state
  * structs of rasterizer_impl.h:29-65).  Any output may be NULL.

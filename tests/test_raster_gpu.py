@@ -784,3 +784,60 @@ def test_graph_safe_forward_is_bit_identical_and_reports_overflow(built):
         model_render.set_async_forward(prev)
         _lib.set_deterministic(prev_det)
         model_render._ASYNC_STATE.clear()
+
+
+def test_projection_prefetch_is_bit_identical(built):
+    """optim.BackwardFusedAdam.prefetch_view: the per-Gaussian backward kernel projects every Gaussian for the NEXT
+    camera from the values it has just updated (wast3d_raster_backward_raw_adam_next) and the next render() starts at the
+    depth sort.  With the deterministic tile backward the whole optimisation trajectory must be bit-identical to the
+    loop that runs K1 in every forward; a render() of a camera that was not announced falls back to K1; sampling
+    offsets outside the announced bounds are reported."""
+    from wast3d_b200 import _lib
+    from wast3d_b200.gaussian_renderer import render
+    from wast3d_b200.scene import GaussianModel, PipelineParams, orbit_cameras, synthetic_gaussians
+    arrs = synthetic_gaussians(30000, seed=31, log_scale_mu=-3.3)
+    cams = orbit_cameras(5, 4.03, 0.0, 0.6911, 208, 160, device="cuda", sphere=True)
+    bg = torch.tensor([0.2, 0.1, 0.0], device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    offs = [-torch.rand(160, 208, 2, device="cuda", generator=gen) for _ in range(6)]
+    order = [0, 3, 1, 4, 2, 0]
+
+    def loop(prefetch, wrong_announce=False):
+        m = GaussianModel.from_arrays(arrs, device="cuda")
+        m.spatial_lr_scale = 1.0
+        opt = m.training_setup(in_backward=True)
+        outs, used = [], []
+        for i, ci in enumerate(order):
+            used.append(opt.projection is not None)
+            out = render(cams[ci], m, PipelineParams(), bg, sampling_offsets=offs[i])
+            outs.append((out["render"].detach().clone(), out["depth"].detach().clone(), out["radii"].clone()))
+            if prefetch and i + 1 < len(order):
+                nxt = order[i + 1]
+                opt.prefetch_view(cams[(nxt + 1) % 5] if wrong_announce else cams[nxt])
+            (out["render"].square().mean() + 0.1 * out["depth"].mean()).backward()
+            opt.step(); opt.zero_grad()
+        return outs, [p.detach().clone() for p in m.parameters()], used
+
+    prev = _lib.set_deterministic(1)
+    try:
+        base, p_base, used0 = loop(False)
+        pre, p_pre, used1 = loop(True)
+        wrong, p_wrong, used2 = loop(True, wrong_announce=True)
+    finally:
+        _lib.set_deterministic(prev)
+    assert not any(used0) and used1 == [False] + [True] * 5 and used2 == [False] + [True] * 5
+    for res, ps in ((pre, p_pre), (wrong, p_wrong)):   # (the wrong announcement is dropped by the key check)
+        for a, b in zip(res, base):
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+        for a, b in zip(ps, p_base):
+            assert torch.equal(a, b)
+    # offsets outside the announced bounds: the pre-projected tile rectangles would be too small -> loud
+    m = GaussianModel.from_arrays(arrs, device="cuda")
+    m.spatial_lr_scale = 1.0
+    opt = m.training_setup(in_backward=True)
+    out = render(cams[0], m, PipelineParams(), bg, sampling_offsets=offs[0])
+    opt.prefetch_view(cams[1])
+    out["render"].mean().backward()
+    opt.step(); opt.zero_grad()
+    with pytest.raises(RuntimeError, match="sampling offsets exceed"):
+        render(cams[1], m, PipelineParams(), bg, sampling_offsets=offs[1] * 3.0)

@@ -30,7 +30,18 @@ class RasterParams(C.Structure):
         ("rotations", C.c_void_p), ("cov3D_precomp", C.c_void_p), ("viewmatrix", C.c_void_p),
         ("projmatrix", C.c_void_p), ("campos", C.c_void_p), ("sampling_offsets", C.c_void_p),
         ("raw_params", C.c_int), ("shs_rest", C.c_void_p), ("colour_wait_event", C.c_void_p),
+        ("preprojected", C.c_int),
     ]
+
+
+class NextView(C.Structure):
+    """struct wast3d_next_view (include/wast3d_b200.h)."""
+
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+                ("scale_modifier", C.c_float), ("D", C.c_int), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p),
+                ("campos", C.c_void_p), ("geom_buffer", C.c_void_p), ("radii", C.c_void_p),
+                ("offset_min_x", C.c_float), ("offset_max_x", C.c_float), ("offset_min_y", C.c_float),
+                ("offset_max_y", C.c_float)]
 
 
 class AdamSegment(C.Structure):
@@ -72,6 +83,9 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wast3d_raster_backward_raw_adam": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,
                                              C.POINTER(AdamGroup), C.POINTER(_vp), _vp, _vp]),
+    "wast3d_raster_backward_raw_adam_next": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                                  C.POINTER(AdamGroup), C.POINTER(_vp), _vp, _vp, _vp]),
+    "wast3d_raster_geom_bytes": (_sz, [_i]),
     "wast3d_raster_export_state": (_i, [C.POINTER(RasterParams), _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp]),
     "wast3d_mark_visible": (_i, [_i, _vp, _vp, _vp, _vp, _vp]),
@@ -229,6 +243,36 @@ class GrowBuffer:
         (a ~10 ms stall every few dozen steps)."""
         t, self.tensor, self.cb = self.tensor, None, None
         return t
+
+
+class FixedBuffer:
+    """GrowBuffer stand-in that hands the library one pre-filled tensor (the geometry buffer a previous
+    wast3d_raster_backward_raw_adam_next already wrote K1's outputs into)."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+        self.error = None
+
+        def _alloc(nbytes, _user):
+            if self.tensor is None or nbytes > self.tensor.numel():
+                self.error = RuntimeError("wast3d_b200: pre-projected geometry buffer is too small")
+                return None
+            return self.tensor.data_ptr()
+
+        self.cb = ALLOC_FN(_alloc)
+
+    def take(self):
+        t, self.tensor, self.cb = self.tensor, None, None
+        return t
+
+
+def geom_buffer(device, P: int) -> torch.Tensor:
+    """A geometry buffer for P Gaussians (wast3d_raster_geom_bytes), sized like GrowBuffer(device, 'geom') would."""
+    gb = GrowBuffer(device, "geom")
+    ptr = gb.cb(int(load().wast3d_raster_geom_bytes(int(P))), None)
+    if gb.error is not None or not ptr:
+        raise gb.error or RuntimeError("geometry buffer allocation failed")
+    return gb.take()
 
 
 def set_tile_cut(mode: int) -> int:

@@ -93,6 +93,8 @@ extern "C" const char* wast3d_strerror(int status) {
         case WAST3D_ERR_NO_DEVICE: return "no sm_100 CUDA device (this library has no CPU fallback)";
         case WAST3D_ERR_OVERFLOW: return "instance count overflows 31 bits";
         case WAST3D_ERR_NON_RGB: return "For non-RGB, provide precomputed Gaussian colors!";
+        case WAST3D_ERR_STALE_PROJECTION:
+            return "preprojected forward: the sampling offsets exceed the bounds the projection assumed";
         default: return "unknown status";
     }
 }

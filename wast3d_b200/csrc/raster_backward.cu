@@ -22,7 +22,7 @@
 //    culled Gaussians), so no output memset is needed.
 //  Summation order across pixels differs from the reference's atomics (both are unordered);
 //  gradients agree to fp32 rounding, not bitwise (tests state the tolerance per tensor).
-#include "raster_math.cuh"
+#include "project.cuh"
 #include <atomic>
 #include <cmath>
 #include <cstdlib>
@@ -571,22 +571,25 @@ struct AdamFused {
 __device__ __forceinline__ float adam_elem(float p, float g, float& m, float& v, const AdamSlot& s) {
     return adam_update(p, g, m, v, s.one_minus_b1, s.b2, s.one_minus_b2, s.step_size, s.inv_bc2_sqrt, s.eps);
 }
+// updated parameter values are also returned in p_new (the next view's projection consumes them from registers)
 template <int N>
-__device__ __forceinline__ void adam_small(const AdamSlot& s, size_t base, const float (&g)[N]) {
-    float p[N], m[N], v[N];
+__device__ __forceinline__ void adam_small(const AdamSlot& s, size_t base, const float (&g)[N], float (&p_new)[N]) {
+    float m[N], v[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) { p[k] = s.p[base + k]; m[k] = s.m[base + k]; v[k] = s.v[base + k]; }
+    for (int k = 0; k < N; ++k) { p_new[k] = s.p[base + k]; m[k] = s.m[base + k]; v[k] = s.v[base + k]; }
 #pragma unroll
-    for (int k = 0; k < N; ++k) p[k] = adam_elem(p[k], g[k], m[k], v[k], s);
+    for (int k = 0; k < N; ++k) p_new[k] = adam_elem(p_new[k], g[k], m[k], v[k], s);
 #pragma unroll
-    for (int k = 0; k < N; ++k) { s.p[base + k] = p[k]; s.m[base + k] = m[k]; s.v[base + k] = v[k]; }
+    for (int k = 0; k < N; ++k) { s.p[base + k] = p_new[k]; s.m[base + k] = m[k]; s.v[base + k] = v[k]; }
 }
 // Adam over a warp's contiguous block of `total` elements whose gradients sit in shared memory.
 // U float4 per lane are loaded from each of p / m / v before any of them is consumed (3U independent 16-byte
 // loads in flight per lane): this loop moves 76% of the fused kernel's bytes and is latency bound otherwise.
-template <int U>
+// KEEP: the updated parameters replace the gradients in shared memory (same linear layout), for a consumer in the
+// same warp after a __syncwarp (the next view's SH -> RGB).
+template <int U, bool KEEP>
 __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base, int total,
-                                                 const float* s_grad, float* g_out, int lane) {
+                                                 float* s_grad, float* g_out, int lane) {
     float* P_ = s.p + base;
     float* M_ = s.m + base;
     float* V_ = s.v + base;
@@ -617,6 +620,7 @@ __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base,
                     __stcs(M4 + q, m[u]);
                     __stcs(V4 + q, v[u]);
                     if (g_out) reinterpret_cast<float4*>(g_out + base)[q] = g;
+                    if (KEEP) *reinterpret_cast<float4*>(s_grad + 4 * q) = p[u];
                 }
             }
         }
@@ -624,10 +628,12 @@ __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base,
         for (int q = lane; q < total; q += 32) {
             const float g = s_grad[q];
             float m = M_[q], v = V_[q];
-            P_[q] = adam_elem(P_[q], g, m, v, s);
+            const float pn = adam_elem(P_[q], g, m, v, s);
+            P_[q] = pn;
             M_[q] = m;
             V_[q] = v;
             if (g_out) g_out[base + q] = g;
+            if (KEEP) s_grad[q] = pn;
         }
     }
 }
@@ -638,7 +644,23 @@ __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base,
 // dL_dsh is dL/d_features_dc [P,1,3] and dL_dsh_rest is dL/d_features_rest [P,M-1,3].
 // ADAM (RAW only): apply the optimizer update in place (AdamFused); the gradient outputs of the six
 // leaves become optional (non-NULL ones are still written: tests).
-template <bool RAW, bool ADAM, int ADAM_U = 4>
+// NEXT (RAW + ADAM only; wast3d_next_view): after the update, every Gaussian is projected for the NEXT view from the
+// parameter values this thread has just computed — K1 of the next forward pass without its 236 B/Gaussian parameter
+// read and without its launch (project.cuh: the very statements preprocess_kernel executes).
+struct NextProj {
+    ProjView view;
+    const float* campos;
+    int D;
+    int* radii;
+    float4* rec;
+    uint32_t* depth_key;
+    uint32_t* tiles_touched;
+    uint8_t* clamped;
+    uint2* rect;
+    uint32_t* bound_words;   // [4] order keys of the offset bounds the tile cut assumed (checked by the next forward)
+};
+
+template <bool RAW, bool ADAM, int ADAM_U = 4, bool NEXT = false>
 __global__ void __launch_bounds__(GB_THREADS)
 gaussian_backward_kernel(const int P, const int D, const int M, const float* __restrict__ means3D,
                          const int* __restrict__ radii, const float* __restrict__ shs,
@@ -655,7 +677,8 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
                          float* __restrict__ dL_dcov3D, float* __restrict__ dL_dsh,
                          float* __restrict__ dL_dsh_rest,
                          float* __restrict__ dL_dscale, float* __restrict__ dL_drot,
-                         float* __restrict__ dL_dviewdepth_out, const __grid_constant__ AdamFused af) {
+                         float* __restrict__ dL_dviewdepth_out, const __grid_constant__ AdamFused af,
+                         const __grid_constant__ NextProj nx) {
     __shared__ __align__(16) float s_sh[GB_WARPS][32 * GB_SH_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * GB_THREADS + threadIdx.x;
@@ -850,6 +873,7 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         }
     }
 
+    float new_dc[3] = {0.f, 0.f, 0.f};   // updated _features_dc of this Gaussian (ADAM)
     // ---- backward.cu:20-139 (SH): staged in, gradients staged out through the same rows
     if (shs != nullptr) {
         const unsigned need = __ballot_sync(0xffffffffu, vis);
@@ -958,12 +982,13 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
             __syncwarp();
             if (RAW && ADAM) {
                 if (live) {
-                    adam_small<3>(af.g[1], 3 * (size_t)idx, dc_grad);
+                    adam_small<3>(af.g[1], 3 * (size_t)idx, dc_grad, new_dc);
                     if (dL_dsh) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
                 }
                 if (rest_floats > 0)
-                    adam_rows_linear<ADAM_U>(af.g[2], (size_t)warp_first * rest_floats, rows_valid * rest_floats, s_sh[warp],
-                                     dL_dsh_rest, lane);
+                    adam_rows_linear<ADAM_U, NEXT>(af.g[2], (size_t)warp_first * rest_floats, rows_valid * rest_floats,
+                                                   s_sh[warp], dL_dsh_rest, lane);
+                if (NEXT) __syncwarp();   // the updated rows are read per Gaussian below
             } else if (RAW) {
                 // NULL feature outputs: the caller rebuilds the SH gradient elsewhere (colour-record exchange)
                 if (live && dL_dsh) { dL_dsh[3 * idx] = dc_grad[0]; dL_dsh[3 * idx + 1] = dc_grad[1]; dL_dsh[3 * idx + 2] = dc_grad[2]; }
@@ -1000,10 +1025,31 @@ gaussian_backward_kernel(const int P, const int D, const int M, const float* __r
         const float go[1] = {dopac};
         const float gs[3] = {dscale.x, dscale.y, dscale.z};
         const float gr[4] = {drot.x, drot.y, drot.z, drot.w};
-        adam_small<3>(af.g[0], 3 * (size_t)idx, gx);
-        adam_small<1>(af.g[3], (size_t)idx, go);
-        adam_small<3>(af.g[4], 3 * (size_t)idx, gs);
-        adam_small<4>(af.g[5], 4 * (size_t)idx, gr);
+        float nxyz[3], nop[1], nsc[3], nrot[4];
+        adam_small<3>(af.g[0], 3 * (size_t)idx, gx, nxyz);
+        adam_small<1>(af.g[3], (size_t)idx, go, nop);
+        adam_small<3>(af.g[4], 3 * (size_t)idx, gs, nsc);
+        adam_small<4>(af.g[5], 4 * (size_t)idx, gr, nrot);
+        if (NEXT) {
+            // K1 of the next view on the fresh values (preprocess_kernel<RAW = true, COLOUR = true>, same statements)
+            if (idx == 0) {
+                nx.bound_words[0] = float_order_key(nx.view.sb.max_x);
+                nx.bound_words[1] = float_order_key(-nx.view.sb.min_x);
+                nx.bound_words[2] = float_order_key(nx.view.sb.max_y);
+                nx.bound_words[3] = float_order_key(-nx.view.sb.min_y);
+            }
+            const float3 p_new = make_float3(nxyz[0], nxyz[1], nxyz[2]);
+            const Projection pr = project_gaussian<true>(p_new, make_float3(nsc[0], nsc[1], nsc[2]), nullptr,
+                                                         make_float4(nrot[0], nrot[1], nrot[2], nrot[3]), nullptr, nop[0],
+                                                         nullptr, nx.view);
+            float3 rgb = make_float3(0.f, 0.f, 0.f);
+            unsigned clamp_bits = 0;
+            if (pr.visible) {
+                const float3 cam = make_float3(nx.campos[0], nx.campos[1], nx.campos[2]);
+                rgb = sh_to_rgb(nx.D, new_dc, s_sh[warp] + lane * (3 * (M - 1)) - 3, p_new, cam, &clamp_bits);
+            }
+            store_projection(idx, pr, rgb, clamp_bits, nx.radii, nx.rec, nx.depth_key, nx.tiles_touched, nx.clamped, nx.rect);
+        }
     }
     if (!ADAM || dL_dopacity) dL_dopacity[idx] = dopac;
     if (!ADAM || dL_dmean3D) {
@@ -1046,7 +1092,7 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
                                 float* dL_dconic, float* dL_dopacity, float* dL_dcolor, float* dL_dmean3D,
                                 float* dL_dcov3D, float* dL_dsh, float* dL_dsh_rest, float* dL_dscale,
                                 float* dL_drot, float* dL_dcamViewDepth, cudaStream_t s,
-                                const AdamFused* adam = nullptr) {
+                                const AdamFused* adam = nullptr, const wast3d_next_view* next = nullptr) {
     const int P = prm->P, W = prm->width, H = prm->height;
     const bool debug = prm->debug != 0;
     const size_t N = (size_t)W * H;
@@ -1161,13 +1207,48 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
                               : gaussian_backward_kernel<false, false>;
     AdamFused af = adam ? *adam : AdamFused{};
     af.l2_prefetch = l2_prefetch_enabled() ? 1 : 0;
+    NextProj nx{};
+    if (next != nullptr) {
+        // project every Gaussian for the next view inside this kernel (wast3d_next_view)
+        if (!adam || !prm->raw_params || !next->geom_buffer || !next->viewmatrix || !next->projmatrix || !next->campos ||
+            next->width <= 0 || next->height <= 0 || next->D < 0 || next->D > 3 || prm->M < (next->D + 1) * (next->D + 1))
+            return WAST3D_ERR_INVALID_ARGUMENT;
+        GeomState gn = GeomState::carve(next->geom_buffer, P, nullptr);
+        const dim3 ngrid((next->width + TILE_X - 1) / TILE_X, (next->height + TILE_Y - 1) / TILE_Y, 1);
+        nx.view.viewmatrix = next->viewmatrix;
+        nx.view.projmatrix = next->projmatrix;
+        nx.view.W = next->width;
+        nx.view.H = next->height;
+        nx.view.tan_fovx = next->tan_fovx;
+        nx.view.tan_fovy = next->tan_fovy;
+        nx.view.focal_y = next->height / (2.0f * next->tan_fovy);   // rasterizer_impl.cu:224-225
+        nx.view.focal_x = next->width / (2.0f * next->tan_fovx);
+        nx.view.grid_x = ngrid.x;
+        nx.view.grid_y = ngrid.y;
+        nx.view.scale_modifier = next->scale_modifier;
+        nx.view.cut_tiles = wast3d_set_tile_cut(-1) != 0;
+        nx.view.sb.min_x = next->offset_min_x;
+        nx.view.sb.max_x = next->offset_max_x;
+        nx.view.sb.min_y = next->offset_min_y;
+        nx.view.sb.max_y = next->offset_max_y;
+        nx.campos = next->campos;
+        nx.D = next->D;
+        nx.radii = next->radii ? next->radii : gn.internal_radii;
+        nx.rec = gn.rec;
+        nx.depth_key = gn.depth_key;
+        nx.tiles_touched = gn.tiles_touched;
+        nx.clamped = gn.clamped;
+        nx.rect = gn.rect;
+        nx.bound_words = gn.totals + 16;
+        gb = gaussian_backward_kernel<true, true, 4, true>;
+    }
     gb<<<(P + GB_THREADS - 1) / GB_THREADS, GB_THREADS, 0, s>>>(
         P, prm->D, prm->M, prm->means3D, radii, prm->shs, prm->shs_rest, g.rec, g.clamped, prm->scales,
         prm->rotations, prm->scale_modifier, prm->cov3D_precomp, prm->viewmatrix, prm->projmatrix,
         prm->campos, focal_x, focal_y, prm->tan_fovx, prm->tan_fovy, (float)(0.5 * W), (float)(0.5 * H), g.grad_rec,
         dL_dmean2D, dL_dconic,
         dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dsh_rest, dL_dscale, dL_drot,
-        dL_dcamViewDepth, af);
+        dL_dcamViewDepth, af, nx);
     W3D_AFTER_LAUNCH(s, debug);
     return WAST3D_OK;
 }
@@ -1227,6 +1308,22 @@ extern "C" int wast3d_raster_backward_raw_adam(const wast3d_raster_params* prm, 
                                                void* img_buffer, const float* dL_dpix, const float* dL_ddepth,
                                                const wast3d_adam_group* groups, float* const* grads_out,
                                                float* dL_dmean2D, void* stream_v) {
+    return wast3d_raster_backward_raw_adam_next(prm, num_rendered, radii, geom_buffer, binning_buffer, img_buffer, dL_dpix,
+                                                dL_ddepth, groups, grads_out, dL_dmean2D, nullptr, stream_v);
+}
+
+extern "C" size_t wast3d_raster_geom_bytes(int P) {
+    if (P < 0) return 0;
+    size_t bytes = 0;
+    GeomState::carve(nullptr, (size_t)P, &bytes);
+    return bytes;
+}
+
+extern "C" int wast3d_raster_backward_raw_adam_next(const wast3d_raster_params* prm, int num_rendered,
+                                                    const int* radii, void* geom_buffer, void* binning_buffer,
+                                                    void* img_buffer, const float* dL_dpix, const float* dL_ddepth,
+                                                    const wast3d_adam_group* groups, float* const* grads_out,
+                                                    float* dL_dmean2D, const wast3d_next_view* next, void* stream_v) {
     int st = validate_params(prm, false);
     if (st != WAST3D_OK) return st;
     if (!prm->raw_params || !groups) return WAST3D_ERR_INVALID_ARGUMENT;
@@ -1259,5 +1356,5 @@ extern "C" int wast3d_raster_backward_raw_adam(const wast3d_raster_params* prm, 
         for (int k = 0; k < 6; ++k) go[k] = grads_out[k];
     return raster_backward_impl(prm, num_rendered, radii, geom_buffer, binning_buffer, img_buffer, dL_dpix,
                                 dL_ddepth, dL_dmean2D, nullptr, go[3], nullptr, go[0], nullptr, go[1], go[2],
-                                go[4], go[5], nullptr, (cudaStream_t)stream_v, &af);
+                                go[4], go[5], nullptr, (cudaStream_t)stream_v, &af, next);
 }

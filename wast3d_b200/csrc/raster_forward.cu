@@ -19,7 +19,7 @@
 //    32 lanes test 32 Gaussians against the warp's 8x4 pixel block at once and the blend loop
 //    only visits survivors; warps retire independently (ballot) and the block leaves when all
 //    have (one __syncthreads_and per batch).
-#include "raster_math.cuh"
+#include "project.cuh"
 #include <atomic>
 #include <cstdlib>
 
@@ -29,71 +29,6 @@ constexpr int PRE_THREADS = 128;
 constexpr int PRE_WARPS = PRE_THREADS / 32;
 constexpr int SH_MAX_ROW = 48;             // M = 16 coefficients x RGB
 constexpr int SH_STRIDE = SH_MAX_ROW + 1;  // odd -> conflict-free per-Gaussian reads
-
-// forward.cu:20-71.  `sh` points at this Gaussian's staged row (k-th coefficient at sh[3k..],
-// k >= 1); the degree-0 coefficient is read from sh_dc (== sh unless the model-space path keeps
-// _features_dc and _features_rest apart).
-__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* sh_dc, const float* sh, float3 pos,
-                                            float3 campos, unsigned* clamped_bits) {
-    float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
-    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-    dir.x = dir.x / len;
-    dir.y = dir.y / len;
-    dir.z = dir.z / len;
-    float res[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        float r = SH_C0 * sh_dc[c];
-        if (deg > 0) {
-            const float x = dir.x, y = dir.y, z = dir.z;
-            r = r - SH_C1 * y * sh[3 + c] + SH_C1 * z * sh[6 + c] - SH_C1 * x * sh[9 + c];
-            if (deg > 1) {
-                const float xx = x * x, yy = y * y, zz = z * z;
-                const float xy = x * y, yz = y * z, xz = x * z;
-                r = r + SH_C2[0] * xy * sh[12 + c] + SH_C2[1] * yz * sh[15 + c] +
-                    SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + SH_C2[3] * xz * sh[21 + c] +
-                    SH_C2[4] * (xx - yy) * sh[24 + c];
-                if (deg > 2) {
-                    r = r + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] +
-                        SH_C3[1] * xy * z * sh[30 + c] +
-                        SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
-                        SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
-                        SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] +
-                        SH_C3[5] * z * (xx - yy) * sh[42 + c] +
-                        SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
-                }
-            }
-        }
-        r += 0.5f;
-        res[c] = r;
-    }
-    unsigned bits = 0;
-    if (res[0] < 0) bits |= 1u;
-    if (res[1] < 0) bits |= 2u;
-    if (res[2] < 0) bits |= 4u;
-    *clamped_bits = bits;
-    return make_float3(fmaxf(res[0], 0.0f), fmaxf(res[1], 0.0f), fmaxf(res[2], 0.0f));
-}
-
-// Half extents of the axis-aligned box around { d : alpha(d) >= 1/255 } for conic (A,B,C) and
-// opacity o: alpha = o*exp(-q(d)), q = 0.5*(A dx^2 + C dy^2) + B dx dy, so the region is
-// q <= tau = ln(255 o) and |dx| <= sqrt(2 tau C / det), |dy| <= sqrt(2 tau A / det).
-// tau is padded for fp32 evaluation error of q (which grows with the conditioning A*C/det);
-// the box is used only to skip pixel blocks where the reference's per-pixel test
-// (forward.cu:355) is certain to reject.
-__device__ __forceinline__ float2 cutoff_extent(float A, float B, float C, float o) {
-    if (!(o >= 1.0f / 255.0f)) return make_float2(-1.0f, -1.0f);  // alpha <= o < 1/255 always
-    const double det = (double)A * (double)C - (double)B * (double)B;
-    const float inf = __int_as_float(0x7f800000);
-    if (!(det > 0.0) || !(A > 0.f) || !(C > 0.f)) return make_float2(inf, inf);
-    const double tau0 = log(255.0 * (double)o);
-    const double kappa = (double)A * (double)C / det;
-    const double tau = tau0 + 1e-3 + tau0 * (1e-3 + 4e-6 * kappa);
-    const float hx = (float)(sqrt(2.0 * tau * (double)C / det) * 1.001 + 0.05);
-    const float hy = (float)(sqrt(2.0 * tau * (double)A / det) * 1.001 + 0.05);
-    if (!(hx == hx) || !(hy == hy)) return make_float2(inf, inf);
-    return make_float2(hx, hy);
-}
 
 // RAW: model-space inputs (wast3d_raster_params::raw_params) — activations applied here.
 // COLOUR: true = SH -> RGB evaluated here (one kernel, as in the reference's preprocessCUDA);
@@ -121,18 +56,9 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     const int warp_first = blockIdx.x * PRE_THREADS + warp * 32;
     const bool live = idx < P;
 
-    bool visible = false;
-    int my_radius_i = 0;
-    uint32_t n_tiles = 0;
-    uint2 my_rect = make_uint2(0u, 0u);
     float3 p_orig = make_float3(0.f, 0.f, 0.f);
-    float3 p_view = make_float3(0.f, 0.f, 0.f);
-    float2 point_image = make_float2(0.f, 0.f);
-    float3 conic = make_float3(0.f, 0.f, 0.f);
-    float opac = 0.f;
-    float2 ext = make_float2(0.f, 0.f);
 
-    // means3D / scales: [P,3] AoS read with coalesced 16-byte loads (load_rows3)
+    // means3D / scales: [P,3] AoS read with coalesced 16-byte loads (load_rows3x2)
     __shared__ __align__(16) float s_v3[PRE_WARPS][192];
     const int rows_valid_w = max(0, min(32, P - warp_first));
     float3 sc_in = make_float3(0.f, 0.f, 0.f);
@@ -143,63 +69,18 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
         p_orig = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
         if (cov3D_precomp == nullptr) sc_in = make_float3(scales[3 * idx], scales[3 * idx + 1], scales[3 * idx + 2]);
     }
+    ProjView pv;
+    pv.viewmatrix = viewmatrix; pv.projmatrix = projmatrix;
+    pv.W = W; pv.H = H; pv.tan_fovx = tan_fovx; pv.tan_fovy = tan_fovy; pv.focal_x = focal_x; pv.focal_y = focal_y;
+    pv.grid_x = grid.x; pv.grid_y = grid.y; pv.scale_modifier = scale_modifier; pv.cut_tiles = cut_tiles;
+    pv.sb = load_sample_bounds(sample_bound_words);
+    Projection pr = Projection::none();
     if (live) {
-        // in_frustum (auxiliary.h:139-164): near plane only
-        p_view = xform_point_4x3(p_orig, viewmatrix);
-        if (p_view.z <= 0.2f) {
-            if (prefiltered) atomicOr(flags, 1u);  // reference: printf + __trap()
-        } else {
-            float4 p_hom = xform_point_4x4(p_orig, projmatrix);
-            float p_w = 1.0f / (p_hom.w + 0.0000001f);
-            float3 p_proj = make_float3(p_hom.x * p_w, p_hom.y * p_w, p_hom.z * p_w);
-
-            float cov6[6];
-            if (cov3D_precomp != nullptr) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) cov6[k] = cov3D_precomp[6 * idx + k];
-            } else {
-                float3 sc = sc_in;
-                float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
-                if (RAW) {
-                    sc = act_exp3(sc);
-                    q = act_normalize4(q, quat_denom(q));
-                }
-                cov3d_from_scale_rot(sc, scale_modifier, q, cov6);
-            }
-            float3 cov = cov2d(p_orig, focal_x, focal_y, tan_fovx, tan_fovy, cov6, viewmatrix, nullptr);
-
-            // EWA inverse (forward.cu:219-223)
-            float det = (cov.x * cov.z - cov.y * cov.y);
-            if (det != 0.0f) {
-                float det_inv = 1.f / det;
-                conic = make_float3(cov.z * det_inv, -cov.y * det_inv, cov.x * det_inv);
-                float mid = 0.5f * (cov.x + cov.z);
-                float lambda1 = mid + sqrt(max(0.1f, mid * mid - det));
-                float lambda2 = mid - sqrt(max(0.1f, mid * mid - det));
-                float my_radius = ceil(3.f * sqrt(max(lambda1, lambda2)));
-                point_image = make_float2(ndc_to_pix(p_proj.x, W), ndc_to_pix(p_proj.y, H));
-                uint2 rect_min, rect_max;
-                tile_rect(point_image, (int)my_radius, rect_min, rect_max, grid);
-                n_tiles = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
-                if (n_tiles != 0) {
-                    visible = true;
-                    my_radius_i = (int)my_radius;
-                    opac = RAW ? act_sigmoid(opacities[idx]) : opacities[idx];
-                    ext = cutoff_extent(conic.x, conic.y, conic.z, opac);
-                    if (cut_tiles) {
-                        // only the tiles that hold a sample inside the alpha >= 1/255 box are instantiated
-                        tile_rect_cut(point_image, my_radius_i, ext.x, ext.y, load_sample_bounds(sample_bound_words),
-                                      rect_min, rect_max, grid);
-                        n_tiles = (rect_max.y - rect_min.y) * (rect_max.x - rect_min.x);
-                    }
-                    // the rectangle the instance emitter expands (8 bytes instead of re-deriving it from the record)
-                    if (n_tiles != 0)
-                        my_rect = make_uint2(rect_min.x | (rect_min.y << 16),
-                                             (rect_max.x - rect_min.x) | ((rect_max.y - rect_min.y) << 16));
-                }
-            }
-        }
+        pr = project_gaussian<RAW>(p_orig, sc_in, rotations ? rotations + 4 * (size_t)idx : nullptr, make_float4(0.f, 0.f, 0.f, 0.f),
+                                   opacities + idx, 0.f, cov3D_precomp ? cov3D_precomp + 6 * (size_t)idx : nullptr, pv);
+        if (pr.behind && prefiltered) atomicOr(flags, 1u);  // reference: printf + __trap()
     }
+    const bool visible = pr.visible;
 
     // colour: SH -> RGB for survivors only
     float3 rgb = make_float3(0.f, 0.f, 0.f);
@@ -235,16 +116,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     }
 
     if (!live) return;
-    radii[idx] = my_radius_i;
-    tiles_touched[idx] = visible ? n_tiles : 0u;
-    rect_out[idx] = my_rect;
-    clamped[idx] = (uint8_t)(clamp_bits | (visible ? 8u : 0u));  // bit 3: render record written
-    depth_key[idx] = visible ? __float_as_uint(p_view.z) : CULLED_KEY;
-    if (visible) {
-        rec[3 * idx + 0] = make_float4(point_image.x, point_image.y, p_view.z, ext.x);
-        rec[3 * idx + 1] = make_float4(conic.x, conic.y, conic.z, opac);
-        rec[3 * idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, ext.y);
-    }
+    store_projection(idx, pr, rgb, clamp_bits, radii, rec, depth_key, tiles_touched, clamped, rect_out);
 }
 
 // Deferred colour pass (forward.cu:20-71,241-246 for the Gaussians preprocess_kernel<.., false> kept):
@@ -465,6 +337,14 @@ tile_digit_hist_kernel(int num_tiles, const uint32_t* __restrict__ tile_count, i
 
 __global__ void tile_copy_flags_kernel(const uint32_t* a, const uint32_t* b, uint32_t* out) {
     if (threadIdx.x == 0) *out = (a ? *a : 0u) | (b ? *b : 0u);
+}
+// Preprojected forward: the tile rectangles were cut with ASSUMED bounds of the sampling offsets (words: order keys
+// of max ox, max -ox, max oy, max -oy); offsets outside them could see Gaussians in tiles that were not instantiated.
+__global__ void check_projection_bounds_kernel(const uint32_t* __restrict__ actual, const uint32_t* __restrict__ assumed,
+                                               uint32_t* __restrict__ flags) {
+    if (threadIdx.x != 0) return;
+    const SampleBounds a = load_sample_bounds(actual), b = load_sample_bounds(assumed);
+    if (!(a.max_x <= b.max_x) || !(a.min_x >= b.min_x) || !(a.max_y <= b.max_y) || !(a.min_y >= b.min_y)) atomicOr(flags, 2u);
 }
 // status_dev[0..3] = {num_rendered, prefiltered violated, look-back time-out, capacity overflow}
 __global__ void copy_status_kernel(const uint32_t* __restrict__ totals, uint32_t* __restrict__ status) {
@@ -865,10 +745,24 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
     const float focal_y = H / (2.0f * prm->tan_fovy);
     const float focal_x = W / (2.0f * prm->tan_fovx);
 
-    W3D_CUDA_TRY(cudaMemsetAsync(g.totals, 0, 32 * sizeof(uint32_t), s));
+    // preprojected (wast3d_raster_backward_raw_adam_next wrote K1's outputs for this view into the buffer): words
+    // 16..19 of totals carry the offset bounds that projection assumed and must survive the reset
+    const bool pre = prm->preprojected != 0;
+    if (pre && (!prm->raw_params || prm->colour_wait_event != nullptr)) return WAST3D_ERR_INVALID_ARGUMENT;
+    W3D_CUDA_TRY(cudaMemsetAsync(g.totals, 0, (pre ? 16 : 32) * sizeof(uint32_t), s));
     const bool cut_tiles = tile_cut_mode() != 0;
     uint32_t* sample_bound_words = g.totals + 8;  // zero = no offsets
-    {
+    if (pre) {
+        ProfScope ps(PS_PREPROCESS, s);
+        if (cut_tiles) {
+            if (prm->sampling_offsets != nullptr) {
+                sample_bounds_kernel<<<148 * 2, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
+                W3D_AFTER_LAUNCH(s, debug);
+            }
+            check_projection_bounds_kernel<<<1, 32, 0, s>>>(sample_bound_words, g.totals + 16, g.totals + 1);
+            W3D_AFTER_LAUNCH(s, debug);
+        }
+    } else {
     ProfScope ps(PS_PREPROCESS, s);
     if (cut_tiles && prm->sampling_offsets != nullptr) {
         sample_bounds_kernel<<<148 * 2, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
@@ -935,6 +829,7 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         W3D_CUDA_TRY(cudaMemcpyAsync(host_totals, g.totals, sizeof(host_totals), cudaMemcpyDeviceToHost, s));
         W3D_CUDA_TRY(cudaStreamSynchronize(s));
         if (host_totals[1] & 1u) return WAST3D_ERR_INVALID_ARGUMENT;  // prefiltered violated
+        if (host_totals[1] & 2u) return WAST3D_ERR_STALE_PROJECTION;
         if (host_totals[2]) {
             set_last_cuda_error(cudaErrorLaunchTimeout, __FILE__, __LINE__);
             return WAST3D_ERR_CUDA;

@@ -21,7 +21,7 @@ NUM_CHANNELS = 3  # cuda_rasterizer/config.h:15
 
 def _params(keep, *, P, D, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefiltered, debug, bg,
             means3D, sh, colors, opacity, scales, rotations, cov3D_precomp, viewmatrix, projmatrix,
-            campos, sampling_offsets, raw_params=False, sh_rest=None, colour_wait_event=None):
+            campos, sampling_offsets, raw_params=False, sh_rest=None, colour_wait_event=None, preprojected=False):
     f = _lib.fptr
     return _lib.RasterParams(
         P=P, D=int(D), M=M, width=int(W), height=int(H), tan_fovx=float(tan_fovx),
@@ -32,7 +32,7 @@ def _params(keep, *, P, D, M, W, H, tan_fovx, tan_fovy, scale_modifier, prefilte
         rotations=f(rotations, keep), cov3D_precomp=f(cov3D_precomp, keep),
         viewmatrix=f(viewmatrix, keep), projmatrix=f(projmatrix, keep), campos=f(campos, keep),
         sampling_offsets=f(sampling_offsets, keep), raw_params=int(bool(raw_params)),
-        shs_rest=f(sh_rest, keep), colour_wait_event=colour_wait_event)
+        shs_rest=f(sh_rest, keep), colour_wait_event=colour_wait_event, preprojected=int(bool(preprojected)))
 
 
 def _sh_coeffs(sh) -> int:

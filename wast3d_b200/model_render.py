@@ -65,6 +65,9 @@ def _async_poll(st, wait=False):
         if overflow:
             err = RuntimeError(f"wast3d_b200: a graph-safe forward needed {r} tile instances but its binning buffer held "
                                f"{cap}; that step's image and gradients are incomplete (capacity raised for the next call)")
+        elif prefilt & 2:
+            err = RuntimeError("wast3d_b200: preprojected forward: the sampling offsets exceed the bounds the projection "
+                               "assumed (BackwardFusedAdam.prefetch_view offset_bounds); that step's image is incomplete")
         elif prefilt & 1:
             err = RuntimeError("wast3d_b200: rasterize_model: invalid argument (prefiltered set but a culled point was seen)")
         elif timeout:
@@ -80,6 +83,15 @@ def async_forward_check(device=None):
     for key, st in _ASYNC_STATE.items():
         if device is None or key[0] == torch.device(device).index:
             _async_poll(st, wait=True)
+
+
+def _projection_key(rs, leaves, P):
+    """What a pre-projected geometry buffer is valid for: the camera tensors (identity + version), the image
+    geometry, and the six parameter tensors exactly as the optimizer-in-backward left them."""
+    cam = tuple((t.data_ptr(), t._version) for t in (rs.viewmatrix, rs.projmatrix, rs.campos))
+    return (cam, int(rs.image_width), int(rs.image_height), float(rs.tanfovx), float(rs.tanfovy),
+            float(rs.scale_modifier), int(rs.sh_degree), int(P), _lib.set_tile_cut(-1),
+            tuple((t.data_ptr(), t._version) for t in leaves))
 
 
 class _RasterizeModel(torch.autograd.Function):
@@ -98,12 +110,26 @@ class _RasterizeModel(torch.autograd.Function):
         P, H, W = int(xyz.size(0)), int(rs.image_height), int(rs.image_width)
         color = torch.empty((3, H, W), dtype=torch.float32, device=dev)
         depth = torch.empty((H, W), dtype=torch.float32, device=dev)
-        radii = torch.empty((P,), dtype=torch.int32, device=dev)
-        geom, binning, img = _lib.GrowBuffer(dev, "geom"), _lib.GrowBuffer(dev, "binning"), _lib.GrowBuffer(dev, "img")
+        # a geometry buffer the previous step's backward already projected into (optim.BackwardFusedAdam.prefetch_view)?
+        fused_opt = getattr(grad_sink, "fused_adam", None) if grad_sink is not None else None
+        proj = getattr(fused_opt, "projection", None) if fused_opt is not None else None
+        pre = False
+        if proj is not None:
+            fused_opt.projection = None   # one shot
+            pre = colour_wait_event is None and P > 0 and \
+                proj["key"] == _projection_key(rs, (xyz, f_dc, f_rest, opacity, scaling, rotation), P)
+        if pre:
+            radii = proj["radii"]
+            geom = _lib.FixedBuffer(proj["geom"])
+        else:
+            radii = torch.empty((P,), dtype=torch.int32, device=dev)
+            geom = _lib.GrowBuffer(dev, "geom")
+        binning, img = _lib.GrowBuffer(dev, "binning"), _lib.GrowBuffer(dev, "img")
         keep: list = []
         # colour_wait_event (torch.cuda.Event): f_dc / f_rest are only read behind it (ABI v5)
         ev = int(colour_wait_event.cuda_event) if colour_wait_event is not None else None
         prm = _prm(keep, rs, xyz, f_dc, f_rest, opacity, scaling, rotation, sampling_offsets, ev)
+        prm.preprojected = int(pre)
         rendered = C.c_int(0)
         ast = None
         if _ASYNC["on"] and P:
@@ -171,12 +197,35 @@ class _RasterizeModel(torch.autograd.Function):
                 if fused_opt.capture_grads:  # test hook: also write the leaf gradients
                     fused_opt.last_grads = [torch.empty_like(t) for t in ctx.sink_params]
                     grads_out = (C.c_void_p * 6)(*[t.data_ptr() if t.numel() else None for t in fused_opt.last_grads])
+                # prefetch_view(): also project every Gaussian for the next camera from the updated values
+                nv, nview, nrs = fused_opt._next_view, None, None
+                fused_opt._next_view = None
+                fused_opt.projection = None
+                if nv is not None:
+                    import math
+                    cam = nv["cam"]
+                    nrs = GaussianRasterizationSettings(
+                        image_height=int(cam.image_height), image_width=int(cam.image_width),
+                        tanfovx=math.tan(cam.FoVx * 0.5), tanfovy=math.tan(cam.FoVy * 0.5), bg=rs.bg,
+                        scale_modifier=nv["scale"], viewmatrix=cam.world_view_transform,
+                        projmatrix=cam.full_proj_transform, sh_degree=rs.sh_degree if nv["D"] is None else int(nv["D"]),
+                        campos=cam.camera_center, prefiltered=False, debug=False)
+                    n_geom = _lib.geom_buffer(dev, P)
+                    n_radii = torch.empty((P,), dtype=torch.int32, device=dev)
+                    b = nv["bounds"]
+                    nview = _lib.NextView(
+                        width=nrs.image_width, height=nrs.image_height, tan_fovx=nrs.tanfovx, tan_fovy=nrs.tanfovy,
+                        scale_modifier=nrs.scale_modifier, D=nrs.sh_degree, viewmatrix=_lib.fptr(nrs.viewmatrix, keep),
+                        projmatrix=_lib.fptr(nrs.projmatrix, keep), campos=_lib.fptr(nrs.campos, keep),
+                        geom_buffer=n_geom.data_ptr(), radii=n_radii.data_ptr(), offset_min_x=b[0], offset_max_x=b[1],
+                        offset_min_y=b[2], offset_max_y=b[3])
                 with torch.cuda.device(dev):
-                    st = lib.wast3d_raster_backward_raw_adam(
+                    st = lib.wast3d_raster_backward_raw_adam_next(
                         C.byref(prm), int(ctx.num_rendered), _lib.fptr(radii, keep, torch.int32),
                         _lib.fptr(geom, keep, torch.uint8), _lib.fptr(binning, keep, torch.uint8),
                         _lib.fptr(img, keep, torch.uint8), _lib.fptr(g_color, keep), _lib.fptr(g_depth, keep),
-                        groups, grads_out, d_m2d.data_ptr() if d_m2d is not None else None, _lib.stream_ptr())
+                        groups, grads_out, d_m2d.data_ptr() if d_m2d is not None else None,
+                        C.byref(nview) if nview is not None else None, _lib.stream_ptr())
                 _lib.check(st, "rasterize_model_backward_adam")
             fused_opt._applied = True
             sink.fresh = False
@@ -185,6 +234,9 @@ class _RasterizeModel(torch.autograd.Function):
             for p_ in ctx.sink_params:
                 if p_.numel():
                     torch.autograd.graph.increment_version(p_)
+            if P and nview is not None:
+                fused_opt.projection = {"geom": n_geom, "radii": n_radii,
+                                        "key": _projection_key(nrs, ctx.sink_params, P)}
             return None, d_m2d, None, None, None, None, None, None, None, None, None
         # arena path only when nothing else has produced a gradient for these leaves in this step: re-pointing
         # .grad at the arena view would drop an earlier regulariser's gradient (it is accumulated by autograd

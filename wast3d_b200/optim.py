@@ -99,6 +99,21 @@ class BackwardFusedAdam(FusedAdam):
         self._applied = False
         self.capture_grads = False  # test hook: keep the leaf gradients of the last backward in .last_grads
         self.last_grads = None
+        self._next_view = None      # request: project for this camera inside the next backward (prefetch_view)
+        self.projection = None      # result: pre-filled geometry buffer + radii of the view projected last
+
+    def prefetch_view(self, viewpoint_camera, scaling_modifier: float = 1.0, sh_degree=None,
+                      offset_bounds=(-1.0, 0.0, -1.0, 0.0)):
+        """Announce the camera of the NEXT render() before this step's loss.backward().  The per-Gaussian backward
+        kernel then also projects every Gaussian for that view from the parameter values it has just updated
+        (wast3d_raster_backward_raw_adam_next), and the next render() of that camera starts at the depth sort: K1 and
+        its re-read of all parameters disappear from the step.  Contract: nothing else modifies the parameters between
+        this backward and that render(); a render() of any other camera / size simply projects as usual.
+        `offset_bounds` = (min x, max x, min y, max y) of the next call's sampling offsets; the default is the range of
+        the reference's own draw, `rand * -1` (gaussian_renderer/__init__.py:31); the next forward verifies it.
+        `sh_degree`: the model's active SH degree at the next render (default: unchanged)."""
+        self._next_view = dict(cam=viewpoint_camera, scale=float(scaling_modifier), D=sh_degree,
+                               bounds=tuple(float(b) for b in offset_bounds))
 
     @torch.no_grad()
     def adam_groups(self, leaves):
