@@ -75,10 +75,11 @@ def parse():
                     help="1 = graph-safe forward (wast3d_raster_forward_async): the instance count is never read back by the "
                          "host, the binning buffer is sized from the largest count seen; 0 = the reference's protocol "
                          "(one blocking read of num_rendered per forward, rasterizer_impl.cu:283)")
-    ap.add_argument("--prefetch-projection", type=int, default=1, choices=[0, 1],
+    ap.add_argument("--prefetch-projection", type=int, default=0, choices=[0, 1],
                     help="single GPU, --sync backward: 1 = the backward kernel also projects every Gaussian for the NEXT step's "
                          "camera from the parameters it has just updated (BackwardFusedAdam.prefetch_view); the next forward "
-                         "skips K1 and its re-read of all parameters; 0 = K1 in every forward")
+                         "skips K1 and its re-read of all parameters; 0 (default: measured equal, profiles/r02_projection_prefetch.md) = K1 "
+                         "in every forward")
     ap.add_argument("--tile-cut", type=int, default=1, choices=[0, 1],
                     help="1 = instantiate Gaussians only in tiles that can see alpha >= 1/255 (default), "
                          "0 = the reference's radius rectangles")

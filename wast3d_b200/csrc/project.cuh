@@ -12,7 +12,11 @@ namespace w3d {
 // forward.cu:20-71.  `sh` points at this Gaussian's staged row (k-th coefficient at sh[3k..],
 // k >= 1); the degree-0 coefficient is read from sh_dc (== sh unless the model-space path keeps
 // _features_dc and _features_rest apart).
-__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* sh_dc, const float* sh, float3 pos,
+// __noinline__: one compiled body for every caller (K1 with colour, the deferred colour kernel, the optimizer kernel's
+// projection of the next view).  Inlined copies are free to contract different multiply-add pairs into FMAs, which
+// made "K1 + deferred colour" differ from "K1 with colour" in the last bit after an unrelated change of K1's loads
+// (tests/test_peer_gpu.py compares those two schedules bit for bit).
+static __device__ __noinline__ float3 sh_to_rgb(int deg, const float* sh_dc, const float* sh, float3 pos,
                                             float3 campos, unsigned* clamped_bits) {
     float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
     const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
@@ -113,8 +117,9 @@ struct Projection {
 // forward.cu:155-256 for one Gaussian.  RAW: model-space inputs (log scales, unnormalised quaternion, opacity logit).
 // The quaternion and the opacity are taken from q_ptr / op_ptr when those are non-NULL (loaded only where the
 // reference's control flow needs them) and from q_val / op_val otherwise (values already in registers).
+// __noinline__ for the same reason as sh_to_rgb: preprocess_kernel and the optimizer kernel must produce the same bits.
 template <bool RAW>
-__device__ __forceinline__ Projection project_gaussian(const float3 p_orig, const float3 sc_in,
+static __device__ __noinline__ Projection project_gaussian(const float3 p_orig, const float3 sc_in,
                                                        const float* __restrict__ q_ptr, const float4 q_val,
                                                        const float* __restrict__ op_ptr, const float op_val,
                                                        const float* __restrict__ cov6_precomp, const ProjView& v) {
