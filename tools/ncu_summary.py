@@ -16,9 +16,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__shared_mem_per_block_static", "launch__grid_size",
         "smsp__inst_executed.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "lts__t_sector_hit_rate.pct", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
-KERNELS = ["preprocess_kernel", "emit_instances_kernel", "render_forward_kernel", "render_backward_direct_kernel",
-           "gaussian_backward_kernel"]
-TRAFFIC_KEYS = {"render_backward_direct_kernel": "render_backward_kernel", "render_forward_kernel": "render_forward_kernel",
+KERNELS = ["preprocess_kernel", "emit_instances_kernel", "onesweep_pass_kernel", "radix_hist_kernel", "render_forward",
+           "render_backward", "gaussian_backward_kernel", "pixel_loss_forward_kernel", "match_kernel<(int)0>",
+           "match_kernel<(int)1>", "knn_query_kernel"]
+TRAFFIC_KEYS = {"render_backward": "render_backward_kernel", "render_forward": "render_forward_kernel",
                 "preprocess_kernel": "preprocess_kernel", "gaussian_backward_kernel": "gaussian_backward_adam_kernel"}
 
 

@@ -12,43 +12,49 @@ namespace w3d {
 // forward.cu:20-71.  `sh` points at this Gaussian's staged row (k-th coefficient at sh[3k..],
 // k >= 1); the degree-0 coefficient is read from sh_dc (== sh unless the model-space path keeps
 // _features_dc and _features_rest apart).
-// __noinline__: one compiled body for every caller (K1 with colour, the deferred colour kernel, the optimizer kernel's
-// projection of the next view).  Inlined copies are free to contract different multiply-add pairs into FMAs, which
-// made "K1 + deferred colour" differ from "K1 with colour" in the last bit after an unrelated change of K1's loads
+// Every multiply / add below is an explicit round-to-nearest intrinsic in the order nvcc's default contraction gives
+// the reference expression (a - b*c -> fma(-b, c, a), left to right): the compiler has no freedom left, so every
+// caller (K1 with colour, the deferred colour kernel, the optimizer kernel's projection of the next view) produces
+// the same bits.  Inlined plain-C copies were free to contract different multiply-add pairs, which made
+// "K1 + deferred colour" differ from "K1 with colour" in the last bit after an unrelated change of K1's loads
 // (tests/test_peer_gpu.py compares those two schedules bit for bit).
-static __device__ __noinline__ float3 sh_to_rgb(int deg, const float* sh_dc, const float* sh, float3 pos,
+__device__ __forceinline__ float3 sh_to_rgb(int deg, const float* sh_dc, const float* sh, float3 pos,
                                             float3 campos, unsigned* clamped_bits) {
-    float3 dir = make_float3(pos.x - campos.x, pos.y - campos.y, pos.z - campos.z);
-    const float len = sqrtf(dir.x * dir.x + dir.y * dir.y + dir.z * dir.z);
-    dir.x = dir.x / len;
-    dir.y = dir.y / len;
-    dir.z = dir.z / len;
+    float3 dir = make_float3(__fsub_rn(pos.x, campos.x), __fsub_rn(pos.y, campos.y), __fsub_rn(pos.z, campos.z));
+    const float len = __fsqrt_rn(__fmaf_rn(dir.z, dir.z, __fmaf_rn(dir.y, dir.y, __fmul_rn(dir.x, dir.x))));
+    dir.x = __fdiv_rn(dir.x, len);
+    dir.y = __fdiv_rn(dir.y, len);
+    dir.z = __fdiv_rn(dir.z, len);
+    const float x = dir.x, y = dir.y, z = dir.z;
+    const float xx = __fmul_rn(x, x), yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
+    const float xy = __fmul_rn(x, y), yz = __fmul_rn(y, z), xz = __fmul_rn(x, z);
     float res[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        float r = SH_C0 * sh_dc[c];
+        float r = __fmul_rn(SH_C0, sh_dc[c]);
         if (deg > 0) {
-            const float x = dir.x, y = dir.y, z = dir.z;
-            r = r - SH_C1 * y * sh[3 + c] + SH_C1 * z * sh[6 + c] - SH_C1 * x * sh[9 + c];
+            r = __fmaf_rn(-__fmul_rn(SH_C1, y), sh[3 + c], r);
+            r = __fmaf_rn(__fmul_rn(SH_C1, z), sh[6 + c], r);
+            r = __fmaf_rn(-__fmul_rn(SH_C1, x), sh[9 + c], r);
             if (deg > 1) {
-                const float xx = x * x, yy = y * y, zz = z * z;
-                const float xy = x * y, yz = y * z, xz = x * z;
-                r = r + SH_C2[0] * xy * sh[12 + c] + SH_C2[1] * yz * sh[15 + c] +
-                    SH_C2[2] * (2.0f * zz - xx - yy) * sh[18 + c] + SH_C2[3] * xz * sh[21 + c] +
-                    SH_C2[4] * (xx - yy) * sh[24 + c];
+                r = __fmaf_rn(__fmul_rn(SH_C2[0], xy), sh[12 + c], r);
+                r = __fmaf_rn(__fmul_rn(SH_C2[1], yz), sh[15 + c], r);
+                r = __fmaf_rn(__fmul_rn(SH_C2[2], __fsub_rn(__fmaf_rn(2.0f, zz, -xx), yy)), sh[18 + c], r);
+                r = __fmaf_rn(__fmul_rn(SH_C2[3], xz), sh[21 + c], r);
+                r = __fmaf_rn(__fmul_rn(SH_C2[4], __fsub_rn(xx, yy)), sh[24 + c], r);
                 if (deg > 2) {
-                    r = r + SH_C3[0] * y * (3.0f * xx - yy) * sh[27 + c] +
-                        SH_C3[1] * xy * z * sh[30 + c] +
-                        SH_C3[2] * y * (4.0f * zz - xx - yy) * sh[33 + c] +
-                        SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * sh[36 + c] +
-                        SH_C3[4] * x * (4.0f * zz - xx - yy) * sh[39 + c] +
-                        SH_C3[5] * z * (xx - yy) * sh[42 + c] +
-                        SH_C3[6] * x * (xx - 3.0f * yy) * sh[45 + c];
+                    r = __fmaf_rn(__fmul_rn(__fmul_rn(SH_C3[0], y), __fmaf_rn(3.0f, xx, -yy)), sh[27 + c], r);
+                    r = __fmaf_rn(__fmul_rn(__fmul_rn(SH_C3[1], xy), z), sh[30 + c], r);
+                    r = __fmaf_rn(__fmul_rn(__fmul_rn(SH_C3[2], y), __fsub_rn(__fmaf_rn(4.0f, zz, -xx), yy)), sh[33 + c], r);
+                    r = __fmaf_rn(__fmul_rn(__fmul_rn(SH_C3[3], z),
+                                            __fmaf_rn(-3.0f, yy, __fmaf_rn(2.0f, zz, -__fmul_rn(3.0f, xx)))), sh[36 + c], r);
+                    r = __fmaf_rn(__fmul_rn(__fmul_rn(SH_C3[4], x), __fsub_rn(__fmaf_rn(4.0f, zz, -xx), yy)), sh[39 + c], r);
+                    r = __fmaf_rn(__fmul_rn(__fmul_rn(SH_C3[5], z), __fsub_rn(xx, yy)), sh[42 + c], r);
+                    r = __fmaf_rn(__fmul_rn(__fmul_rn(SH_C3[6], x), __fmaf_rn(-3.0f, yy, xx)), sh[45 + c], r);
                 }
             }
         }
-        r += 0.5f;
-        res[c] = r;
+        res[c] = __fadd_rn(r, 0.5f);
     }
     unsigned bits = 0;
     if (res[0] < 0) bits |= 1u;
@@ -117,9 +123,8 @@ struct Projection {
 // forward.cu:155-256 for one Gaussian.  RAW: model-space inputs (log scales, unnormalised quaternion, opacity logit).
 // The quaternion and the opacity are taken from q_ptr / op_ptr when those are non-NULL (loaded only where the
 // reference's control flow needs them) and from q_val / op_val otherwise (values already in registers).
-// __noinline__ for the same reason as sh_to_rgb: preprocess_kernel and the optimizer kernel must produce the same bits.
 template <bool RAW>
-static __device__ __noinline__ Projection project_gaussian(const float3 p_orig, const float3 sc_in,
+__device__ __forceinline__ Projection project_gaussian(const float3 p_orig, const float3 sc_in,
                                                        const float* __restrict__ q_ptr, const float4 q_val,
                                                        const float* __restrict__ op_ptr, const float op_val,
                                                        const float* __restrict__ cov6_precomp, const ProjView& v) {
