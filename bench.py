@@ -797,7 +797,7 @@ def main():
         alg_bytes = 80.0 * R + 32.0 * N  # K7 reads 40 B/instance, 40 B/instance of gradient RMW, 32 B/pixel
         achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
         traffic, traffic_src = traffic_of("render_backward_kernel")
-        roofline = {"bound": "hbm", "kernel": "render_backward_direct_kernel (K7)", "achieved": round(achieved, 2),
+        roofline = {"bound": "hbm", "kernel": "render_backward_warp_kernel (K7)", "achieved": round(achieved, 2),
                     "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                     "frac": round(achieved / hbm_peak, 5), "traffic": traffic, "traffic_source": traffic_src,
                     "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
@@ -809,7 +809,7 @@ def main():
                     if k_ms > 0 else 0.0}
     k7 = avg["render_backward"]
     roofline["other_kernels"] = {
-        "render_backward_direct_kernel (K7)": {"kernel_ms": round(k7, 4), "bound": "issue (FP32/MUFU/shuffle), DRAM ~2% busy",
+        "render_backward_warp_kernel (K7)": {"kernel_ms": round(k7, 4), "bound": "issue (FP32/MUFU/shuffle), DRAM ~2% busy",
                                                "algorithmic_GBps": round((80.0 * R + 32.0 * N) / (k7 * 1e-3) / 1e9, 1) if k7 > 0 else 0.0}}
     # whole step in the reference's units: the rasteriser's HBM roofline the north star is quoted on
     roofline["step_algorithmic_GBps"] = round((fwd_bytes + bwd_bytes + adam_bytes) / (ms_step * 1e-3) / 1e9, 1)
