@@ -734,7 +734,8 @@ def test_notebook_loop_two_renders_and_leaf_regulariser(built):
         opt_b.step()
 
 
-def test_graph_safe_forward_is_bit_identical_and_reports_overflow(built):
+@pytest.mark.parametrize("P,W,H,mu", [(60000, 320, 240, -3.4), (300000, 800, 800, -4.6)])
+def test_graph_safe_forward_is_bit_identical_and_reports_overflow(built, P, W, H, mu):
     """wast3d_raster_forward_async through render(): no host read of num_rendered, instance capacity from the largest
     count seen.  Same image / depth / radii bits as the synchronous protocol, same gradients (deterministic backward),
     and a capacity that is too small is reported (one call late, or at async_forward_check) instead of corrupting
@@ -742,11 +743,11 @@ def test_graph_safe_forward_is_bit_identical_and_reports_overflow(built):
     from wast3d_b200 import _lib, model_render
     from wast3d_b200.gaussian_renderer import render
     from wast3d_b200.scene import GaussianModel, PipelineParams, orbit_cameras, synthetic_gaussians
-    arrs = synthetic_gaussians(60000, seed=21, log_scale_mu=-3.4)
-    cams = orbit_cameras(4, 4.03, 0.0, 0.6911, 320, 240, device="cuda", sphere=True)
+    arrs = synthetic_gaussians(P, seed=21, log_scale_mu=mu)
+    cams = orbit_cameras(4, 4.03, 0.0, 0.6911, W, H, device="cuda", sphere=True)
     bg = torch.tensor([0.1, 0.2, 0.3], device="cuda")
     torch.manual_seed(1)
-    offs = -torch.rand(240, 320, 2, device="cuda")
+    offs = -torch.rand(H, W, 2, device="cuda")
 
     def run(cam):
         m = GaussianModel.from_arrays(arrs, device="cuda")
@@ -764,7 +765,7 @@ def test_graph_safe_forward_is_bit_identical_and_reports_overflow(built):
         got = [run(c) for c in cams]                 # first call synchronous (learns R), the rest graph-safe
         got2 = [run(c) for c in cams]
         model_render.async_forward_check()
-        key = (torch.cuda.current_device(), 320, 240)
+        key = (torch.cuda.current_device(), W, H)
         assert model_render._ASYNC_STATE[key]["seen"] > 100000
         for res in (got, got2):
             for a, b in zip(res, want):

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #include <cstdlib>
+#include <algorithm>
 #include <cmath>
 #include "../../include/wast3d_b200.h"
 
@@ -163,6 +164,8 @@ constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 inline size_t scan_num_blocks(size_t n) { return (n + SCAN_TILE - 1) / SCAN_TILE; }
 // block sums for a 2-level scan (level-1 sums are themselves scanned by one block in a loop)
 inline size_t scan_scratch_words(size_t n) { return scan_num_blocks(n) + 8; }
+// emit_instances_kernel<FUSED>: ticket, error word, one look-back status word per group of 2048 Gaussians
+inline size_t emit_scan_workspace_words(size_t P) { return (P + 2047) / 2048 + 2; }
 
 // Per-Gaussian render record, 48 bytes, gathered with three 16-byte cp.async per instance.
 //   r0 = { mean2D.x, mean2D.y, view depth, cutoff half-extent x }
@@ -185,6 +188,8 @@ struct GeomState {
     uint32_t* totals;        // [4]  {num_rendered, num_visible, ...}
     float4* grad_rec;        // [3P] backward accumulators (see raster_backward.cu)
     uint2* rect;             // [P]  instantiated tile rectangle {x0 | y0 << 16, width | height << 16}; 0 = none
+    uint2* rect_sorted;      // [P]  the same in depth order (gathered by the last depth-sort pass)
+    uint32_t* count_sorted;  // [P]  tiles per Gaussian in depth order
 
     static GeomState carve(void* chunk, size_t P, size_t* bytes) {
         Carver c(chunk);
@@ -203,6 +208,8 @@ struct GeomState {
         g.totals = c.take<uint32_t>(32);
         g.grad_rec = c.take<float4>(3 * P);
         g.rect = c.take<uint2>(P);
+        g.rect_sorted = c.take<uint2>(P);
+        g.count_sorted = c.take<uint32_t>(P);
         if (bytes) *bytes = c.bytes();
         return g;
     }
@@ -255,12 +262,21 @@ inline int bits_for(uint32_t n) {
 // out[i] = sum_{k<i} in[perm ? perm[k] : k]; total (optional) receives the full sum.
 int scan_exclusive_u32(const uint32_t* in, const uint32_t* perm, uint32_t* out, size_t n,
                        uint32_t* scratch, uint32_t* total, cudaStream_t s, bool debug);
+// Optional rider of a sort pass: with the sorted value v landing at position g, also dst[g] = src[v] and
+// cnt[g] = width * height of that rectangle (the rasteriser's last depth pass: the tile rectangles in depth order,
+// so that the offsets scan and the instance emission read them coalesced instead of gathering per Gaussian again).
+struct GatherRect {
+    const uint2* src = nullptr;
+    uint2* dst = nullptr;
+    uint32_t* cnt = nullptr;
+};
 // One stable LSD pass on bits [shift, shift+bits) (bits <= 8).  vals_in == NULL means iota.
 // keys_out == NULL means "do not write keys" (last pass).
 // n_dev (optional, device): process min(*n_dev, n) elements; n is then the capacity the launch is sized for.
 int radix_pass_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
                    uint32_t* vals_out, size_t n, int shift, int bits, uint32_t* hist,
-                   uint32_t* scan_scratch, cudaStream_t s, bool debug, const uint32_t* n_dev = nullptr);
+                   uint32_t* scan_scratch, cudaStream_t s, bool debug, const uint32_t* n_dev = nullptr,
+                   GatherRect gather = GatherRect());
 
 // Single-pass (decoupled look-back) variants — see scan_sort.cu.  The workspace `ws` of
 // onesweep_workspace_words(n, passes) words is zeroed by onesweep_prepare() once per sort;
@@ -271,8 +287,10 @@ int onesweep_prepare(uint32_t* ws, size_t n, int passes, cudaStream_t s);
 int onesweep_hist(const uint32_t* keys, size_t n, int passes, const int* shifts, const int* bits,
                   uint32_t* ws, cudaStream_t s, bool debug);
 int onesweep_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                  size_t n, int shift, int bits, uint32_t* ws, int passes, int pass, cudaStream_t s, bool debug);
+                  size_t n, int shift, int bits, uint32_t* ws, int passes, int pass, cudaStream_t s, bool debug,
+                  const uint32_t* n_dev = nullptr, GatherRect gather = GatherRect());
 uint32_t* onesweep_digit_hist(uint32_t* ws, size_t n, int passes, int pass);
+int onesweep_scan_digits(uint32_t* ws, size_t n, int passes, cudaStream_t s, bool debug);
 uint32_t* onesweep_error_word(uint32_t* ws, size_t n, int passes);
 size_t scan_lookback_workspace_words(size_t n);
 int scan_exclusive_lookback_u32(const uint32_t* in, const uint32_t* perm, uint32_t* out, size_t n,
@@ -318,5 +336,88 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
     return m;
 }
+
+// ---- block scan and decoupled look-back (scan_sort.cu; the fused offsets scan of emit_instances_kernel) ----------
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Exclusive scan of one value per thread across a block of SCAN_THREADS; returns the
+// exclusive prefix and writes the block total to *total (valid for all threads).
+template <int THREADS = SCAN_THREADS>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sums[THREADS / 32];
+    __shared__ uint32_t block_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = warp_incl_scan(v, lane);
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = lane < THREADS / 32 ? warp_sums[lane] : 0;
+        uint32_t wi = warp_incl_scan(w, lane);
+        if (lane < THREADS / 32) warp_sums[lane] = wi - w;
+        if (lane == THREADS / 32 - 1) block_total = wi;
+    }
+    __syncthreads();
+    uint32_t r = incl - v + warp_sums[warp];
+    *total = block_total;
+    __syncthreads();
+    return r;
+}
+
+// Look-back status words carry a flag in bits [31:30] (1 = aggregate of this tile only, 2 = inclusive prefix up to this
+// tile) and a 30-bit count; every wait is bounded and raises an error flag instead of hanging the device.
+constexpr uint32_t OS_AGG = 1u << 30, OS_PREFIX = 2u << 30, OS_VALUE = (1u << 30) - 1u;
+constexpr uint32_t OS_SPIN_LIMIT = 1u << 20;  // ~1 s of polling; a healthy wait is a few dozen polls
+
+__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Single-kernel exclusive scan with look-back.  ws: 2 + nblocks zero-initialised words
+// (ticket, error, status[nblocks]).  The look-back is done by warp 0, 32 predecessors per step.
+__device__ __forceinline__ uint32_t lookback_warp(uint32_t* status, uint32_t tile, uint32_t count,
+                                                  uint32_t* err, int lane) {
+    if (tile == 0) {
+        if (lane == 0) st_status(status, count | OS_PREFIX);
+        return 0;
+    }
+    if (lane == 0) st_status(status + tile, count | OS_AGG);
+    uint32_t excl = 0, spins = 0;
+    int look = (int)tile;  // exclusive upper end of the window
+    while (true) {
+        const int idx = look - 1 - lane;
+        uint32_t v = idx >= 0 ? ld_status(status + idx) : OS_PREFIX;  // before tile 0: empty prefix
+        const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 30) == 2u);
+        const unsigned invalid = __ballot_sync(0xffffffffu, (v >> 30) == 0u);
+        const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;      // nearest predecessor with a prefix
+        const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
+        if (invalid & need) {
+            if (++spins > OS_SPIN_LIMIT) {
+                if (lane == 0) atomicOr(err, 1u);
+                break;
+            }
+            continue;
+        }
+        uint32_t c = lane <= first ? (v & OS_VALUE) : 0u;
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        excl += c;
+        if (first < 32) break;
+        look -= 32;
+    }
+    if (lane == 0) st_status(status + tile, (excl + count) | OS_PREFIX);
+    return excl;
+}
+
 
 }  // namespace w3d

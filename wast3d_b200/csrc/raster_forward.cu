@@ -48,7 +48,7 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
                   const float focal_x, const float focal_y, const dim3 grid,
                   const bool prefiltered, int* __restrict__ radii, float4* __restrict__ rec,
                   uint32_t* __restrict__ depth_key, uint32_t* __restrict__ tiles_touched,
-                  uint8_t* __restrict__ clamped, uint2* __restrict__ rect_out, uint32_t* __restrict__ flags,
+                  uint8_t* __restrict__ clamped, uint2* __restrict__ rect_out, uint32_t* __restrict__ totals,
                   const uint32_t* __restrict__ sample_bound_words, const bool cut_tiles, const bool vec3_loads) {
     __shared__ __align__(16) float s_sh[PRE_WARPS][32 * SH_STRIDE];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -78,9 +78,13 @@ preprocess_kernel(const int P, const int D, const int M, const float* __restrict
     if (live) {
         pr = project_gaussian<RAW>(p_orig, sc_in, rotations ? rotations + 4 * (size_t)idx : nullptr, make_float4(0.f, 0.f, 0.f, 0.f),
                                    opacities + idx, 0.f, cov3D_precomp ? cov3D_precomp + 6 * (size_t)idx : nullptr, pv);
-        if (pr.behind && prefiltered) atomicOr(flags, 1u);  // reference: printf + __trap()
+        if (pr.behind && prefiltered) atomicOr(totals + 1, 1u);  // reference: printf + __trap()
     }
     const bool visible = pr.visible;
+    {   // num_rendered (rasterizer_impl.cu:279-283 takes it from the end of the scan): one atomic per warp
+        const uint32_t warp_tiles = __reduce_add_sync(0xffffffffu, pr.visible ? pr.n_tiles : 0u);
+        if (lane == 0 && warp_tiles != 0u) atomicAdd(totals, warp_tiles);
+    }
 
     // colour: SH -> RGB for survivors only
     float3 rgb = make_float3(0.f, 0.f, 0.f);
@@ -215,13 +219,83 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
 constexpr int EMIT_THREADS = 256;
 constexpr int EMIT_MAX_SMEM_TILES = 12288;  // 48 KB of counters; larger grids count in global memory
 
+// FUSED: the exclusive scan of the per-Gaussian tile counts (rasterizer_impl.cu:279) happens here instead of in its own
+// kernels: a block takes EMIT_GROUP depth-consecutive Gaussians by ticket (8 per thread, so the ticket / gather /
+// look-back latency chain is paid once per 2048 Gaussians), scans their counts, gets the instances before it with a
+// decoupled look-back over `scan_ws` (ticket, error word, one status word per group — zeroed by the caller), parks
+// (offset, id, rectangle) in shared memory and then emits warp by warp as above.  !FUSED reads precomputed `offsets`
+// (the preprojected path, and R >= 2^30 which the status words cannot hold).
+constexpr int EMIT_PER_THREAD = 8;
+constexpr int EMIT_GROUP = EMIT_THREADS * EMIT_PER_THREAD;
+struct EmitGroup {
+    uint32_t off[EMIT_GROUP], id[EMIT_GROUP], xy0[EMIT_GROUP], wh[EMIT_GROUP];
+};
+
+// One warp's 32 Gaussians (one per lane: first instance `off`, count `n`, id, rectangle origin, width): their instances
+// form the contiguous range [off_0, max(off + n)) which the lanes write with coalesced stores, 32 slots per step.
+// Gaussians without instances are squeezed out first (through `scratch`, 4 x 32 words of this warp), so the first
+// instances of the remaining lanes are strictly increasing and a slot finds its Gaussian with one OR-reduction of the
+// "starts in this window" bits and two popcounts instead of a shuffle binary search.
+__device__ __forceinline__ void emit_warp_run(uint32_t off, uint32_t n, uint32_t id, uint32_t xy0, uint32_t w,
+                                              const int lane, uint32_t* __restrict__ scratch,
+                                              uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                              uint32_t* __restrict__ tile_count, uint32_t* s_count, const bool smem_hist,
+                                              const uint32_t grid_x, const uint32_t capacity) {
+    const unsigned has = __ballot_sync(0xffffffffu, n != 0u);
+    if (has == 0u) return;
+    const uint32_t end = __reduce_max_sync(0xffffffffu, n != 0u ? off + n : 0u);
+    if (has != 0xffffffffu) {
+        __syncwarp();
+        if (n != 0u) {
+            const int r = __popc(has & lanemask_lt());
+            scratch[r] = off; scratch[32 + r] = id; scratch[64 + r] = xy0; scratch[96 + r] = w;
+        }
+        __syncwarp();
+        const bool live = lane < __popc(has);
+        off = live ? scratch[lane] : 0xFFFFFFFFu;
+        id = scratch[32 + lane]; xy0 = scratch[64 + lane]; w = live ? scratch[96 + lane] : 1u;
+    }
+    // floor(t / w) = umulhi(t, ceil(2^32 / w)) while t * w < 2^32 (t < w * h: rectangles up to 1024 tiles wide and 2^22
+    // tiles large qualify); inv = 0 marks the Gaussians that take the division
+    const uint32_t wn = __reduce_max_sync(0xffffffffu, w);
+    const uint32_t inv = w > 1u ? 0xFFFFFFFFu / w + 1u : 0u;
+    const bool all_fast = wn < 1024u && end - __shfl_sync(0xffffffffu, off, 0) < (1u << 22);   // warp-uniform
+    const uint32_t begin = __shfl_sync(0xffffffffu, off, 0);
+    const unsigned le = 0xFFFFFFFFu >> (31 - lane);
+    for (uint32_t p0 = begin; p0 < end; p0 += 32) {   // warp-uniform trip count
+        const uint32_t rel = off - p0;                 // lanes that start inside this window: rel < 32
+        const unsigned starts = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+        const int before = __popc(__ballot_sync(0xffffffffu, off < p0));   // lanes that started earlier (>= 1 after step 0)
+        const int l = before - 1 + __popc(starts & le);                   // the last lane with off_l <= p0 + lane
+        const uint32_t p = p0 + lane;
+        const uint32_t o = __shfl_sync(0xffffffffu, off, l);
+        const uint32_t src_xy0 = __shfl_sync(0xffffffffu, xy0, l);
+        const uint32_t src_w = __shfl_sync(0xffffffffu, w, l);
+        const uint32_t src_id = __shfl_sync(0xffffffffu, id, l);
+        const uint32_t src_inv = __shfl_sync(0xffffffffu, inv, l);
+        if (p < end && p < capacity) {
+            const uint32_t t = p - o;
+            const uint32_t ty = src_w == 1u ? t : (all_fast ? __umulhi(t, src_inv) : t / src_w);
+            const uint32_t tx = t - ty * src_w;
+            const uint32_t tile = ((src_xy0 >> 16) + ty) * grid_x + (src_xy0 & 0xFFFFu) + tx;
+            keys[p] = tile;
+            vals[p] = src_id;
+            if (smem_hist) atomicAdd(&s_count[tile], 1u);
+            else atomicAdd(&tile_count[tile], 1u);
+        }
+    }
+}
+
+template <bool FUSED>
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
-                      const uint2* __restrict__ rect, uint32_t* __restrict__ keys,
+                      const uint2* __restrict__ rect /* depth order */, uint32_t* __restrict__ keys,
                       uint32_t* __restrict__ vals, uint32_t* __restrict__ tile_count, const dim3 grid,
                       const int num_tiles, const bool smem_hist, const uint32_t capacity,
-                      uint32_t* __restrict__ totals) {
-    extern __shared__ uint32_t s_count[];
+                      uint32_t* __restrict__ totals, uint32_t* __restrict__ scan_ws) {
+    extern __shared__ __align__(16) uint32_t s_count[];   // [smem_hist ? num_tiles : 0] counters, then (FUSED) an EmitGroup
+    __shared__ uint32_t s_ticket, s_base;
+    __shared__ uint32_t s_scratch[EMIT_THREADS / 32][128];
     // graph-safe forward: the pair arrays hold `capacity` instances; a view that needs more raises totals[3]
     // (nothing is written out of bounds; the image of that call is incomplete and the host layer reports it)
     if (blockIdx.x == 0 && threadIdx.x == 0 && totals[0] > capacity) totals[3] = 1u;
@@ -229,46 +303,99 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
         for (int t = threadIdx.x; t < num_tiles; t += EMIT_THREADS) s_count[t] = 0;
         __syncthreads();
     }
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = EMIT_THREADS / 32;
-    const int n_chunks = (P + 31) / 32;
-    for (int chunk = blockIdx.x * warps_per_block + (threadIdx.x >> 5); chunk < n_chunks;
-         chunk += gridDim.x * warps_per_block) {
-        const int k = chunk * 32 + lane;
-        uint32_t id = 0, n = 0, off = 0xFFFFFFFFu, xy0 = 0, w = 1;
-        if (k < P) {
-            id = order[k];
-            off = offsets[k];
-            const uint2 rc = rect[id];   // the rectangle K1 counted: one 8-byte gather per Gaussian
-            xy0 = rc.x;
-            w = rc.y & 0xFFFFu;
-            n = w * (rc.y >> 16);
-            if (n == 0) w = 1;
-        }
-        const uint32_t begin = __shfl_sync(0xffffffffu, off, 0);
-        const uint32_t end = __reduce_max_sync(0xffffffffu, k < P ? off + n : 0u);
-        for (uint32_t p0 = begin; p0 < end; p0 += 32) {   // warp-uniform trip count
-            const uint32_t p = p0 + lane;
-            // largest lane l with off_l <= p (offsets are non-decreasing; lanes past P hold UINT_MAX)
-            int l = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int warps_per_block = EMIT_THREADS / 32;
+    if (FUSED) {
+        EmitGroup& grp = *reinterpret_cast<EmitGroup*>(s_count + (smem_hist ? (num_tiles + 3) / 4 * 4 : 0));
+        const uint32_t n_groups = (uint32_t)((P + EMIT_GROUP - 1) / EMIT_GROUP);
+        while (true) {
+            __syncthreads();   // everybody is done with the previous group's shared arrays
+            if (threadIdx.x == 0) s_ticket = atomicAdd(scan_ws, 1u);
+            __syncthreads();
+            const uint32_t ticket = s_ticket;
+            if (ticket >= n_groups) break;
+            // thread t owns Gaussians [k0, k0 + 8) of the group
+            const int k0 = (int)ticket * EMIT_GROUP + threadIdx.x * EMIT_PER_THREAD;
+            uint32_t ids[EMIT_PER_THREAD], cnt[EMIT_PER_THREAD], xy[EMIT_PER_THREAD], wh[EMIT_PER_THREAD];
+            if (k0 + EMIT_PER_THREAD <= P) {
+                const uint4 a = *reinterpret_cast<const uint4*>(order + k0), b = *reinterpret_cast<const uint4*>(order + k0 + 4);
+                ids[0] = a.x; ids[1] = a.y; ids[2] = a.z; ids[3] = a.w; ids[4] = b.x; ids[5] = b.y; ids[6] = b.z; ids[7] = b.w;
+            } else {
 #pragma unroll
-            for (int step = 16; step >= 1; step >>= 1) {
-                const uint32_t v = __shfl_sync(0xffffffffu, off, l + step);   // l + step <= 31
-                if (v <= p) l += step;
+                for (int j = 0; j < EMIT_PER_THREAD; ++j) ids[j] = k0 + j < P ? order[k0 + j] : 0xFFFFFFFFu;
             }
-            const uint32_t o = __shfl_sync(0xffffffffu, off, l);
-            const uint32_t src_xy0 = __shfl_sync(0xffffffffu, xy0, l);
-            const uint32_t src_w = __shfl_sync(0xffffffffu, w, l);
-            const uint32_t src_id = __shfl_sync(0xffffffffu, id, l);
-            if (p < end && p < capacity) {
-                const uint32_t t = p - o;
-                const uint32_t ty = t / src_w, tx = t - ty * src_w;
-                const uint32_t tile = ((src_xy0 >> 16) + ty) * grid.x + (src_xy0 & 0xFFFFu) + tx;
-                keys[p] = tile;
-                vals[p] = src_id;
-                if (smem_hist) atomicAdd(&s_count[tile], 1u);
-                else atomicAdd(&tile_count[tile], 1u);
+            uint32_t sum = 0;
+            if (k0 + EMIT_PER_THREAD <= P) {   // the rectangles K1 counted, in depth order: 64 contiguous bytes per thread
+#pragma unroll
+                for (int j = 0; j < EMIT_PER_THREAD; j += 2) {
+                    const uint4 rr = *reinterpret_cast<const uint4*>(rect + k0 + j);
+                    xy[j] = rr.x; wh[j] = rr.y; xy[j + 1] = rr.z; wh[j + 1] = rr.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < EMIT_PER_THREAD; ++j) {
+                    const uint2 rc = k0 + j < P ? rect[k0 + j] : make_uint2(0u, 0u);
+                    xy[j] = rc.x;
+                    wh[j] = rc.y;
+                }
             }
+#pragma unroll
+            for (int j = 0; j < EMIT_PER_THREAD; ++j) {
+                cnt[j] = (wh[j] & 0xFFFFu) * (wh[j] >> 16);
+                sum += cnt[j];
+            }
+            uint32_t group_total;
+            uint32_t run = block_excl_scan<EMIT_THREADS>(sum, &group_total);
+            if (threadIdx.x < 32) {
+                const uint32_t e = lookback_warp(scan_ws + 2, ticket, group_total, scan_ws + 1, lane);
+                if (lane == 0) s_base = e;
+            }
+            __syncthreads();
+            run += s_base;
+            uint32_t offs[EMIT_PER_THREAD];
+#pragma unroll
+            for (int j = 0; j < EMIT_PER_THREAD; ++j) {
+                offs[j] = k0 + j < P ? run : 0xFFFFFFFFu;
+                run += cnt[j];
+            }
+            const int slot = threadIdx.x * EMIT_PER_THREAD;
+            *reinterpret_cast<uint4*>(grp.off + slot) = make_uint4(offs[0], offs[1], offs[2], offs[3]);
+            *reinterpret_cast<uint4*>(grp.off + slot + 4) = make_uint4(offs[4], offs[5], offs[6], offs[7]);
+            *reinterpret_cast<uint4*>(grp.id + slot) = make_uint4(ids[0], ids[1], ids[2], ids[3]);
+            *reinterpret_cast<uint4*>(grp.id + slot + 4) = make_uint4(ids[4], ids[5], ids[6], ids[7]);
+            *reinterpret_cast<uint4*>(grp.xy0 + slot) = make_uint4(xy[0], xy[1], xy[2], xy[3]);
+            *reinterpret_cast<uint4*>(grp.xy0 + slot + 4) = make_uint4(xy[4], xy[5], xy[6], xy[7]);
+            *reinterpret_cast<uint4*>(grp.wh + slot) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            *reinterpret_cast<uint4*>(grp.wh + slot + 4) = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+            __syncthreads();
+            // warp w emits Gaussians [256 w, 256 w + 256) of the group, 32 at a time
+#pragma unroll 1
+            for (int sub = 0; sub < EMIT_PER_THREAD; ++sub) {
+                const int sl = warp * (32 * EMIT_PER_THREAD) + sub * 32 + lane;
+                const uint32_t off = grp.off[sl], rcw = grp.wh[sl];
+                uint32_t w = rcw & 0xFFFFu;
+                const uint32_t n = w * (rcw >> 16);
+                if (n == 0) w = 1;
+                emit_warp_run(off, off != 0xFFFFFFFFu ? n : 0u, grp.id[sl], grp.xy0[sl], w, lane, s_scratch[warp], keys, vals,
+                              tile_count, s_count, smem_hist, grid.x, capacity);
+            }
+        }
+    } else {
+        const int n_chunks = (P + 31) / 32;
+        for (int chunk = blockIdx.x * warps_per_block + warp; chunk < n_chunks; chunk += gridDim.x * warps_per_block) {
+            const int k = chunk * 32 + lane;
+            uint32_t id = 0, n = 0, off = 0xFFFFFFFFu, xy0 = 0, w = 1;
+            if (k < P) {
+                id = order[k];
+                off = offsets[k];
+                const uint2 rc = rect[k];   // the rectangle K1 counted (depth order)
+                xy0 = rc.x;
+                w = rc.y & 0xFFFFu;
+                n = w * (rc.y >> 16);
+                if (n == 0) w = 1;
+            }
+            emit_warp_run(off, n, id, xy0, w, lane, s_scratch[warp], keys, vals, tile_count, s_count, smem_hist, grid.x,
+                          capacity);
         }
     }
     if (smem_hist) {
@@ -337,6 +464,9 @@ tile_digit_hist_kernel(int num_tiles, const uint32_t* __restrict__ tile_count, i
 
 __global__ void tile_copy_flags_kernel(const uint32_t* a, const uint32_t* b, uint32_t* out) {
     if (threadIdx.x == 0) *out = (a ? *a : 0u) | (b ? *b : 0u);
+}
+__global__ void tile_or_flag_kernel(const uint32_t* a, uint32_t* out) {
+    if (threadIdx.x == 0 && *a) atomicOr(out, *a);
 }
 // Preprojected forward: the tile rectangles were cut with ASSUMED bounds of the sampling offsets (words: order keys
 // of max ox, max -ox, max oy, max -oy); offsets outside them could see Gaussians in tiles that were not instantiated.
@@ -641,14 +771,24 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
 // ------------------------------------------------------------------ host -----------------
 // Which flavour of the sort / scan primitives each binning stage uses: 0 = multi-kernel (histogram,
 // table scan, scatter), 1 = single-kernel passes with decoupled look-back.  Measured on B200
-// (profiles/r01_sort_modes.md): the depth sort of P keys is launch-bound and wins with look-back
-// (5 launches instead of 20), the tile partition of R pairs and the offsets scan are a few percent
-// faster multi-kernel.  WAST3D_SORT_MODE=0|1 forces one flavour everywhere (experiments, tests).
+// (profiles/r02_sort_chain.md): with the windowed look-back both sorts win single-kernel (depth sort of P keys: 5
+// launches instead of 20; tile partition of R pairs: no key histograms at all, the digit bases follow from the
+// per-tile counts).  The offsets scan is fused into emit_instances_kernel; where it runs on its own (preprojected
+// views, WAST3D_EMIT_SCAN=0) the multi-kernel flavour is the default.  WAST3D_SORT_MODE=0|1 forces one flavour
+// everywhere (experiments, tests).  In the synchronous protocol a look-back time-out behind the host read of
+// num_rendered (emit, tile partition: never observed, it takes a hung GPU) is only recorded in the geometry buffer's
+// totals[2]; wast3d_raster_forward_async reports it through status_dev[2].
 enum SortStage { STAGE_DEPTH = 0, STAGE_SCAN = 1, STAGE_TILE = 2 };
 static int sort_mode(SortStage stage) {
     static const int forced = getenv("WAST3D_SORT_MODE") ? atoi(getenv("WAST3D_SORT_MODE")) : -1;
+    // per-stage override (A/B measurements): WAST3D_SORT_DEPTH / WAST3D_SORT_SCAN / WAST3D_SORT_TILE = 0|1
+    static const char* const names[3] = {"WAST3D_SORT_DEPTH", "WAST3D_SORT_SCAN", "WAST3D_SORT_TILE"};
+    static const int per_stage[3] = {getenv(names[0]) ? atoi(getenv(names[0])) : -1,
+                                     getenv(names[1]) ? atoi(getenv(names[1])) : -1,
+                                     getenv(names[2]) ? atoi(getenv(names[2])) : -1};
+    if (per_stage[stage] == 0 || per_stage[stage] == 1) return per_stage[stage];
     if (forced == 0 || forced == 1) return forced;
-    return stage == STAGE_DEPTH ? 1 : 0;
+    return stage == STAGE_SCAN ? 0 : 1;
 }
 
 // Tile cut (tile_rect_cut, raster_math.cuh): 1 = instantiate a Gaussian only in the tiles that can see
@@ -778,7 +918,7 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         P, prm->D, prm->M, prm->means3D, prm->scales, prm->scale_modifier, prm->rotations,
         prm->opacities, prm->shs, prm->shs_rest, prm->cov3D_precomp, prm->colors_precomp, prm->viewmatrix,
         prm->projmatrix, prm->campos, W, H, prm->tan_fovx, prm->tan_fovy, focal_x, focal_y, grid,
-        prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.rect, g.totals + 1,
+        prm->prefiltered != 0, radii, g.rec, g.depth_key, g.tiles_touched, g.clamped, g.rect, g.totals,
         sample_bound_words, cut_tiles, k1_vec);
     W3D_AFTER_LAUNCH(s, debug);
     }
@@ -799,27 +939,39 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         if (st) return st;
     }
     for (int p = 0; p < 4; ++p) {
+        // the last pass also lays the tile rectangles (and their tile counts) out in depth order
+        GatherRect gather;
+        if (p == 3) { gather.src = g.rect; gather.dst = g.rect_sorted; gather.cnt = g.count_sorted; }
         if (sort_mode(STAGE_DEPTH) == 1)
-            st = onesweep_pass(kin[p], vin[p], kout[p], vout[p], P, shifts[p], bits[p], g.sort_ws, 4, p, s, debug);
+            st = onesweep_pass(kin[p], vin[p], kout[p], vout[p], P, shifts[p], bits[p], g.sort_ws, 4, p, s, debug,
+                               nullptr, gather);
         else
             st = radix_pass_u32(kin[p], vin[p], kout[p], vout[p], P, shifts[p], bits[p], g.sort_ws,
-                                g.sort_ws + rs_hist_words(P), s, debug);
+                                g.sort_ws + rs_hist_words(P), s, debug, nullptr, gather);
         if (st) return st;
     }
     }
-    {
-    ProfScope ps(PS_SCAN, s);
-    if (sort_mode(STAGE_SCAN) == 1)
-        st = scan_exclusive_lookback_u32(g.tiles_touched, g.order_a, g.offsets, P, g.scan_ws, g.totals, s, debug);
-    else
-        st = scan_exclusive_u32(g.tiles_touched, g.order_a, g.offsets, P, g.scan_ws, g.totals, s, debug);
-    if (st) return st;
-    // look-back time-outs (never expected) of the depth sort and the scan, read with num_rendered
-    if (sort_mode(STAGE_DEPTH) == 1 || sort_mode(STAGE_SCAN) == 1) {
-        tile_copy_flags_kernel<<<1, 32, 0, s>>>(sort_mode(STAGE_DEPTH) == 1 ? onesweep_error_word(g.sort_ws, P, 4) : nullptr,
-                                               sort_mode(STAGE_SCAN) == 1 ? g.scan_ws + 1 : nullptr, g.totals + 2);
-        W3D_AFTER_LAUNCH(s, debug);
+    // Offsets of the Gaussians' instance runs (rasterizer_impl.cu:279).  Default: fused into emit_instances_kernel
+    // (K1 already summed num_rendered); WAST3D_EMIT_SCAN=0, a preprojected view (its projection ran before totals was
+    // reset) and counts the look-back status words cannot hold take the stand-alone scan.
+    static const bool emit_scan_env = !(getenv("WAST3D_EMIT_SCAN") && atoi(getenv("WAST3D_EMIT_SCAN")) == 0);
+    bool fused_scan = emit_scan_env && !pre && (!async || capacity <= (long long)OS_VALUE);
+    auto standalone_scan = [&]() -> int {
+        ProfScope ps(PS_SCAN, s);
+        if (sort_mode(STAGE_SCAN) == 1)
+            return scan_exclusive_lookback_u32(g.count_sorted, nullptr, g.offsets, P, g.scan_ws, g.totals, s, debug);
+        return scan_exclusive_u32(g.count_sorted, nullptr, g.offsets, P, g.scan_ws, g.totals, s, debug);
+    };
+    if (!fused_scan) {
+        st = standalone_scan();
+        if (st) return st;
     }
+    // look-back time-outs (never expected) of the depth sort and the scan, read with num_rendered
+    if (sort_mode(STAGE_DEPTH) == 1 || (!fused_scan && sort_mode(STAGE_SCAN) == 1)) {
+        tile_copy_flags_kernel<<<1, 32, 0, s>>>(sort_mode(STAGE_DEPTH) == 1 ? onesweep_error_word(g.sort_ws, P, 4) : nullptr,
+                                               !fused_scan && sort_mode(STAGE_SCAN) == 1 ? g.scan_ws + 1 : nullptr,
+                                               g.totals + 2);
+        W3D_AFTER_LAUNCH(s, debug);
     }
 
     uint32_t R;   // instances the binning buffer is carved for (== num_rendered in the synchronous protocol)
@@ -836,6 +988,11 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         }
         if (host_totals[0] > 0x7FFFFFFFu) return WAST3D_ERR_OVERFLOW;
         R = host_totals[0];
+        if (fused_scan && R > OS_VALUE) {   // more instances than a look-back status word holds: scan on its own
+            fused_scan = false;
+            st = standalone_scan();
+            if (st) return st;
+        }
     } else {
         R = (uint32_t)capacity;
     }
@@ -859,15 +1016,32 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         const int n_chunks = (P + 31) / 32;
         int blocks = 148 * 4;
         if (blocks > (n_chunks + 7) / 8) blocks = (n_chunks + 7) / 8;
-        emit_instances_kernel<<<blocks, EMIT_THREADS, smem, s>>>(P, g.order_a, g.offsets, g.rect, bn.keys_a, bn.vals_a,
-                                                               im.tile_count, grid, (int)num_tiles, smem_hist, R, g.totals);
+        if (fused_scan) {
+            W3D_CUDA_TRY(cudaMemsetAsync(g.scan_ws, 0, emit_scan_workspace_words(P) * sizeof(uint32_t), s));
+            const size_t fsmem = (smem_hist ? (size_t)(num_tiles + 3) / 4 * 4 * sizeof(uint32_t) : 0) + sizeof(EmitGroup);
+            // up to 80 KB of dynamic shared memory: opt in (per device, so on every launch; the call only records a number)
+            W3D_CUDA_TRY(cudaFuncSetAttribute(emit_instances_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)(EMIT_MAX_SMEM_TILES * sizeof(uint32_t) + sizeof(EmitGroup))));
+            const int n_groups = (P + EMIT_GROUP - 1) / EMIT_GROUP;
+            blocks = n_groups < 148 * 4 ? n_groups : 148 * 4;
+            emit_instances_kernel<true><<<blocks, EMIT_THREADS, fsmem, s>>>(P, g.order_a, nullptr, g.rect_sorted, bn.keys_a,
+                                                                         bn.vals_a, im.tile_count, grid, (int)num_tiles,
+                                                                         smem_hist, R, g.totals, g.scan_ws);
+            W3D_AFTER_LAUNCH(s, debug);
+            // a look-back time-out (never expected) joins the flags; the synchronous protocol has read them already
+            tile_or_flag_kernel<<<1, 32, 0, s>>>(g.scan_ws + 1, g.totals + 2);
+        } else {
+            emit_instances_kernel<false><<<blocks, EMIT_THREADS, smem, s>>>(P, g.order_a, g.offsets, g.rect_sorted, bn.keys_a,
+                                                                          bn.vals_a, im.tile_count, grid, (int)num_tiles,
+                                                                          smem_hist, R, g.totals, nullptr);
+        }
         W3D_AFTER_LAUNCH(s, debug);
         }
         ProfScope* pts = new ProfScope(PS_TILE_SORT, s);
         int bpp;
         const int passes = tile_sort_passes(num_tiles, &bpp);
         if (passes > TILE_SORT_MAX_PASSES) { delete pts; return WAST3D_ERR_OVERFLOW; }
-        const bool tile_lookback = sort_mode(STAGE_TILE) == 1 && !async;   // look-back passes need the host-side count
+        const bool tile_lookback = sort_mode(STAGE_TILE) == 1;
         if (tile_lookback) {
             st = onesweep_prepare(bn.sort_ws, R, passes, s);
             if (st) { delete pts; return st; }
@@ -875,13 +1049,15 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
             tile_digit_hist_kernel<<<(num_tiles + 255) / 256, 256, 0, s>>>(
                 (int)num_tiles, im.tile_count, passes, bpp, onesweep_digit_hist(bn.sort_ws, R, passes, 0));
             W3D_AFTER_LAUNCH(s, debug);
+            st = onesweep_scan_digits(bn.sort_ws, R, passes, s, debug);
+            if (st) { delete pts; return st; }
         }
         uint32_t *kin = bn.keys_a, *vin = bn.vals_a, *kout = bn.keys_b, *vout = bn.vals_b;
         for (int p = 0; p < passes; ++p) {
             // the last pass does not need to write the sorted tile ids: ranges come from the counts
             if (tile_lookback)
                 st = onesweep_pass(kin, vin, p + 1 < passes ? kout : nullptr, vout, R, p * bpp, bpp, bn.sort_ws,
-                                   passes, p, s, debug);
+                                   passes, p, s, debug, n_dev);
             else
                 st = radix_pass_u32(kin, vin, p + 1 < passes ? kout : nullptr, vout, R, p * bpp, bpp, bn.sort_ws,
                                     bn.sort_ws + rs_hist_words(R), s, debug, n_dev);
@@ -889,6 +1065,10 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
             uint32_t* t;
             t = kin; kin = kout; kout = t;
             t = vin; vin = vout; vout = t;
+        }
+        if (tile_lookback) {   // a look-back time-out (never expected) joins the flags of the depth sort and the scan
+            tile_or_flag_kernel<<<1, 32, 0, s>>>(onesweep_error_word(bn.sort_ws, R, passes), g.totals + 2);
+            W3D_AFTER_LAUNCH(s, debug);
         }
         delete pts;
         ProfScope ps(PS_RANGES, s);

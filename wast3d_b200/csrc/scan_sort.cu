@@ -15,38 +15,6 @@
 namespace w3d {
 
 // ------------------------------------------------------------------ scan ----------------
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= d) v += t;
-    }
-    return v;
-}
-
-// Exclusive scan of one value per thread across a block of SCAN_THREADS; returns the
-// exclusive prefix and writes the block total to *total (valid for all threads).
-template <int THREADS = SCAN_THREADS>
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total) {
-    __shared__ uint32_t warp_sums[THREADS / 32];
-    __shared__ uint32_t block_total;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = warp_incl_scan(v, lane);
-    if (lane == 31) warp_sums[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = lane < THREADS / 32 ? warp_sums[lane] : 0;
-        uint32_t wi = warp_incl_scan(w, lane);
-        if (lane < THREADS / 32) warp_sums[lane] = wi - w;
-        if (lane == THREADS / 32 - 1) block_total = wi;
-    }
-    __syncthreads();
-    uint32_t r = incl - v + warp_sums[warp];
-    *total = block_total;
-    __syncthreads();
-    return r;
-}
-
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_reduce_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm, size_t n,
                    uint32_t* __restrict__ block_sums) {
@@ -142,38 +110,6 @@ radix_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int shift, uint32
 }
 
 constexpr int OS_THREADS = 512;
-template <bool HAS_VALS, bool WRITE_KEYS, bool LOOKBACK>
-__global__ void onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
-                                     uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
-                                     int shift, uint32_t mask, const uint32_t* __restrict__ digit_hist,
-                                     uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                                     uint32_t* __restrict__ err, unsigned nblocks, const uint32_t* __restrict__ n_dev);
-
-int radix_pass_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
-                   uint32_t* vals_out, size_t n, int shift, int bits, uint32_t* hist,
-                   uint32_t* scan_scratch, cudaStream_t s, bool debug, const uint32_t* n_dev) {
-    if (n == 0) return WAST3D_OK;
-    if (bits < 1 || bits > 8) return WAST3D_ERR_INVALID_ARGUMENT;
-    if (n > 0xFFFFFFFFull - RS_TILE) return WAST3D_ERR_OVERFLOW;
-    const unsigned nb = (unsigned)rs_num_blocks(n);
-    const uint32_t mask = (1u << bits) - 1u;
-    radix_hist_kernel<<<nb, RS_THREADS, 0, s>>>(keys_in, n, shift, mask, hist, nb, n_dev);
-    W3D_AFTER_LAUNCH(s, debug);
-    int st = scan_exclusive_u32(hist, nullptr, hist, (size_t)nb * RS_RADIX, scan_scratch, nullptr,
-                                s, debug);
-    if (st != WAST3D_OK) return st;
-#define W3D_SCATTER(HV, WK)                                                                          \
-    onesweep_pass_kernel<HV, WK, false><<<nb, OS_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n, \
-                                                                  shift, mask, hist, nullptr, nullptr, nullptr, nb, n_dev)
-    if (vals_in) {
-        if (keys_out) W3D_SCATTER(true, true); else W3D_SCATTER(true, false);
-    } else {
-        if (keys_out) W3D_SCATTER(false, true); else W3D_SCATTER(false, false);
-    }
-#undef W3D_SCATTER
-    W3D_AFTER_LAUNCH(s, debug);
-    return WAST3D_OK;
-}
 
 // ------------------------------------------------------------------ single-pass variants --
 // Decoupled look-back ("onesweep"): ONE kernel per radix pass and ONE kernel per scan instead of
@@ -182,17 +118,6 @@ int radix_pass_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* k
 // without any assumption on block scheduling); every wait is bounded anyway and raises an error
 // flag instead of hanging the device.  Status words carry the flag in bits [31:30]
 // (1 = aggregate of this tile only, 2 = inclusive prefix up to this tile) and a 30-bit count.
-constexpr uint32_t OS_AGG = 1u << 30, OS_PREFIX = 2u << 30, OS_VALUE = (1u << 30) - 1u;
-constexpr uint32_t OS_SPIN_LIMIT = 1u << 20;  // ~1 s of polling; a healthy wait is a few dozen polls
-
-__device__ __forceinline__ uint32_t ld_status(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_status(uint32_t* p, uint32_t v) {
-    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Global digit histograms of up to 4 passes from one read of the keys.
 __global__ void __launch_bounds__(256)
 onesweep_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int npasses, int4 shifts, int4 masks,
@@ -217,133 +142,260 @@ onesweep_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int npasses, i
 
 // 512 threads x 8 keys: the per-warp ranking chain (match -> shared counter -> next key) is a
 // latency chain, so the tile is spread over 16 warps with 8 dependent steps each instead of
-// 8 warps with 16, and 4 blocks (64 warps) fit an SM.  The look-back wait is placed after the
-// keys have been ranked and parked in shared memory, when predecessors have had time to publish.
+// 8 warps with 16, and 3 blocks (48 warps) fit an SM.  The values never pass through registers:
+// they are staged with cp.async at kernel entry (in flight during the whole ranking phase) and
+// permuted shared -> shared.  The look-back wait is placed after the keys have been ranked and
+// parked in shared memory, when predecessors have had time to publish.
 constexpr int OS_ITEMS = 8;
 constexpr int OS_TILE = OS_THREADS * OS_ITEMS;
 static_assert(OS_TILE == RS_TILE, "workspace sizing assumes the same tile size");
+constexpr int OS_WARPS = OS_THREADS / 32;
+struct OsSmem {
+    uint16_t warp_hist[OS_WARPS][RS_RADIX];  // <= OS_TILE, fits 16 bits
+    uint32_t bin_start[RS_RADIX];            // first local position of a digit
+    uint32_t bin_off[RS_RADIX];              // global position of a digit's first key minus bin_start
+    uint32_t skeys[OS_TILE];
+    uint32_t svals[OS_TILE];
+    uint32_t stage[OS_TILE];                 // values in load order
+    uint32_t warp_total[RS_RADIX / 32];
+    uint32_t tile;
+};
 
-// LOOKBACK = false: the multi-kernel flavour — `digit_hist` is then the scanned bin-major table
+// LOOKBACK = false: the multi-kernel flavour — `digit_base` is then the scanned bin-major table
 // of per-tile scatter bases (bases[digit * nblocks + tile]) and status/ticket/err are unused.
-template <bool HAS_VALS, bool WRITE_KEYS, bool LOOKBACK>
+// LOOKBACK = true: `digit_base` holds the EXCLUSIVE prefix of the global digit histogram.
+template <bool HAS_VALS, bool WRITE_KEYS, bool LOOKBACK, int LBW>
 __global__ void __launch_bounds__(OS_THREADS, 3)
 onesweep_pass_kernel(const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, size_t n,
-                     int shift, uint32_t mask, const uint32_t* __restrict__ digit_hist,
+                     int shift, uint32_t mask, const uint32_t* __restrict__ digit_base,
                      uint32_t* __restrict__ status, uint32_t* __restrict__ ticket,
-                     uint32_t* __restrict__ err, unsigned nblocks, const uint32_t* __restrict__ n_dev) {
-    constexpr int WARPS = OS_THREADS / 32;
-    if (!LOOKBACK && n_dev != nullptr) {   // device-side element count (see radix_hist_kernel)
-        n = min(n, (size_t)*n_dev);
-        if ((size_t)blockIdx.x * OS_TILE >= n) return;   // whole block past the end (uniform)
-    }
-    __shared__ uint16_t warp_hist[WARPS][RS_RADIX];  // <= OS_TILE, fits 16 bits
-    __shared__ uint32_t bin_start[RS_RADIX];
-    __shared__ uint32_t bin_base[RS_RADIX];
-    __shared__ uint32_t skeys[OS_TILE];
-    __shared__ uint32_t svals[OS_TILE];
-    __shared__ uint32_t s_tile;
+                     uint32_t* __restrict__ err, unsigned nblocks, const uint32_t* __restrict__ n_dev,
+                     const GatherRect gather) {
+    extern __shared__ __align__(16) unsigned char os_smem_raw[];
+    OsSmem& sm = *reinterpret_cast<OsSmem*>(os_smem_raw);
+    if (n_dev != nullptr) n = min(n, (size_t)*n_dev);   // device-side element count (see radix_hist_kernel)
+    if (!LOOKBACK && (size_t)blockIdx.x * OS_TILE >= n) return;   // whole block past the end (uniform)
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
-    if (LOOKBACK && threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < WARPS * RS_RADIX / 2; i += OS_THREADS)
-        reinterpret_cast<uint32_t*>(&warp_hist[0][0])[i] = 0;
+    if (LOOKBACK && threadIdx.x == 0) sm.tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < OS_WARPS * RS_RADIX / 2; i += OS_THREADS)
+        reinterpret_cast<uint32_t*>(&sm.warp_hist[0][0])[i] = 0;
     __syncthreads();
-    const uint32_t tile = LOOKBACK ? s_tile : blockIdx.x;
+    const uint32_t tile = LOOKBACK ? sm.tile : blockIdx.x;
+    // look-back with a device-side count: tickets past the last tile have nothing to sort and nobody waits for them
+    if (LOOKBACK && (size_t)tile * OS_TILE >= n) return;
 
     const size_t tile_base = (size_t)tile * OS_TILE;
-    const size_t warp_base = tile_base + (size_t)warp * (32 * OS_ITEMS);
-    uint32_t key[OS_ITEMS], rank[OS_ITEMS];
+    const size_t remaining = n - tile_base;
+    const uint32_t count_tile = remaining < (size_t)OS_TILE ? (uint32_t)remaining : (uint32_t)OS_TILE;
+    const uint32_t* tkeys = keys_in + tile_base;
+    const uint32_t local0 = (uint32_t)warp * (32 * OS_ITEMS) + lane;   // + 32 j: this thread's j-th item in the tile
+
+    if (HAS_VALS) {
+        const uint32_t* tvals = vals_in + tile_base;
+        if ((reinterpret_cast<uintptr_t>(tvals) & 15) == 0) {
+#pragma unroll
+            for (int c = 0; c < OS_ITEMS / 4; ++c) {
+                const uint32_t e = 4 * (c * OS_THREADS + threadIdx.x);
+                if (e + 4 <= count_tile) cp_async16(sm.stage + e, tvals + e);
+                else
+                    for (uint32_t k = e; k < count_tile; ++k) cp_async4(sm.stage + k, tvals + k);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < OS_ITEMS; ++j) {
+                const uint32_t e = j * OS_THREADS + threadIdx.x;
+                if (e < count_tile) cp_async4(sm.stage + e, tvals + e);
+            }
+        }
+        cp_async_commit();
+    }
+    uint32_t key[OS_ITEMS];
+#pragma unroll
+    for (int j = 0; j < OS_ITEMS; ++j) {
+        const uint32_t li = local0 + 32 * j;
+        key[j] = li < count_tile ? tkeys[li] : 0xFFFFFFFFu;
+    }
+    // multi-kernel flavour: this tile's scatter bases are an L2 round trip away - fetch them under the ranking phase
+    // digits are < nbins = mask + 1 <= RS_RADIX: thread t < nbins owns digit t (its count, its look-back column)
+    const bool owner = threadIdx.x <= mask;
+    uint32_t dstart = 0;
+    if (owner) dstart = LOOKBACK ? digit_base[threadIdx.x] : digit_base[(size_t)threadIdx.x * nblocks + tile];
+    // Out-of-range items only exist at the very end of the last tile; give them the highest
+    // digit (`mask`) so they rank after every real key of that digit and are simply not written.
+    // All match operations are issued before the dependent shared-memory chain starts.
     unsigned peers[OS_ITEMS];
 #pragma unroll
     for (int j = 0; j < OS_ITEMS; ++j) {
-        size_t i = warp_base + (size_t)j * 32 + lane;
-        key[j] = i < n ? keys_in[i] : 0xFFFFFFFFu;
-    }
-    // Out-of-range items only exist at the very end of the last tile; give them the highest
-    // digit so they rank after every real key of that digit and are simply not written.
-    // All match operations are issued before the dependent shared-memory chain starts.
-#pragma unroll
-    for (int j = 0; j < OS_ITEMS; ++j) {
-        size_t i = warp_base + (size_t)j * 32 + lane;
-        uint32_t d = i < n ? ((key[j] >> shift) & mask) : (RS_RADIX - 1);
+        const uint32_t d = local0 + 32 * j < count_tile ? ((key[j] >> shift) & mask) : mask;
         peers[j] = __match_any_sync(0xffffffffu, d);
     }
+    // (one ballot per digit bit instead of MATCH.ANY was measured slower: tile partition 0.270 vs 0.241 ms at C3)
+    uint32_t rank2[OS_ITEMS / 2];   // ranks inside the warp's run of the digit, two 16-bit fields per register
+    uint16_t* const my_hist = sm.warp_hist[warp];
 #pragma unroll
     for (int j = 0; j < OS_ITEMS; ++j) {
-        size_t i = warp_base + (size_t)j * 32 + lane;
-        uint32_t d = i < n ? ((key[j] >> shift) & mask) : (RS_RADIX - 1);
-        uint32_t before = warp_hist[warp][d];
+        const uint32_t d = local0 + 32 * j < count_tile ? ((key[j] >> shift) & mask) : mask;
+        const uint32_t before = my_hist[d];
         __syncwarp();
-        if ((peers[j] & lt) == 0) warp_hist[warp][d] = (uint16_t)(before + __popc(peers[j]));
+        if ((peers[j] & lt) == 0) my_hist[d] = (uint16_t)(before + __popc(peers[j]));
         __syncwarp();
-        rank[j] = before + __popc(peers[j] & lt);
+        const uint32_t r = before + __popc(peers[j] & lt);
+        if (j & 1) rank2[j >> 1] |= r << 16; else rank2[j >> 1] = r;
     }
     __syncthreads();
-    // threads 0..255: thread t owns digit t
-    const bool owner = threadIdx.x < RS_RADIX;
     uint32_t run = 0;
     if (owner) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            uint32_t c = warp_hist[w][threadIdx.x];
-            warp_hist[w][threadIdx.x] = (uint16_t)run;
+        for (int w = 0; w < OS_WARPS; ++w) {
+            const uint32_t c = sm.warp_hist[w][threadIdx.x];
+            sm.warp_hist[w][threadIdx.x] = (uint16_t)run;
             run += c;
         }
     }
-    // Padding of the last tile was counted under digit RS_RADIX-1; it must not be published
+    // Padding of the last tile was counted under the highest digit; it must not be published
     // (it ranks after every real key of that digit, so local positions stay right).
-    const size_t remaining = n - tile_base;
-    const uint32_t count_tile = remaining < (size_t)OS_TILE ? (uint32_t)remaining : (uint32_t)OS_TILE;
     uint32_t real = run;
-    if (threadIdx.x == RS_RADIX - 1) real -= (uint32_t)OS_TILE - count_tile;
+    if (threadIdx.x == mask) real -= (uint32_t)OS_TILE - count_tile;
     uint32_t* my_status = status + (size_t)tile * RS_RADIX + threadIdx.x;
     if (LOOKBACK && owner) st_status(my_status, real | (tile == 0 ? OS_PREFIX : OS_AGG));
-    uint32_t tot;
-    const uint32_t start = block_excl_scan<OS_THREADS>(run, &tot);
-    uint32_t dstart = 0;
-    if (LOOKBACK) dstart = block_excl_scan<OS_THREADS>(owner ? digit_hist[threadIdx.x] : 0u, &tot);
-    else if (owner) dstart = digit_hist[(size_t)threadIdx.x * nblocks + tile];
-    if (owner) bin_start[threadIdx.x] = start;
+    // exclusive scan of the digit totals: the owners sit in warps 0..7 (run = 0 elsewhere)
+    const uint32_t incl = warp_incl_scan(run, lane);
+    if (warp < RS_RADIX / 32 && lane == 31) sm.warp_total[warp] = incl;
+    if (HAS_VALS) cp_async_wait_all();
+    __syncthreads();
+    uint32_t start = incl - run;
+    if (owner) {
+#pragma unroll
+        for (int w = 0; w < RS_RADIX / 32 - 1; ++w) start += w < warp ? sm.warp_total[w] : 0u;
+        sm.bin_start[threadIdx.x] = start;
+    }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < OS_ITEMS; ++j) {
-        size_t i = warp_base + (size_t)j * 32 + lane;
-        uint32_t d = i < n ? ((key[j] >> shift) & mask) : (RS_RADIX - 1);
-        uint32_t pos = bin_start[d] + warp_hist[warp][d] + rank[j];
-        skeys[pos] = key[j];
-        // values are only loaded now, so they are not live across the ranking phase
-        svals[pos] = i < n ? (HAS_VALS ? __ldg(vals_in + i) : (uint32_t)i) : 0u;
+        const uint32_t li = local0 + 32 * j;
+        const uint32_t d = li < count_tile ? ((key[j] >> shift) & mask) : mask;
+        const uint32_t r = (j & 1) ? (rank2[j >> 1] >> 16) : (rank2[j >> 1] & 0xFFFFu);
+        const uint32_t pos = sm.bin_start[d] + my_hist[d] + r;
+        sm.skeys[pos] = key[j];
+        sm.svals[pos] = HAS_VALS ? sm.stage[li] : (uint32_t)tile_base + li;
     }
     // look-back over earlier tiles, one digit column per thread
     if (owner) {
         uint32_t excl = 0;
         if (LOOKBACK && tile != 0) {
+            // LBW predecessors are read per round trip (independent loads) and consumed nearest first up to the
+            // first one that has not published yet: when a whole wave of tiles starts together (the depth sort is
+            // barely two waves) the inclusive prefixes then spread ~sqrt(LBW) times faster than one at a time
             uint32_t spins = 0;
-            bool failed = false;
-            for (uint32_t look = tile; look-- > 0 && !failed;) {
-                uint32_t v;
-                while (((v = ld_status(status + (size_t)look * RS_RADIX + threadIdx.x)) >> 30) == 0) {
-                    if (++spins > OS_SPIN_LIMIT) { failed = true; break; }
+            bool failed = false, done = false;
+            int left = (int)tile;   // predecessors not yet summed; sp = status word of the nearest of them
+            const uint32_t* sp = status + (size_t)(tile - 1) * RS_RADIX + threadIdx.x;
+            while (!done && !failed) {
+                uint32_t v[LBW];
+#pragma unroll
+                for (int i = 0; i < LBW; ++i) v[i] = i < left ? ld_status(sp - (size_t)i * RS_RADIX) : OS_PREFIX;
+                int consumed = 0;
+#pragma unroll
+                for (int i = 0; i < LBW; ++i) {
+                    const uint32_t f = v[i] >> 30;
+                    if (!done && consumed == i && f != 0u) {
+                        excl += v[i] & OS_VALUE;
+                        consumed = i + 1;
+                        done = f == 2u;
+                    }
                 }
-                if (failed) break;
-                excl += v & OS_VALUE;
-                if ((v >> 30) == 2u) break;
+                left -= consumed;
+                sp -= (size_t)consumed * RS_RADIX;
+                if (consumed == 0 && ++spins > OS_SPIN_LIMIT) failed = true;
             }
             if (failed) atomicOr(err, 1u);
             st_status(my_status, (excl + real) | OS_PREFIX);
         }
-        bin_base[threadIdx.x] = dstart + excl;
+        sm.bin_off[threadIdx.x] = dstart + excl - start;
     }
     __syncthreads();
     for (uint32_t p = threadIdx.x; p < count_tile; p += OS_THREADS) {
-        uint32_t k = skeys[p];
-        uint32_t d = (k >> shift) & mask;
-        size_t g = (size_t)bin_base[d] + (p - bin_start[d]);
+        const uint32_t k = sm.skeys[p];
+        const size_t g = (size_t)(sm.bin_off[(k >> shift) & mask] + p);
         if (WRITE_KEYS) keys_out[g] = k;
-        vals_out[g] = svals[p];
+        const uint32_t v = sm.svals[p];
+        vals_out[g] = v;
+        if (gather.src != nullptr) {   // uniform
+            const uint2 rc = __ldg(gather.src + v);
+            gather.dst[g] = rc;
+            gather.cnt[g] = (rc.y & 0xFFFFu) * (rc.y >> 16);
+        }
     }
+}
+
+// Exclusive prefix (in place) of `passes` global digit histograms — the look-back passes take their digit bases from it.
+__global__ void __launch_bounds__(RS_RADIX)
+digit_scan_kernel(uint32_t* __restrict__ digit_hist) {
+    uint32_t* h = digit_hist + (size_t)blockIdx.x * RS_RADIX;
+    uint32_t tot;
+    const uint32_t v = h[threadIdx.x];
+    const uint32_t ex = block_excl_scan<RS_RADIX>(v, &tot);
+    h[threadIdx.x] = ex;
+}
+
+template <bool HV, bool WK, bool LB, int LBW>
+static void launch_pass(unsigned nb, cudaStream_t s, const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
+                        uint32_t* vals_out, size_t n, int shift, uint32_t mask, const uint32_t* digit_base,
+                        uint32_t* status, uint32_t* ticket, uint32_t* err, const uint32_t* n_dev, GatherRect gather) {
+    auto k = onesweep_pass_kernel<HV, WK, LB, LBW>;
+    // 58 KB of dynamic shared memory: opt in (per device, so set on every launch; the call only records a number)
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OsSmem));
+    k<<<nb, OS_THREADS, sizeof(OsSmem), s>>>(keys_in, vals_in, keys_out, vals_out, n, shift, mask, digit_base, status,
+                                             ticket, err, nb, n_dev, gather);
+}
+template <bool LB>
+static void launch_pass_any(unsigned nb, cudaStream_t s, const uint32_t* keys_in, const uint32_t* vals_in,
+                            uint32_t* keys_out, uint32_t* vals_out, size_t n, int shift, uint32_t mask,
+                            const uint32_t* digit_base, uint32_t* status, uint32_t* ticket, uint32_t* err,
+                            const uint32_t* n_dev, int lb_window, GatherRect gather) {
+#define W3D_PASS(HV, WK)                                                                                          \
+    do {                                                                                                          \
+        if (!LB || lb_window <= 1)                                                                                \
+            launch_pass<HV, WK, LB, 1>(nb, s, keys_in, vals_in, keys_out, vals_out, n, shift, mask, digit_base,   \
+                                       status, ticket, err, n_dev, gather);                                       \
+        else if (lb_window <= 4)                                                                                  \
+            launch_pass<HV, WK, LB, 4>(nb, s, keys_in, vals_in, keys_out, vals_out, n, shift, mask, digit_base,   \
+                                       status, ticket, err, n_dev, gather);                                       \
+        else if (lb_window <= 8)                                                                                  \
+            launch_pass<HV, WK, LB, 8>(nb, s, keys_in, vals_in, keys_out, vals_out, n, shift, mask, digit_base,   \
+                                       status, ticket, err, n_dev, gather);                                       \
+        else                                                                                                      \
+            launch_pass<HV, WK, LB, 16>(nb, s, keys_in, vals_in, keys_out, vals_out, n, shift, mask, digit_base,  \
+                                        status, ticket, err, n_dev, gather);                                      \
+    } while (0)
+    if (vals_in) {
+        if (keys_out) W3D_PASS(true, true); else W3D_PASS(true, false);
+    } else {
+        if (keys_out) W3D_PASS(false, true); else W3D_PASS(false, false);
+    }
+#undef W3D_PASS
+}
+
+int radix_pass_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out,
+                   uint32_t* vals_out, size_t n, int shift, int bits, uint32_t* hist,
+                   uint32_t* scan_scratch, cudaStream_t s, bool debug, const uint32_t* n_dev, GatherRect gather) {
+    if (n == 0) return WAST3D_OK;
+    if (bits < 1 || bits > 8) return WAST3D_ERR_INVALID_ARGUMENT;
+    if (n > 0xFFFFFFFFull - RS_TILE) return WAST3D_ERR_OVERFLOW;
+    const unsigned nb = (unsigned)rs_num_blocks(n);
+    const uint32_t mask = (1u << bits) - 1u;
+    radix_hist_kernel<<<nb, RS_THREADS, 0, s>>>(keys_in, n, shift, mask, hist, nb, n_dev);
+    W3D_AFTER_LAUNCH(s, debug);
+    int st = scan_exclusive_u32(hist, nullptr, hist, (size_t)nb * RS_RADIX, scan_scratch, nullptr,
+                                s, debug);
+    if (st != WAST3D_OK) return st;
+    launch_pass_any<false>(nb, s, keys_in, vals_in, keys_out, vals_out, n, shift, mask, hist, nullptr, nullptr, nullptr,
+                           n_dev, 1, gather);
+    W3D_AFTER_LAUNCH(s, debug);
+    return WAST3D_OK;
 }
 
 size_t onesweep_workspace_words(size_t n, int passes) {
@@ -370,6 +422,15 @@ int onesweep_prepare(uint32_t* ws, size_t n, int passes, cudaStream_t s) {
     return WAST3D_OK;
 }
 
+// The look-back passes read digit BASES: turn the `passes` global digit histograms at the head of the workspace into
+// their exclusive prefixes (callers that fill onesweep_digit_hist() themselves call this afterwards).
+int onesweep_scan_digits(uint32_t* ws, size_t n, int passes, cudaStream_t s, bool debug) {
+    if (n == 0) return WAST3D_OK;
+    digit_scan_kernel<<<passes, RS_RADIX, 0, s>>>(OnesweepWs(ws, n, passes).digit_hist);
+    W3D_AFTER_LAUNCH(s, debug);
+    return WAST3D_OK;
+}
+
 int onesweep_hist(const uint32_t* keys, size_t n, int passes, const int* shifts, const int* bits,
                   uint32_t* ws, cudaStream_t s, bool debug) {
     if (n == 0) return WAST3D_OK;
@@ -386,27 +447,31 @@ int onesweep_hist(const uint32_t* keys, size_t n, int passes, const int* shifts,
     onesweep_hist_kernel<<<(unsigned)blocks, 256, 0, s>>>(keys, n, passes, make_int4(sh[0], sh[1], sh[2], sh[3]),
                                                           make_int4(mk[0], mk[1], mk[2], mk[3]), w.digit_hist);
     W3D_AFTER_LAUNCH(s, debug);
-    return WAST3D_OK;
+    return onesweep_scan_digits(ws, n, passes, s, debug);
+}
+
+// WAST3D_LB_WINDOW: predecessors read per look-back round trip (1, 4, 8 or 16; default 8)
+static int lookback_window() {
+    static const int w = [] {
+        const char* e = getenv("WAST3D_LB_WINDOW");
+        int v = e ? atoi(e) : 8;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    return w;
 }
 
 int onesweep_pass(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
-                  size_t n, int shift, int bits, uint32_t* ws, int passes, int pass, cudaStream_t s, bool debug) {
+                  size_t n, int shift, int bits, uint32_t* ws, int passes, int pass, cudaStream_t s, bool debug,
+                  const uint32_t* n_dev, GatherRect gather) {
     if (n == 0) return WAST3D_OK;
     if (bits < 1 || bits > 8 || pass < 0 || pass >= passes) return WAST3D_ERR_INVALID_ARGUMENT;
     if (n >= (size_t)OS_VALUE) return WAST3D_ERR_OVERFLOW;
     const unsigned nb = (unsigned)rs_num_blocks(n);
     const uint32_t mask = (1u << bits) - 1u;
     OnesweepWs w(ws, n, passes);
-#define W3D_OS(HV, WK)                                                                                   \
-    onesweep_pass_kernel<HV, WK, true><<<nb, OS_THREADS, 0, s>>>(keys_in, vals_in, keys_out, vals_out, n, shift, \
-                                                                 mask, w.digit_hist + (size_t)pass * RS_RADIX,   \
-                                                                 w.status(pass), w.ticket(pass), w.err, nb, nullptr)
-    if (vals_in) {
-        if (keys_out) W3D_OS(true, true); else W3D_OS(true, false);
-    } else {
-        if (keys_out) W3D_OS(false, true); else W3D_OS(false, false);
-    }
-#undef W3D_OS
+    launch_pass_any<true>(nb, s, keys_in, vals_in, keys_out, vals_out, n, shift, mask,
+                          w.digit_hist + (size_t)pass * RS_RADIX, w.status(pass), w.ticket(pass), w.err, n_dev,
+                          lookback_window(), gather);
     W3D_AFTER_LAUNCH(s, debug);
     return WAST3D_OK;
 }
@@ -415,42 +480,6 @@ uint32_t* onesweep_digit_hist(uint32_t* ws, size_t n, int passes, int pass) {
     return OnesweepWs(ws, n, passes).digit_hist + (size_t)pass * RS_RADIX;
 }
 uint32_t* onesweep_error_word(uint32_t* ws, size_t n, int passes) { return OnesweepWs(ws, n, passes).err; }
-
-// Single-kernel exclusive scan with look-back.  ws: 2 + nblocks zero-initialised words
-// (ticket, error, status[nblocks]).  The look-back is done by warp 0, 32 predecessors per step.
-__device__ __forceinline__ uint32_t lookback_warp(uint32_t* status, uint32_t tile, uint32_t count,
-                                                  uint32_t* err, int lane) {
-    if (tile == 0) {
-        if (lane == 0) st_status(status, count | OS_PREFIX);
-        return 0;
-    }
-    if (lane == 0) st_status(status + tile, count | OS_AGG);
-    uint32_t excl = 0, spins = 0;
-    int look = (int)tile;  // exclusive upper end of the window
-    while (true) {
-        const int idx = look - 1 - lane;
-        uint32_t v = idx >= 0 ? ld_status(status + idx) : OS_PREFIX;  // before tile 0: empty prefix
-        const unsigned is_prefix = __ballot_sync(0xffffffffu, (v >> 30) == 2u);
-        const unsigned invalid = __ballot_sync(0xffffffffu, (v >> 30) == 0u);
-        const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;      // nearest predecessor with a prefix
-        const unsigned need = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);
-        if (invalid & need) {
-            if (++spins > OS_SPIN_LIMIT) {
-                if (lane == 0) atomicOr(err, 1u);
-                break;
-            }
-            continue;
-        }
-        uint32_t c = lane <= first ? (v & OS_VALUE) : 0u;
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-        excl += c;
-        if (first < 32) break;
-        look -= 32;
-    }
-    if (lane == 0) st_status(status + tile, (excl + count) | OS_PREFIX);
-    return excl;
-}
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_lookback_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ perm,
@@ -542,7 +571,7 @@ extern "C" int wast3d_test_sort_pairs(size_t n, const uint32_t* keys_in, const u
         uint32_t* ko = to_out ? keys_out : ka;
         uint32_t* vo = to_out ? vals_out : va;
         if (mode == 0) st = radix_pass_u32(kin, vin, ko, vo, n, shifts[p], bits[p], hist, scr, s, false, nullptr);
-        else st = onesweep_pass(kin, vin, ko, vo, n, shifts[p], bits[p], ws, passes, p, s, false);
+        else st = onesweep_pass(kin, vin, ko, vo, n, shifts[p], bits[p], ws, passes, p, s, false, nullptr);
         kin = ko;
         vin = vo;
     }
