@@ -72,14 +72,19 @@ __device__ __forceinline__ float3 sh_to_rgb(int deg, const float* sh_dc, const f
 // (forward.cu:355) is certain to reject.
 __device__ __forceinline__ float2 cutoff_extent(float A, float B, float C, float o) {
     if (!(o >= 1.0f / 255.0f)) return make_float2(-1.0f, -1.0f);  // alpha <= o < 1/255 always
-    const double det = (double)A * (double)C - (double)B * (double)B;
+    // det = A C - B^2 without cancellation (Kahan: the rounding error of B*B is recovered with one fma), so that fp32
+    // is enough: every other step loses a few ulp against pads of 1e-3 (measured: the double-precision log / sqrt of
+    // the first version were 9 % of K1's instructions)
+    const float w = __fmul_rn(B, B);
+    const float det = __fadd_rn(__fmaf_rn(A, C, -w), __fmaf_rn(-B, B, w));
     const float inf = __int_as_float(0x7f800000);
-    if (!(det > 0.0) || !(A > 0.f) || !(C > 0.f)) return make_float2(inf, inf);
-    const double tau0 = log(255.0 * (double)o);
-    const double kappa = (double)A * (double)C / det;
-    const double tau = tau0 + 1e-3 + tau0 * (1e-3 + 4e-6 * kappa);
-    const float hx = (float)(sqrt(2.0 * tau * (double)C / det) * 1.001 + 0.05);
-    const float hy = (float)(sqrt(2.0 * tau * (double)A / det) * 1.001 + 0.05);
+    if (!(det > 0.f) || !(A > 0.f) || !(C > 0.f)) return make_float2(inf, inf);
+    const float tau0 = logf(255.0f * o);
+    const float inv_det = 1.0f / det;
+    const float kappa = A * C * inv_det;
+    const float tau = tau0 + 1e-3f + tau0 * (1e-3f + 4e-6f * kappa);
+    const float hx = sqrtf(2.0f * tau * C * inv_det) * 1.001f + 0.05f;
+    const float hy = sqrtf(2.0f * tau * A * inv_det) * 1.001f + 0.05f;
     if (!(hx == hx) || !(hy == hy)) return make_float2(inf, inf);
     return make_float2(hx, hy);
 }

@@ -367,13 +367,16 @@ __device__ __forceinline__ void stage_rows_linear(const float* __restrict__ g_ro
                                                   float* s_rows, int lane) {
     const int total = rows_valid * row_floats;
     const int total4 = (((size_t)g_rows & 15) == 0 && row_floats >= 4) ? (total >> 2) : 0;
-    int g = (4 * lane) / row_floats, e = 4 * lane - g * row_floats;
+    // row of a float4: f / row_floats = umulhi(f, ceil(2^32 / row_floats)), exact for f < 2^16 (f < 32 rows x 48 floats)
+    const uint32_t magic = 0xFFFFFFFFu / (uint32_t)max(row_floats, 2) + 1u;
     for (int q = lane; q < total4; q += 32) {
-        const bool spill = e + 3 >= row_floats;  // the float4 reaches into row g + 1
-        const bool want = (((need >> g) & 1u) && e < used) || (spill && ((need >> (g + 1)) & 1u));
+        const uint32_t f = 4u * (uint32_t)q;
+        const uint32_t g = __umulhi(f, magic);
+        const int e = (int)(f - g * (uint32_t)row_floats);
+        const unsigned rows = need >> g;            // bit 0: row g, bit 1: row g + 1
+        const bool spill = e + 3 >= row_floats;     // the float4 reaches into row g + 1
+        const bool want = ((rows & 1u) && e < used) || (spill && (rows & 2u));
         if (want) cp_async16(s_rows + 4 * q, g_rows + 4 * q);
-        e += 128;
-        while (e >= row_floats) { e -= row_floats; ++g; }
     }
     cp_async_commit();
     for (int i = (total4 << 2) + lane; i < total; i += 32) {  // unaligned base or tail
