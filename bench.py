@@ -1026,6 +1026,45 @@ def main():
         except Exception as e:  # a side metric never fails the bench line
             extra["notebook_loop_29_2"] = {"error": repr(e)}
 
+    # ---- the whole step as ONE CUDA graph (wast3d_b200.graphed.GraphedStep): graph-safe forward, Adam step count on
+    # the device, camera / targets in static buffers; same model, same loss, same views as the timed region, which
+    # stays eager because its dominant kernel is bracketed by CUDA events inside the library (roofline.kernel_ms)
+    if rank == 0 and world == 1 and args.sync == "backward" and not args.no_extra:
+        try:
+            from wast3d_b200.graphed import GraphedStep
+            torch.cuda.empty_cache()
+            gs = GraphedStep(pc, pipe, bg, cams[0], lambda o, t, d: style_loss(o, t, d, fused=args.loss == "fused"),
+                             target=tgt_dev[0], depth_target=dtgt_dev[0], warmup_cameras=cams[: min(len(cams), 8)])
+
+            def g_step(i):
+                gs.set_view(cams[i % len(cams)])
+                gs.set_targets(tgt_dev[i % 2], dtgt_dev[i % 2])
+                return gs.step()
+            for i in range(10):
+                g_step(i)
+            r_seen = gs.check()
+            ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t_host = time.perf_counter()
+            ev_a.record()
+            for i in range(args.steps):
+                g_step(10 + i)
+            ev_b.record()
+            t_host = (time.perf_counter() - t_host) * 1e3 / args.steps
+            gs.check()
+            g_ms = ev_a.elapsed_time(ev_b) / args.steps
+            extra["cuda_graph_step"] = {
+                "ms_per_step": round(g_ms, 4), "iters_per_s": round(1e3 / g_ms, 2), "steps": args.steps,
+                "eager_ms_per_step": round(ms_step, 4), "speedup_vs_eager": round(ms_step / g_ms, 4),
+                "host_issue_ms_per_step": round(t_host, 4), "kernels_per_graph": int(gs.launches_per_step),
+                "instance_capacity": int(gs.capacity), "instances_seen": int(r_seen),
+                "what": "sampling offsets + render (graph-safe forward) + fused pixel loss + backward with Adam in the "
+                        "per-Gaussian kernel (step count and bias corrections on the device), replayed with one launch; "
+                        "per step the host copies the camera (3 small tensors) and the targets into static buffers"}
+            del gs
+            torch.cuda.empty_cache()
+        except Exception as e:  # a side metric never fails the bench line
+            extra["cuda_graph_step"] = {"error": repr(e)}
+
     # ---- view-parallel replicas must still be bit-identical after the run (every element is computed by one rank)
     replicas_equal = None
     if world > 1:

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define WAST3D_ABI_VERSION 6
+#define WAST3D_ABI_VERSION 7
 
 enum wast3d_status {
     WAST3D_OK = 0,
@@ -173,7 +173,19 @@ typedef struct wast3d_adam_group {
     float lr, beta1, beta2, eps;
     int step;
     int reserved;
+    /* ABI v7.  NULL: lr and step above give the bias-corrected step size (host values, baked into the launch).
+     * Non-NULL: DEVICE [2] floats {lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)} that the kernel reads when it RUNS —
+     * written by wast3d_adam_schedule_step on the same stream, so that a CUDA graph of the step can be replayed
+     * (lr and step are then ignored; step >= 1 is still required). */
+    const float* schedule_dev;
 } wast3d_adam_group;
+/* One optimizer tick on the device (ABI v7): *step_dev += 1, then for every group k
+ *   schedule_dev[2k] = lr_k / (1 - beta1_k^t),  schedule_dev[2k + 1] = 1 / sqrt(1 - beta2_k^t)      (t = *step_dev)
+ * in double precision like torch.optim.Adam's host arithmetic (scene/gaussian_model.py:154-163 configures it);
+ * hyper_dev [ngroups][3] doubles = {lr, beta1, beta2} per group, rewritten by the caller whenever a learning rate
+ * changes (scene/gaussian_model.py:169-176 update_learning_rate).  One tiny kernel; capturable. */
+int wast3d_adam_schedule_step(int ngroups, const double* hyper_dev, unsigned long long* step_dev,
+                              float* schedule_dev, void* stream);
 int wast3d_raster_backward_raw_adam(const wast3d_raster_params* prm, int num_rendered, const int* radii,
                                     void* geom_buffer, void* binning_buffer, void* img_buffer,
                                     const float* dL_dpix, const float* dL_ddepth,

@@ -40,7 +40,7 @@ def test_python_binding_covers_header(built):
     _lib.load()
     assert _lib.MISSING == []
     assert sorted(_lib.SIGNATURES) == header_symbols()
-    assert _lib.load().wast3d_abi_version() == 6
+    assert _lib.load().wast3d_abi_version() == 7
     assert _lib.load().wast3d_strerror(0) == b"ok"
     assert b"no CPU fallback" in _lib.load().wast3d_strerror(4)
 

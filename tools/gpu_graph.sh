@@ -1,0 +1,12 @@
+#!/bin/bash
+TAG=${1:-g}
+mkdir -p gpurun_out
+for cfg in c3 c2 c5; do
+(timeout 500 python bench.py --config $cfg --no-cpu-baseline --no-ref-cuda > gpurun_out/bench_${cfg}_$TAG.json 2> gpurun_out/bench_${cfg}_$TAG.err; echo "bench $cfg rc=$?"; tail -2 gpurun_out/bench_${cfg}_$TAG.err
+python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_${cfg}_$TAG.json"))
+print("$cfg", round(d["value"],1), round(d["ms_per_step"],4), "e2e", round(d["e2e"]["value"],1), d["extra"].get("cuda_graph_step"))
+PY
+)
+done

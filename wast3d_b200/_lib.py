@@ -56,7 +56,7 @@ class AdamGroup(C.Structure):
 
     _fields_ = [("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("lr", C.c_float),
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int),
-                ("reserved", C.c_int)]
+                ("reserved", C.c_int), ("schedule_dev", C.c_void_p)]
 
 
 class PairArgs(C.Structure):
@@ -72,6 +72,7 @@ _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 SIGNATURES = {
     "wast3d_strerror": (C.c_char_p, [_i]),
     "wast3d_abi_version": (_i, []),
+    "wast3d_adam_schedule_step": (_i, [_i, _vp, _vp, _vp, _vp]),
     "wast3d_device_check": (_i, [_i]),
     "wast3d_raster_forward": (_i, [C.POINTER(RasterParams), ALLOC_FN, _vp, ALLOC_FN, _vp, ALLOC_FN, _vp,
                                    _vp, _vp, _vp, C.POINTER(_i), _vp]),

@@ -62,3 +62,30 @@ extern "C" int wast3d_adam_step(size_t n, float* param, const float* grad, float
     W3D_AFTER_LAUNCH(s, false);
     return WAST3D_OK;
 }
+
+namespace w3d {
+// wast3d_adam_schedule_step: the optimizer's step count and bias-corrected scalars live on the device, so that a
+// captured launch sequence (CUDA graph) advances them itself.  Same double-precision expressions as adam_scalars().
+__global__ void adam_schedule_kernel(int ngroups, const double* __restrict__ hyper, unsigned long long* __restrict__ step,
+                                     float* __restrict__ schedule) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long t = *step + 1ull;
+    *step = t;
+    for (int k = 0; k < ngroups; ++k) {
+        const double lr = hyper[3 * k], b1 = hyper[3 * k + 1], b2 = hyper[3 * k + 2];
+        const double bc1 = 1.0 - pow(b1, (double)t);
+        const double bc2 = 1.0 - pow(b2, (double)t);
+        schedule[2 * k] = (float)(lr / bc1);
+        schedule[2 * k + 1] = (float)(1.0 / sqrt(bc2));
+    }
+}
+}  // namespace w3d
+
+extern "C" int wast3d_adam_schedule_step(int ngroups, const double* hyper_dev, unsigned long long* step_dev,
+                                         float* schedule_dev, void* stream_v) {
+    if (ngroups < 1 || !hyper_dev || !step_dev || !schedule_dev) return WAST3D_ERR_INVALID_ARGUMENT;
+    cudaStream_t s = (cudaStream_t)stream_v;
+    w3d::adam_schedule_kernel<<<1, 32, 0, s>>>(ngroups, hyper_dev, step_dev, schedule_dev);
+    W3D_AFTER_LAUNCH(s, false);
+    return WAST3D_OK;
+}

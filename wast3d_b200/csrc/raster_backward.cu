@@ -562,23 +562,31 @@ struct AdamSlot {  // one GaussianModel parameter group
     float* m;
     float* v;
     float step_size, inv_bc2_sqrt, one_minus_b1, b2, one_minus_b2, eps;
+    const float* sched;   // optional device {step_size, inv_bc2_sqrt} read at run time (wast3d_adam_group::schedule_dev)
 };
 struct AdamFused {
     AdamSlot g[6];  // xyz, f_dc, f_rest, opacity, scaling, rotation
     int l2_prefetch;  // 1: each warp asks L2 for its parameter / moment tiles before the chain rule
 };
 
-__device__ __forceinline__ float adam_elem(float p, float g, float& m, float& v, const AdamSlot& s) {
-    return adam_update(p, g, m, v, s.one_minus_b1, s.b2, s.one_minus_b2, s.step_size, s.inv_bc2_sqrt, s.eps);
+struct AdamStep { float step_size, inv_bc2_sqrt; };   // the two step-dependent scalars of a group
+__device__ __forceinline__ AdamStep adam_step_scalars(const AdamSlot& s) {
+    AdamStep a = {s.step_size, s.inv_bc2_sqrt};
+    if (s.sched != nullptr) { a.step_size = __ldg(s.sched); a.inv_bc2_sqrt = __ldg(s.sched + 1); }   // uniform
+    return a;
+}
+__device__ __forceinline__ float adam_elem(float p, float g, float& m, float& v, const AdamSlot& s, const AdamStep& a) {
+    return adam_update(p, g, m, v, s.one_minus_b1, s.b2, s.one_minus_b2, a.step_size, a.inv_bc2_sqrt, s.eps);
 }
 // updated parameter values are also returned in p_new (the next view's projection consumes them from registers)
 template <int N>
 __device__ __forceinline__ void adam_small(const AdamSlot& s, size_t base, const float (&g)[N], float (&p_new)[N]) {
     float m[N], v[N];
+    const AdamStep a = adam_step_scalars(s);
 #pragma unroll
     for (int k = 0; k < N; ++k) { p_new[k] = s.p[base + k]; m[k] = s.m[base + k]; v[k] = s.v[base + k]; }
 #pragma unroll
-    for (int k = 0; k < N; ++k) p_new[k] = adam_elem(p_new[k], g[k], m[k], v[k], s);
+    for (int k = 0; k < N; ++k) p_new[k] = adam_elem(p_new[k], g[k], m[k], v[k], s, a);
 #pragma unroll
     for (int k = 0; k < N; ++k) { s.p[base + k] = p_new[k]; s.m[base + k] = m[k]; s.v[base + k] = v[k]; }
 }
@@ -593,6 +601,7 @@ __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base,
     float* P_ = s.p + base;
     float* M_ = s.m + base;
     float* V_ = s.v + base;
+    const AdamStep a = adam_step_scalars(s);
     const bool vec = (total & 3) == 0 && ((((size_t)P_ | (size_t)M_ | (size_t)V_ | (size_t)s_grad) & 15) == 0) &&
                      (g_out == nullptr || (((size_t)(g_out + base)) & 15) == 0);
     if (vec) {
@@ -612,10 +621,10 @@ __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base,
                 const int q = q0 + 32 * u + lane;
                 if (q < n4) {
                     const float4 g = *reinterpret_cast<const float4*>(s_grad + 4 * q);
-                    p[u].x = adam_elem(p[u].x, g.x, m[u].x, v[u].x, s);
-                    p[u].y = adam_elem(p[u].y, g.y, m[u].y, v[u].y, s);
-                    p[u].z = adam_elem(p[u].z, g.z, m[u].z, v[u].z, s);
-                    p[u].w = adam_elem(p[u].w, g.w, m[u].w, v[u].w, s);
+                    p[u].x = adam_elem(p[u].x, g.x, m[u].x, v[u].x, s, a);
+                    p[u].y = adam_elem(p[u].y, g.y, m[u].y, v[u].y, s, a);
+                    p[u].z = adam_elem(p[u].z, g.z, m[u].z, v[u].z, s, a);
+                    p[u].w = adam_elem(p[u].w, g.w, m[u].w, v[u].w, s, a);
                     P4[q] = p[u];
                     __stcs(M4 + q, m[u]);
                     __stcs(V4 + q, v[u]);
@@ -628,7 +637,7 @@ __device__ __forceinline__ void adam_rows_linear(const AdamSlot& s, size_t base,
         for (int q = lane; q < total; q += 32) {
             const float g = s_grad[q];
             float m = M_[q], v = V_[q];
-            const float pn = adam_elem(P_[q], g, m, v, s);
+            const float pn = adam_elem(P_[q], g, m, v, s, a);
             P_[q] = pn;
             M_[q] = m;
             V_[q] = v;
@@ -1115,10 +1124,20 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
         ProfScope ps(PS_RENDER_BWD, s);
         // the buffers below are sized by the ACTUAL instance count; after a graph-safe forward `num_rendered` is only
         // the capacity the binning buffer was carved for, so read the count (a test mode may synchronise)
-        uint32_t r_dev = 0;
-        W3D_CUDA_TRY(cudaMemcpyAsync(&r_dev, g.totals, sizeof(r_dev), cudaMemcpyDeviceToHost, s));
-        W3D_CUDA_TRY(cudaStreamSynchronize(s));
-        const size_t R = r_dev < (uint32_t)num_rendered ? r_dev : (size_t)num_rendered;
+        // While the stream is being captured into a CUDA graph nothing may be read back: the buffers then take the
+        // capacity and the sort passes the device-side count.
+        cudaStreamCaptureStatus capture = cudaStreamCaptureStatusNone;
+        W3D_CUDA_TRY(cudaStreamIsCapturing(s, &capture));
+        const uint32_t* n_dev = nullptr;
+        size_t R = (size_t)num_rendered;
+        if (capture == cudaStreamCaptureStatusNone) {
+            uint32_t r_dev = 0;
+            W3D_CUDA_TRY(cudaMemcpyAsync(&r_dev, g.totals, sizeof(r_dev), cudaMemcpyDeviceToHost, s));
+            W3D_CUDA_TRY(cudaStreamSynchronize(s));
+            if (r_dev < (uint32_t)num_rendered) R = r_dev;
+        } else {
+            n_dev = g.totals;
+        }
         const uint32_t* plist = point_list_ptr(bn, num_tiles);
         const size_t hist_words = rs_hist_words(R), hist_scr = scan_scratch_words(hist_words);
         Carver sizer(nullptr);
@@ -1153,7 +1172,7 @@ static int raster_backward_impl(const wast3d_raster_params* prm, int num_rendere
             uint32_t *kout = ka, *vout = va;
             for (int p = 0; p < passes && st == WAST3D_OK; ++p) {
                 const int nb = (p == passes - 1) ? bits - 8 * p : 8;
-                st = radix_pass_u32(kin, vin, kout, vout, R, 8 * p, nb, hist, hist + hist_words, s, debug);
+                st = radix_pass_u32(kin, vin, kout, vout, R, 8 * p, nb, hist, hist + hist_words, s, debug, n_dev);
                 kin = kout; vin = vout;
                 kout = (kout == ka) ? kb : ka;
                 vout = (vout == va) ? vb : va;
@@ -1350,6 +1369,7 @@ extern "C" int wast3d_raster_backward_raw_adam_next(const wast3d_raster_params* 
         d.b2 = sc.b2;
         d.one_minus_b2 = sc.one_minus_b2;
         d.eps = h.eps;
+        d.sched = h.schedule_dev;
     }
     float* go[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (grads_out)

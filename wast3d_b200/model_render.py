@@ -42,6 +42,15 @@ def _prm(keep, rs: GaussianRasterizationSettings, xyz, f_dc, f_rest, opacity, sc
 # overflow (the view needed more instances than the capacity: the image of that call was incomplete) raises
 # RuntimeError at the next call / at async_forward_check(), after the capacity has been raised.
 _ASYNC = {"on": bool(int(__import__("os").environ.get("WAST3D_ASYNC_FORWARD", "0")))}
+# CUDA-graph capture (graphed.GraphedStep): a fixed instance capacity and a pinned word block that receives the status of
+# every replay; no events, no host reads while the stream is capturing
+_CAPTURE: dict = {"capacity": None, "status_host": None}
+_LAST: dict = {"num_rendered": 0}
+
+
+def last_num_rendered() -> int:
+    """Instance count of the last synchronous rasterize_model() forward (the capacity in graph-safe calls)."""
+    return int(_LAST["num_rendered"])
 _ASYNC_STATE: dict = {}   # (device index, W, H) -> {"seen": max R, "pending": [(event, pinned, capacity)]}
 
 
@@ -132,11 +141,23 @@ class _RasterizeModel(torch.autograd.Function):
         prm.preprojected = int(pre)
         rendered = C.c_int(0)
         ast = None
-        if _ASYNC["on"] and P:
+        capturing = _CAPTURE["capacity"] is not None and P > 0
+        if capturing:
+            with torch.cuda.device(dev):
+                status = torch.empty(4, dtype=torch.int32, device=dev)
+                st = lib.wast3d_raster_forward_async(
+                    C.byref(prm), geom.cb, None, binning.cb, None, img.cb, None, color.data_ptr(), depth.data_ptr(),
+                    radii.data_ptr(), int(_CAPTURE["capacity"]), status.data_ptr(), _lib.stream_ptr())
+                rendered.value = int(_CAPTURE["capacity"])
+                if st == 0:
+                    _CAPTURE["status_host"].copy_(status, non_blocking=True)
+        elif _ASYNC["on"] and P:
             ast = _ASYNC_STATE.setdefault((dev.index, W, H), {"seen": 0, "pending": []})
             _async_poll(ast)   # raises if an earlier call of this size overflowed
         with torch.cuda.device(dev):
-            if ast is not None and ast["seen"] > 0:
+            if capturing:
+                pass
+            elif ast is not None and ast["seen"] > 0:
                 # capacity: 25% + 64k above the largest count seen, bucketed so that it (and the buffer size) is stable
                 cap = min(_lib.bucket_bytes(ast["seen"] + ast["seen"] // 4 + 65536), 0x7FFFFFFF)
                 status = torch.empty(4, dtype=torch.int32, device=dev)
@@ -163,6 +184,7 @@ class _RasterizeModel(torch.autograd.Function):
         _lib.check(st, "rasterize_model")
         ctx.raster_settings = rs
         ctx.num_rendered = rendered.value
+        _LAST["num_rendered"] = int(rendered.value)
         ctx.save_for_backward(xyz, f_dc, f_rest, opacity, scaling, rotation, radii, geom_t, binning_t, img_t,
                               sampling_offsets if sampling_offsets is not None else torch.empty(0))
         ctx.mark_non_differentiable(radii)

@@ -99,6 +99,8 @@ class BackwardFusedAdam(FusedAdam):
         self._applied = False
         self.capture_grads = False  # test hook: keep the leaf gradients of the last backward in .last_grads
         self.last_grads = None
+        self._schedule = None       # device_schedule(): [6, 2] step-dependent scalars read by the kernel at run time
+        self._hyper = self._step_dev = self._hyper_host = None
         self._next_view = None      # request: project for this camera inside the next backward (prefetch_view)
         self.projection = None      # result: pre-filled geometry buffer + radii of the view projected last
 
@@ -114,6 +116,43 @@ class BackwardFusedAdam(FusedAdam):
         `sh_degree`: the model's active SH degree at the next render (default: unchanged)."""
         self._next_view = dict(cam=viewpoint_camera, scale=float(scaling_modifier), D=sh_degree,
                                bounds=tuple(float(b) for b in offset_bounds))
+
+    @torch.no_grad()
+    def device_schedule(self, on: bool = True):
+        """Keep the step count and the bias-corrected step sizes on the DEVICE (wast3d_adam_schedule_step): the launch
+        sequence of a step then carries no step-dependent host value and can be replayed as a CUDA graph
+        (wast3d_b200.graphed.GraphedStep).  Learning rates are read from param_groups at every sync_hyper() call
+        (GraphedStep does it before each replay); betas from the groups at this call."""
+        if not on:
+            self._schedule = self._hyper = self._step_dev = self._hyper_host = None
+            return
+        p0 = self.param_groups[0]["params"][0]
+        steps = {int(self.state[g["params"][0]].get("step", 0)) if self.state[g["params"][0]] else 0 for g in self.param_groups}
+        if len(steps) != 1:
+            raise RuntimeError("BackwardFusedAdam.device_schedule: the six groups must be at the same step")
+        self._schedule = torch.zeros(6, 2, dtype=torch.float32, device=p0.device)
+        self._step_dev = torch.full((1,), steps.pop(), dtype=torch.int64, device=p0.device)
+        self._hyper_host = torch.zeros(6, 3, dtype=torch.float64, pin_memory=True)
+        self._hyper = torch.zeros(6, 3, dtype=torch.float64, device=p0.device)
+        self.sync_hyper(force=True)
+
+    @torch.no_grad()
+    def sync_hyper(self, force: bool = False):
+        """Copy the groups' current lr / betas to the device table when they changed (device_schedule mode)."""
+        if self._schedule is None:
+            return
+        rows = [[float(g["lr"]), float(g["betas"][0]), float(g["betas"][1])] for g in self.param_groups]
+        new = torch.tensor(rows, dtype=torch.float64)
+        if force or not torch.equal(new, self._hyper_host):
+            self._hyper_host.copy_(new)
+            self._hyper.copy_(self._hyper_host, non_blocking=True)
+
+    def advance_host_steps(self, n: int = 1):
+        """Book-keeping after a graph replay: the device counter advanced, state['step'] follows."""
+        for g in self.param_groups:
+            st = self.state[g["params"][0]]
+            if st:
+                st["step"] += n
 
     @torch.no_grad()
     def adam_groups(self, leaves):
@@ -136,7 +175,13 @@ class BackwardFusedAdam(FusedAdam):
             b1, b2 = group["betas"]
             ptr = lambda t: t.data_ptr() if t.numel() else None
             arr[k] = _lib.AdamGroup(ptr(p), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), float(group["lr"]), float(b1),
-                                    float(b2), float(group["eps"]), int(st["step"]), 0)
+                                    float(b2), float(group["eps"]), int(st["step"]), 0,
+                                    self._schedule[k].data_ptr() if self._schedule is not None else None)
+        if self._schedule is not None:
+            # the kernel reads lr / (1 - beta1^t) and 1 / sqrt(1 - beta2^t) from the device: advance them on this stream
+            _lib.check(_lib.load().wast3d_adam_schedule_step(6, self._hyper.data_ptr(), self._step_dev.data_ptr(),
+                                                            self._schedule.data_ptr(), _lib.stream_ptr()),
+                       "adam_schedule_step")
         return arr
 
     @torch.no_grad()

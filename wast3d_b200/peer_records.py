@@ -28,7 +28,8 @@ from .peer import PeerBuffer, PeerShardedAdam
 
 class _AdamGroup(C.Structure):  # struct wast3d_adam_group (include/wast3d_b200.h)
     _fields_ = [("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("lr", C.c_float),
-                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int), ("reserved", C.c_int)]
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int), ("reserved", C.c_int),
+                ("schedule_dev", C.c_void_p)]
 
 
 def _staged(lib):
@@ -146,7 +147,7 @@ class PeerRecordAdam(torch.optim.Optimizer):
                 b1, b2 = h["betas"]
                 return _AdamGroup(p.data_ptr() if p.numel() else None, m.data_ptr() if p.numel() else None,
                                   v.data_ptr() if p.numel() else None, float(h["lr"]), float(b1), float(b2),
-                                  float(h["eps"]), self._feat_steps, 0)
+                                  float(h["eps"]), self._feat_steps, 0, None)
             gd = grp(self.f_dc, self.m_dc, self.v_dc, hd)
             gr = grp(self.f_rest, self.m_rest, self.v_rest, hr)
             M = 1 + (int(self.f_rest.size(1)) if self.f_rest.numel() else 0)
