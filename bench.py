@@ -75,6 +75,11 @@ def parse():
                     help="1 = graph-safe forward (wast3d_raster_forward_async): the instance count is never read back by the "
                          "host, the binning buffer is sized from the largest count seen; 0 = the reference's protocol "
                          "(one blocking read of num_rendered per forward, rasterizer_impl.cu:283)")
+    ap.add_argument("--cuda-graph", type=int, default=1, choices=[0, 1],
+                    help="single GPU, --sync backward: 1 = the timed steps replay ONE captured CUDA graph of the whole step "
+                         "(wast3d_b200.graphed.GraphedStep: graph-safe forward, Adam step count on the device); the dominant "
+                         "kernel's duration is then taken from an eager region of the same steps right after (a replayed "
+                         "graph cannot be bracketed per kernel); 0 = eager launches")
     ap.add_argument("--prefetch-projection", type=int, default=0, choices=[0, 1],
                     help="single GPU, --sync backward: 1 = the backward kernel also projects every Gaussian for the NEXT step's "
                          "camera from the parameters it has just updated (BackwardFusedAdam.prefetch_view); the next forward "
@@ -394,12 +399,14 @@ def workload_config(spec, n):
 
 ASYNC_FWD = [True]
 PREFETCH = [True]
+GRAPH_INFO = [False]   # False, True, or {"error": ...} when the capture failed and the run stayed eager
 
 
 def implementation_info(sync):
     return {"grad_sync": sync, "peer_backend": PEER_BACKEND[0] if sync in ("peer", "records") else None,
             "loss": LOSS_KIND[0], "graph_safe_forward": ASYNC_FWD[0],
-            "projection_prefetch": bool(PREFETCH[0]) and sync == "backward"}
+            "projection_prefetch": bool(PREFETCH[0]) and sync == "backward",
+            "cuda_graph_replay": GRAPH_INFO[0]}
 
 
 def c1_case(dev, n_content=50_000, n_style=10_000):
@@ -563,7 +570,42 @@ def main():
             prepared[i] = c2
         return prepared[i]
 
+    graph = [None]        # GraphedStep once captured
+    use_graph = [False]   # the steps of the current region replay it
+
+    def graph_step(i, host_io):
+        """The same step as below through GraphedStep: camera and targets go into its static buffers, one launch."""
+        gs = graph[0]
+        cam = camera_for(i, host_io)
+        k = i % 2
+        if host_io:
+            main = torch.cuda.current_stream(dev)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(stage_free[k])
+                stage_tgt[k].copy_(tgt_host[k], non_blocking=True)
+                stage_dtgt[k].copy_(dtgt_host[k], non_blocking=True)
+                stage_full[k].record(copy_stream)
+            gs.set_view(cam)
+            main.wait_event(stage_full[k])
+            gs.set_targets(stage_tgt[k], stage_dtgt[k])
+            stage_free[k].record(main)
+        else:
+            gs.set_view(cam)
+            gs.set_targets(tgt_dev[k], dtgt_dev[k])
+        loss = gs.step()
+        if host_io:
+            if len(pending) == 2:
+                read_loss(pending.pop(0))
+            loss_host[k].copy_(loss, non_blocking=True)
+            loss_ready[k].record(main)
+            pending.append(k)
+            if len(pending) == 2:
+                read_loss(pending.pop(0))
+        return None
+
     def step(i, host_io):
+        if use_graph[0]:
+            return graph_step(i, host_io)
         cam = camera_for(i, host_io)
         k = i % 2
         if host_io:  # this step's inputs come from pinned host memory
@@ -657,6 +699,18 @@ def main():
     n_warm = max(args.warmup, 3)
     for i in range(n_warm):
         step(i, False)
+    if args.cuda_graph and world == 1 and args.sync == "backward" and not args.prefetch_projection:
+        try:
+            from wast3d_b200.graphed import GraphedStep
+            graph[0] = GraphedStep(pc, pipe, bg, cams[0], lambda o, t, d: style_loss(o, t, d, fused=args.loss == "fused"),
+                                   target=tgt_dev[0], depth_target=dtgt_dev[0], warmup_cameras=cams)
+            n_warm += len(cams)
+            use_graph[0] = True
+            GRAPH_INFO[0] = True
+        except Exception as e:   # both are product paths: stay eager and say so in the line
+            graph[0] = None
+            GRAPH_INFO[0] = {"error": repr(e)}
+            print("bench.py: CUDA-graph capture failed, timing the eager step:", repr(e), file=sys.stderr, flush=True)
 
     def settle(host_io, first):
         """Untimed rounds (one step per camera) until two consecutive rounds agree within 3% AND the
@@ -725,6 +779,9 @@ def main():
     _lib.profile_enable([])
     ms_step = ms_total / args.steps
     value = world * args.steps / (ms_total * 1e-3)
+    if use_graph[0]:
+        gs_r = graph[0].check()   # raises if a replay overflowed the captured instance capacity
+        launches = int(graph[0].launches_per_step) * args.steps   # kernels of ours inside the replayed graphs
 
     # ---- end to end through the public API with host buffers
     settle(True, it0)  # the host-buffer variant allocates differently: let the allocator settle again
@@ -742,6 +799,19 @@ def main():
     ms_e2e = min(e2e_attempts)
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
     h2d = tgt_host[0].numel() * 4 + dtgt_host[0].numel() * 4 + sum(t.numel() * 4 for t in cam_host[0])
+
+    eager_ms_step = None
+    if use_graph[0]:
+        # A replayed graph cannot be bracketed per kernel: the same K steps once more as eager launches, with the two
+        # candidate dominant kernels bracketed by CUDA events inside the library (roofline.kernel_ms)
+        graph[0].check()
+        use_graph[0] = False
+        settle(False, it0)
+        _lib.profile_enable(["render_backward", "gaussian_backward"])
+        _lib.profile_read()
+        eager_ms_step = timed(args.steps, False, it0) / args.steps
+        prof = _lib.profile_read()
+        _lib.profile_enable([])
 
     # ---- per-stage breakdown (separate short pass; events between stages perturb the step a little)
     _lib.profile_enable(None)
@@ -807,6 +877,10 @@ def main():
                              "reference's radius rectangles, scene.tile_instances_R_reference_rects)",
                     "achieved_in_reference_units": round((80.0 * R_ref + 32.0 * N) / (k_ms * 1e-3) / 1e9, 2)
                     if k_ms > 0 else 0.0}
+    roofline["kernel_ms_source"] = ("CUDA events inside the library over %d eager steps run right after the timed region "
+                                    "(the timed steps replay a CUDA graph, which cannot be bracketed per kernel)" % args.steps
+                                    if eager_ms_step is not None else
+                                    "CUDA events inside the library over the timed region")
     k7 = avg["render_backward"]
     roofline["other_kernels"] = {
         "render_backward_warp_kernel (K7)": {"kernel_ms": round(k7, 4), "bound": "issue (FP32/MUFU/shuffle), DRAM ~2% busy",
@@ -1029,7 +1103,15 @@ def main():
     # ---- the whole step as ONE CUDA graph (wast3d_b200.graphed.GraphedStep): graph-safe forward, Adam step count on
     # the device, camera / targets in static buffers; same model, same loss, same views as the timed region, which
     # stays eager because its dominant kernel is bracketed by CUDA events inside the library (roofline.kernel_ms)
-    if rank == 0 and world == 1 and args.sync == "backward" and not args.no_extra:
+    if graph[0] is not None:
+        extra["cuda_graph_step"] = {
+            "used_for_value_and_e2e": True, "ms_per_step": round(ms_step, 4), "eager_ms_per_step": round(eager_ms_step, 4),
+            "speedup_vs_eager": round(eager_ms_step / ms_step, 4), "kernels_per_graph": int(graph[0].launches_per_step),
+            "instance_capacity": int(graph[0].capacity),
+            "what": "sampling offsets + render (graph-safe forward) + fused pixel loss + backward with Adam in the "
+                    "per-Gaussian kernel (step count and bias corrections on the device), replayed with one launch; "
+                    "per step the host copies the camera (3 small tensors) and the targets into static buffers"}
+    elif rank == 0 and world == 1 and args.sync == "backward" and not args.no_extra and args.cuda_graph:
         try:
             from wast3d_b200.graphed import GraphedStep
             torch.cuda.empty_cache()
