@@ -176,11 +176,31 @@ __global__ void __launch_bounds__(256)
 sample_bounds_kernel(size_t n_pix, const float* __restrict__ offs, uint32_t* __restrict__ words) {
     const float inf = __int_as_float(0x7f800000);
     float mx = -inf, nx = -inf, my = -inf, ny = -inf;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_pix; i += (size_t)gridDim.x * blockDim.x) {
-        const float2 o = *reinterpret_cast<const float2*>(offs + 2 * i);
-        if (!(o.x == o.x) || !(o.y == o.y)) mx = nx = my = ny = inf;
-        mx = fmaxf(mx, o.x); nx = fmaxf(nx, -o.x);
-        my = fmaxf(my, o.y); ny = fmaxf(ny, -o.y);
+    // two pixels (16 bytes) per load, four independent loads in flight per thread: the kernel is a latency chain otherwise
+    const size_t n2 = n_pix / 2, stride = (size_t)gridDim.x * blockDim.x;
+    const bool vec = (reinterpret_cast<uintptr_t>(offs) & 15) == 0;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto take = [&](float4 o) {
+        if (!(o.x == o.x) || !(o.y == o.y) || !(o.z == o.z) || !(o.w == o.w)) mx = nx = my = ny = inf;
+        mx = fmaxf(mx, fmaxf(o.x, o.z)); nx = fmaxf(nx, fmaxf(-o.x, -o.z));
+        my = fmaxf(my, fmaxf(o.y, o.w)); ny = fmaxf(ny, fmaxf(-o.y, -o.w));
+    };
+    if (vec) {
+        const float4* o4 = reinterpret_cast<const float4*>(offs);
+        for (; i + 3 * stride < n2; i += 4 * stride) {
+            const float4 a = o4[i], b = o4[i + stride], c = o4[i + 2 * stride], d = o4[i + 3 * stride];
+            take(a); take(b); take(c); take(d);
+        }
+        for (; i < n2; i += stride) take(o4[i]);
+        if (blockIdx.x == 0 && threadIdx.x == 0 && (n_pix & 1)) {
+            const float2 o = *reinterpret_cast<const float2*>(offs + 2 * (n_pix - 1));
+            take(make_float4(o.x, o.y, o.x, o.y));
+        }
+    } else {
+        for (; i < n_pix; i += stride) {
+            const float2 o = *reinterpret_cast<const float2*>(offs + 2 * i);
+            take(make_float4(o.x, o.y, o.x, o.y));
+        }
     }
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) {
@@ -477,8 +497,12 @@ __global__ void check_projection_bounds_kernel(const uint32_t* __restrict__ actu
     if (!(a.max_x <= b.max_x) || !(a.min_x >= b.min_x) || !(a.max_y <= b.max_y) || !(a.min_y >= b.min_y)) atomicOr(flags, 2u);
 }
 // status_dev[0..3] = {num_rendered, prefiltered violated, look-back time-out, capacity overflow}
-__global__ void copy_status_kernel(const uint32_t* __restrict__ totals, uint32_t* __restrict__ status) {
-    if (threadIdx.x < 4) status[threadIdx.x] = totals[threadIdx.x];
+__global__ void copy_status_kernel(const uint32_t* __restrict__ totals, uint32_t* __restrict__ status,
+                                   const uint32_t* e0, const uint32_t* e1, const uint32_t* e2) {
+    if (threadIdx.x >= 4) return;
+    uint32_t v = totals[threadIdx.x];
+    if (threadIdx.x == 2) v |= (e0 ? *e0 : 0u) | (e1 ? *e1 : 0u) | (e2 ? *e2 : 0u);   // look-back time-outs of every stage
+    status[threadIdx.x] = v;
 }
 
 // ------------------------------------------------------------------ K6 -------------------
@@ -896,7 +920,7 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         ProfScope ps(PS_PREPROCESS, s);
         if (cut_tiles) {
             if (prm->sampling_offsets != nullptr) {
-                sample_bounds_kernel<<<148 * 2, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
+                sample_bounds_kernel<<<148 * 4, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
                 W3D_AFTER_LAUNCH(s, debug);
             }
             check_projection_bounds_kernel<<<1, 32, 0, s>>>(sample_bound_words, g.totals + 16, g.totals + 1);
@@ -905,7 +929,7 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
     } else {
     ProfScope ps(PS_PREPROCESS, s);
     if (cut_tiles && prm->sampling_offsets != nullptr) {
-        sample_bounds_kernel<<<148 * 2, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
+        sample_bounds_kernel<<<148 * 4, 256, 0, s>>>(N, prm->sampling_offsets, sample_bound_words);
         W3D_AFTER_LAUNCH(s, debug);
     }
     // WAST3D_K1_VEC: 1 (default) = means3D / scales through coalesced 16-byte loads, 0 = strided scalar loads (A/B)
@@ -966,8 +990,12 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
         st = standalone_scan();
         if (st) return st;
     }
-    // look-back time-outs (never expected) of the depth sort and the scan, read with num_rendered
-    if (sort_mode(STAGE_DEPTH) == 1 || (!fused_scan && sort_mode(STAGE_SCAN) == 1)) {
+    // look-back time-outs (never expected) of the depth sort and the scan, read with num_rendered; the graph-safe
+    // forward collects every stage's error word in its last kernel instead (copy_status_kernel)
+    const uint32_t* err_words[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (sort_mode(STAGE_DEPTH) == 1) err_words[0] = onesweep_error_word(g.sort_ws, P, 4);
+    if (!fused_scan && sort_mode(STAGE_SCAN) == 1) err_words[1] = g.scan_ws + 1;
+    if (!async && (sort_mode(STAGE_DEPTH) == 1 || (!fused_scan && sort_mode(STAGE_SCAN) == 1))) {
         tile_copy_flags_kernel<<<1, 32, 0, s>>>(sort_mode(STAGE_DEPTH) == 1 ? onesweep_error_word(g.sort_ws, P, 4) : nullptr,
                                                !fused_scan && sort_mode(STAGE_SCAN) == 1 ? g.scan_ws + 1 : nullptr,
                                                g.totals + 2);
@@ -1029,7 +1057,8 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
                                                                          smem_hist, R, g.totals, g.scan_ws);
             W3D_AFTER_LAUNCH(s, debug);
             // a look-back time-out (never expected) joins the flags; the synchronous protocol has read them already
-            tile_or_flag_kernel<<<1, 32, 0, s>>>(g.scan_ws + 1, g.totals + 2);
+            err_words[1] = g.scan_ws + 1;
+            if (!async) tile_or_flag_kernel<<<1, 32, 0, s>>>(g.scan_ws + 1, g.totals + 2);
         } else {
             emit_instances_kernel<false><<<blocks, EMIT_THREADS, smem, s>>>(P, g.order_a, g.offsets, g.rect_sorted, bn.keys_a,
                                                                           bn.vals_a, im.tile_count, grid, (int)num_tiles,
@@ -1067,8 +1096,11 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
             t = vin; vin = vout; vout = t;
         }
         if (tile_lookback) {   // a look-back time-out (never expected) joins the flags of the depth sort and the scan
-            tile_or_flag_kernel<<<1, 32, 0, s>>>(onesweep_error_word(bn.sort_ws, R, passes), g.totals + 2);
-            W3D_AFTER_LAUNCH(s, debug);
+            err_words[2] = onesweep_error_word(bn.sort_ws, R, passes);
+            if (!async) {
+                tile_or_flag_kernel<<<1, 32, 0, s>>>(err_words[2], g.totals + 2);
+                W3D_AFTER_LAUNCH(s, debug);
+            }
         }
         delete pts;
         ProfScope ps(PS_RANGES, s);
@@ -1106,7 +1138,7 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
     W3D_AFTER_LAUNCH(s, debug);
     }
     if (async && status_dev) {
-        copy_status_kernel<<<1, 32, 0, s>>>(g.totals, status_dev);
+        copy_status_kernel<<<1, 32, 0, s>>>(g.totals, status_dev, err_words[0], err_words[1], err_words[2]);
         W3D_AFTER_LAUNCH(s, debug);
     }
     return WAST3D_OK;
