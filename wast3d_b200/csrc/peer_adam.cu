@@ -138,7 +138,11 @@ peer_adam_kernel(const __grid_constant__ PeerArgs a) {
     // NVLink latency (~2 us) x bandwidth (~0.9 TB/s per direction) needs ~2 MB of peer loads in flight per
     // GPU: every thread issues all loads of U float4 columns (U * (WORLD + 3) 16-byte loads) before it
     // touches any of them.
-    constexpr int U = MC ? 4 : (WORLD <= 2 ? 4 : (WORLD <= 5 ? 2 : 1));
+    // Multicast: the switch-side reduction has the longest latency and the late launch runs on a dozen CTAs only (the
+    // next view's projection and sorting own the other SMs), so 8 reduced columns are in flight per thread; the local
+    // parameter / moment loads follow in groups of UL columns to stay inside the register budget.
+    constexpr int U = MC ? 8 : (WORLD <= 2 ? 4 : (WORLD <= 5 ? 2 : 1));
+    constexpr int UL = U < 4 ? U : 4;
     constexpr int NG = MC ? 1 : WORLD;  // gradient loads per column
     const unsigned long long tile = (unsigned long long)PEER_THREADS * U;
     for (int sidx = 0; sidx < a.nsegs; ++sidx) {
@@ -147,44 +151,54 @@ peer_adam_kernel(const __grid_constant__ PeerArgs a) {
         const unsigned long long hi = seg.end4 < a.shard_end4 ? seg.end4 : a.shard_end4;
         for (unsigned long long base = lo + (unsigned long long)blockIdx.x * tile; base < hi;
              base += (unsigned long long)gridDim.x * tile) {
-            float4 g[U][NG], p[U], m[U], v[U];
+            float4 g[U][NG];
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const unsigned long long i = base + (unsigned long long)u * PEER_THREADS + threadIdx.x;
                 const bool in = i < hi;
-                const unsigned long long j = i - a.shard_begin4;
                 if (MC) {
                     g[u][0] = in ? mc_ld_reduce_add(a.mc_grads + i) : z;
                 } else {
 #pragma unroll
                     for (int q = 0; q < NG; ++q) g[u][q] = in ? ld_stream(a.grads[q] + i) : z;
                 }
-                p[u] = in ? ld_stream(a.params[rank] + i) : z;
-                m[u] = in ? ld_stream(a.m + j) : z;
-                v[u] = in ? ld_stream(a.v + j) : z;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const unsigned long long i = base + (unsigned long long)u * PEER_THREADS + threadIdx.x;
-                if (i >= hi) continue;
-                const unsigned long long j = i - a.shard_begin4;
-                float4 gs = g[u][0];
+            for (int u0 = 0; u0 < U; u0 += UL) {
+                float4 p[UL], m[UL], v[UL];
 #pragma unroll
-                for (int q = 1; q < NG; ++q) {
-                    gs.x += g[u][q].x; gs.y += g[u][q].y; gs.z += g[u][q].z; gs.w += g[u][q].w;
+                for (int k = 0; k < UL; ++k) {
+                    const unsigned long long i = base + (unsigned long long)(u0 + k) * PEER_THREADS + threadIdx.x;
+                    const bool in = i < hi;
+                    const unsigned long long j = i - a.shard_begin4;
+                    p[k] = in ? ld_stream(a.params[rank] + i) : z;
+                    m[k] = in ? ld_stream(a.m + j) : z;
+                    v[k] = in ? ld_stream(a.v + j) : z;
                 }
-                if (WORLD > 1) {
-                    gs.x *= a.grad_scale; gs.y *= a.grad_scale; gs.z *= a.grad_scale; gs.w *= a.grad_scale;
-                }
-                adam4(p[u], gs, m[u], v[u], seg);
-                st_stream(a.m + j, m[u]);
-                st_stream(a.v + j, v[u]);
-                if (MC) {
-                    mc_st(a.mc_params + i, p[u]);
-                } else {
 #pragma unroll
-                    for (int q = 0; q < WORLD; ++q) st_stream(a.params[q] + i, p[u]);
+                for (int k = 0; k < UL; ++k) {
+                    const int u = u0 + k;
+                    const unsigned long long i = base + (unsigned long long)u * PEER_THREADS + threadIdx.x;
+                    if (i >= hi) continue;
+                    const unsigned long long j = i - a.shard_begin4;
+                    float4 gs = g[u][0];
+#pragma unroll
+                    for (int q = 1; q < NG; ++q) {
+                        gs.x += g[u][q].x; gs.y += g[u][q].y; gs.z += g[u][q].z; gs.w += g[u][q].w;
+                    }
+                    if (WORLD > 1) {
+                        gs.x *= a.grad_scale; gs.y *= a.grad_scale; gs.z *= a.grad_scale; gs.w *= a.grad_scale;
+                    }
+                    adam4(p[k], gs, m[k], v[k], seg);
+                    st_stream(a.m + j, m[k]);
+                    st_stream(a.v + j, v[k]);
+                    if (MC) {
+                        mc_st(a.mc_params + i, p[k]);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < WORLD; ++q) st_stream(a.params[q] + i, p[k]);
+                    }
                 }
             }
         }
