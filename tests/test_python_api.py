@@ -70,3 +70,22 @@ def test_camera_conventions():
     assert abs(v[0].item()) < 1e-5 and abs(v[1].item()) < 1e-5
     assert torch.allclose(cam.camera_center, torch.tensor([3.0, 1.0, 2.0]), atol=1e-5)
     assert torch.allclose(cam.full_proj_transform, wv @ cam.projection_matrix)
+
+
+def test_update_learning_rate_follows_the_reference_schedule():
+    """scene/gaussian_model.py:169-176 + utils/general_utils.py:29-62 (lr_delay_steps = 0): log-linear from
+    position_lr_init to position_lr_final (both times spatial_lr_scale) over position_lr_max_steps, xyz group only."""
+    import numpy as np
+    from wast3d_b200.scene import GaussianModel, OptimizationParams, synthetic_gaussians
+    m = GaussianModel.from_arrays(synthetic_gaussians(64, seed=0), device="cpu")
+    m.spatial_lr_scale = 5.0
+    m.training_setup(OptimizationParams())
+    others = [g["lr"] for g in m.optimizer.param_groups[1:]]
+    for it in (0, 1, 777, 29_999, 30_000, 45_000):
+        t = np.clip(it / 30_000, 0, 1)
+        want = float(np.exp(np.log(0.00016 * 5.0) * (1 - t) + np.log(0.0000016 * 5.0) * t))
+        got = m.update_learning_rate(it)
+        assert abs(got - want) <= 1e-12 * want
+        assert m.optimizer.param_groups[0]["lr"] == got
+    assert [g["lr"] for g in m.optimizer.param_groups[1:]] == others
+    assert m.update_learning_rate(-1) == 0.0

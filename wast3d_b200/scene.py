@@ -187,6 +187,9 @@ class PipelineParams:
 class OptimizationParams:
     """Learning rates of arguments/__init__.py OptimizationParams used by training_setup."""
     position_lr_init: float = 0.00016
+    position_lr_final: float = 0.0000016
+    position_lr_delay_mult: float = 0.01
+    position_lr_max_steps: int = 30_000
     feature_lr: float = 0.0025
     opacity_lr: float = 0.05
     scaling_lr: float = 0.005
@@ -340,4 +343,21 @@ class GaussianModel:
             self.optimizer = FusedAdam(groups, lr=0.0, eps=1e-15)
         else:
             self.optimizer = torch.optim.Adam(groups, lr=0.0, eps=1e-15)
+        self._xyz_lr = (a.position_lr_init * self.spatial_lr_scale, a.position_lr_final * self.spatial_lr_scale,
+                        a.position_lr_delay_mult, a.position_lr_max_steps)
         return self.optimizer
+
+    def update_learning_rate(self, iteration):
+        """Per-step learning rate of the positions (scene/gaussian_model.py:169-176 with the schedule of
+        utils/general_utils.py:29-62): log-linear interpolation from position_lr_init to position_lr_final over
+        position_lr_max_steps (no delay phase, as the reference configures it: lr_delay_steps = 0).  Returns the rate."""
+        lr0, lr1, _delay_mult, max_steps = self._xyz_lr
+        if iteration < 0 or (lr0 == 0.0 and lr1 == 0.0):
+            lr = 0.0
+        else:
+            t = min(max(iteration / max_steps, 0.0), 1.0)
+            lr = float(math.exp(math.log(lr0) * (1.0 - t) + math.log(lr1) * t))
+        for group in self.optimizer.param_groups:
+            if group["name"] == "xyz":
+                group["lr"] = lr
+                return lr
