@@ -209,11 +209,15 @@ sample_bounds_kernel(size_t n_pix, const float* __restrict__ offs, uint32_t* __r
         my = fmaxf(my, __shfl_xor_sync(0xffffffffu, my, d));
         ny = fmaxf(ny, __shfl_xor_sync(0xffffffffu, ny, d));
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicMax(words + 0, float_order_key(mx));
-        atomicMax(words + 1, float_order_key(nx));
-        atomicMax(words + 2, float_order_key(my));
-        atomicMax(words + 3, float_order_key(ny));
+    // one set of atomics per block: 4700 warps hammering four words cost more than reading the offsets
+    __shared__ float s_red[4][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_red[0][warp] = mx; s_red[1][warp] = nx; s_red[2][warp] = my; s_red[3][warp] = ny; }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        float v = s_red[threadIdx.x][0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) v = fmaxf(v, s_red[threadIdx.x][w]);
+        atomicMax(words + threadIdx.x, float_order_key(v));
     }
 }
 
