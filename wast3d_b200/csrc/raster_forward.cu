@@ -743,7 +743,6 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
             }
         }
         unsigned m = __ballot_sync(0xffffffffu, hit);
-        bool warp_done = false;
         while (m) {
             const int j = __ffs(m) - 1;
             m &= m - 1;
@@ -775,12 +774,10 @@ render_forward_warp_kernel(const uint2* __restrict__ ranges, const uint32_t* __r
                     }
                 }
             }
-            if (__all_sync(0xffffffffu, done)) {
-                warp_done = true;
-                break;
-            }
         }
-        if (warp_done) break;
+        // all 32 pixels saturated: checked once per round (a vote per hit cost 3.6 % of the kernel's instructions; the at
+        // most 31 hits a finished warp still walks through skip their body)
+        if (__all_sync(0xffffffffu, done)) break;
         __syncwarp();   // everybody is done reading stage st before round b + 3 overwrites it
     }
     cp_async_wait<0>();
