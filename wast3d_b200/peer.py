@@ -308,8 +308,10 @@ class PeerShardedAdam(torch.optim.Optimizer):
         # beside it does: every request it keeps in flight queues in front of theirs (profiles/r01_overlap.md)
         # defaults = the measured configurations: multicast 12 (N = 4 and N = 8), plain peer loads / stores 37 at N = 2
         # and 20 at N = 4
-        # round 2, N = 8 (8 x B200, multicast): 12 CTAs 3.50 ms per step, 20 CTAs 3.66 ms (profiles/r02_scaling_n8.md)
-        default_ctas = 12 if self.multicast else (37 if W <= 2 else 20)
+        # end of round 2 (8 reduced columns in flight per thread; the binning chain beside the exchange is latency-bound
+        # and suffers from every extra CTA): N = 8, multicast: 4 / 6 / 8 / 12 / 20 CTAs = 3.50 / 3.24 / 3.22 / 3.45 /
+        # 3.57 ms per step; N = 4 (twice the shard per rank): 8 / 12 CTAs = 3.55 / 3.30 ms (profiles/r02_scaling.md)
+        default_ctas = (12 if W <= 4 else 8) if self.multicast else (37 if W <= 2 else 20)
         self.late_ctas = int(os.environ.get("WAST3D_PEER_LATE_CTAS", str(default_ctas)))
         if W > 1:  # replicas start identical: rank 0's values win (the reference has one copy)
             dist.broadcast(self._param_flat, src=dist.get_global_rank(group, 0) if group is not None else 0,
