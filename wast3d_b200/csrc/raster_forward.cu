@@ -474,16 +474,24 @@ tile_ranges_from_counts_kernel(int num_tiles, const uint32_t* __restrict__ tile_
     }
 }
 
-// Global digit histograms of the tile-id radix passes from the per-tile instance counts.
-__global__ void __launch_bounds__(256)
-tile_digit_hist_kernel(int num_tiles, const uint32_t* __restrict__ tile_count, int passes, int bpp,
-                       uint32_t* __restrict__ digit_hist /*[passes][RS_RADIX]*/) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= num_tiles) return;
-    const uint32_t c = tile_count[t];
-    if (c == 0) return;
+// Digit BASES (exclusive prefix of the global digit histogram) of the tile-id radix passes from the per-tile instance
+// counts: one block per pass, no read of the keys.
+__global__ void __launch_bounds__(RS_RADIX)
+tile_digit_bases_kernel(int num_tiles, const uint32_t* __restrict__ tile_count, int bpp,
+                        uint32_t* __restrict__ digit_base /*[passes][RS_RADIX]*/) {
+    __shared__ uint32_t h[RS_RADIX];
+    const int p = blockIdx.x;
     const uint32_t mask = (1u << bpp) - 1u;
-    for (int p = 0; p < passes; ++p) atomicAdd(digit_hist + p * RS_RADIX + (((uint32_t)t >> (p * bpp)) & mask), c);
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (int t = threadIdx.x; t < num_tiles; t += RS_RADIX) {
+        const uint32_t c = tile_count[t];
+        if (c) atomicAdd(&h[((uint32_t)t >> (p * bpp)) & mask], c);
+    }
+    __syncthreads();
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan<RS_RADIX>(h[threadIdx.x], &tot);
+    digit_base[p * RS_RADIX + threadIdx.x] = ex;
 }
 
 __global__ void tile_copy_flags_kernel(const uint32_t* a, const uint32_t* b, uint32_t* out) {
@@ -1076,11 +1084,9 @@ static int raster_forward_impl(const wast3d_raster_params* prm, wast3d_alloc_fn 
             st = onesweep_prepare(bn.sort_ws, R, passes, s);
             if (st) { delete pts; return st; }
             // the per-pass global digit histograms follow from the per-tile counts: no read of the keys
-            tile_digit_hist_kernel<<<(num_tiles + 255) / 256, 256, 0, s>>>(
-                (int)num_tiles, im.tile_count, passes, bpp, onesweep_digit_hist(bn.sort_ws, R, passes, 0));
+            tile_digit_bases_kernel<<<passes, RS_RADIX, 0, s>>>((int)num_tiles, im.tile_count, bpp,
+                                                                 onesweep_digit_hist(bn.sort_ws, R, passes, 0));
             W3D_AFTER_LAUNCH(s, debug);
-            st = onesweep_scan_digits(bn.sort_ws, R, passes, s, debug);
-            if (st) { delete pts; return st; }
         }
         uint32_t *kin = bn.keys_a, *vin = bn.vals_a, *kout = bn.keys_b, *vout = bn.vals_b;
         for (int p = 0; p < passes; ++p) {
