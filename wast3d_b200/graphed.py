@@ -38,6 +38,9 @@ class GraphedStep:
         opt = getattr(model, "optimizer", None)
         if not isinstance(opt, BackwardFusedAdam):
             raise RuntimeError("GraphedStep needs the optimizer-in-backward (training_setup(..., in_backward=True))")
+        if getattr(pipe, "debug", False) or getattr(pipe, "convert_SHs_python", False) or getattr(pipe, "compute_cov3D_python", False):
+            raise RuntimeError("GraphedStep: pipe.debug (synchronises after every launch) and the Python SH / covariance "
+                               "paths cannot be captured")
         self.model, self.pipe, self.bg, self.loss_fn, self.opt = model, pipe, background, loss_fn, opt
         dev = model.get_xyz.device
         self.H, self.W = int(camera.image_height), int(camera.image_width)
