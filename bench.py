@@ -421,6 +421,7 @@ def workload_config(spec, n):
 ASYNC_FWD = [True]
 PREFETCH = [True]
 GRAPH_INFO = [False]   # False, True, or {"error": ...} when the capture failed and the run stayed eager
+REF_EARLY = [None]     # extra.reference_cuda_sm100 measured before our own steps (single GPU), or the exception
 
 
 def implementation_info(sync):
@@ -717,6 +718,12 @@ def main():
     # round's time is within 3% of the previous one (allocator growth, lazy CUDA module loading and
     # first-touch paging of the image make the first few dozen steps of a fresh process slow and
     # erratic; steady state is what is measured).  Never more than 20 extra rounds.
+    if rank == 0 and world == 1 and not args.no_ref_cuda and not args.no_extra and reference_cuda_available():
+        try:
+            REF_EARLY[0] = time_reference_cuda(spec, dev, steps=10, warmup=3, arrs=arrs)
+        except Exception as e:  # a baseline leg never fails the bench line
+            REF_EARLY[0] = e
+        torch.cuda.empty_cache()
     n_warm = max(args.warmup, 3)
     for i in range(n_warm):
         step(i, False)
@@ -1057,12 +1064,19 @@ def main():
             extra["c1_cpu_torch_vs_gpu"] = {"error": repr(e)}
 
     # ---- the kernel to beat: the reference's own CUDA code recompiled for sm_100, same scene,
-    # same cameras / targets, same stream, after our timed region (it is the baseline here, never on our path)
+    # same cameras / targets, same stream (it is the baseline here, never on our path); timed BEFORE our own warm-up
+    # (REF_EARLY): run after our timed region, with the captured graph's private memory pool and the extras' blocks
+    # in the caching allocator, its host-synchronous forward took anything between 5 and 52 ms from run to run
     ref_cuda = None
     if rank == 0 and world == 1 and not args.no_ref_cuda and reference_cuda_available():
         try:
-            torch.cuda.empty_cache()
-            ref_cuda = time_reference_cuda(spec, dev, steps=10, warmup=3, arrs=arrs)
+            if REF_EARLY[0] is None:
+                torch.cuda.empty_cache()
+                ref_cuda = time_reference_cuda(spec, dev, steps=10, warmup=3, arrs=arrs)
+            elif isinstance(REF_EARLY[0], Exception):
+                raise REF_EARLY[0]
+            else:
+                ref_cuda = REF_EARLY[0]
             ours_fwd = sum(stages.get(k, 0.0) for k in ("preprocess", "depth_sort", "scan", "emit_instances", "tile_sort",
                                                         "tile_ranges", "render_forward"))
             ours_bwd = sum(stages.get(k, 0.0) for k in ("backward_zero", "render_backward", "gaussian_backward"))
