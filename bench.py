@@ -64,7 +64,7 @@ def parse():
                          "(peer.PeerShardedAdam), 'nccl' = chunked NCCL all-reduce overlapped with the dense fused Adam "
                          "(with one GPU: just the dense fused Adam); 'backward' (one GPU only) = the Adam update applied by the "
                          "rasteriser's per-Gaussian backward kernel, leaf gradients never written (optim.BackwardFusedAdam); "
-                         "'records' = STAGED, not yet run on a GPU: peer launch for the 11 geometry floats, SH features rebuilt "
+                         "'records' = peer launch for the 11 geometry floats, SH features rebuilt "
                          "on every rank from 16-byte colour records (peer_records.PeerRecordAdam); "
                          "'auto' = peer with N > 1, backward with N = 1")
     ap.add_argument("--overlap", type=int, default=1, choices=[0, 1],

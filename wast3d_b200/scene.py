@@ -322,7 +322,8 @@ class GaussianModel:
         ]
         self.grad_sink = None
         if peer and feature_records:
-            # staged for round 2 (peer_records.py): features updated from per-view colour records, never exchanged
+            # optional (peer_records.py; measured equal to the feature exchange, profiles/r02_scaling.md): features updated
+            # from per-view colour records, never exchanged
             from .peer_records import PeerRecordAdam
             self.optimizer = PeerRecordAdam(groups, self._xyz, self._features_dc, self._features_rest,
                                             lambda: self.active_sh_degree, lr=0.0, eps=1e-15, group=group,
