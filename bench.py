@@ -304,34 +304,51 @@ def time_reference_cuda(spec, dev, steps, warmup, arrs=None, knn=True):
         torch.cuda.synchronize()
         if torch.cuda.memory_stats(dev).get("num_device_alloc", 0) == a0:
             break
-    torch.cuda.synchronize()
-    t_all0 = ev(); t_all0.record()
-    for i in range(done, done + steps):
-        cam = cams[i % len(cams)]
-        k = i % 2
-        e = [ev() for _ in range(4)]
-        e[0].record()
-        offs = pad_offsets(torch.rand(H, W, 2, device=dev) * -1, H, W)
-        out = rt.render(cam, bg, offs)
-        loss = style_loss(out, tgt[k], dtgt[k], fused=False)
-        e[1].record()
-        loss.backward()
-        e[2].record()
-        rt.optimizer.step()
-        rt.optimizer.zero_grad(set_to_none=True)
-        e[3].record()
-        R = rt.rr.R
-        recs.append(e)
-    t_all1 = ev(); t_all1.record()
-    torch.cuda.synchronize()
+    warm_done = done
+    # Same stall rule as our own arm (main(): "a fresh box occasionally stalls one step for hundreds of milliseconds"):
+    # the K steps are one bracket; when its slowest step is > 5x the median step the bracket is measured again (at most
+    # three) and the FASTEST bracket is reported, every bracket listed.  Fair to the reference: its host-synchronous
+    # forward is hit harder by such a stall than an asynchronous loop (seen: 87 ms / step in one run of four, 15.7 else).
+    attempts = []
+    best = None
+    for attempt in range(3):
+        recs = []
+        torch.cuda.synchronize()
+        t_all0 = ev(); t_all0.record()
+        for i in range(done, done + steps):
+            cam = cams[i % len(cams)]
+            k = i % 2
+            e = [ev() for _ in range(4)]
+            e[0].record()
+            offs = pad_offsets(torch.rand(H, W, 2, device=dev) * -1, H, W)
+            out = rt.render(cam, bg, offs)
+            loss = style_loss(out, tgt[k], dtgt[k], fused=False)
+            e[1].record()
+            loss.backward()
+            e[2].record()
+            rt.optimizer.step()
+            rt.optimizer.zero_grad(set_to_none=True)
+            e[3].record()
+            R = rt.rr.R
+            recs.append(e)
+        done += steps
+        t_all1 = ev(); t_all1.record()
+        torch.cuda.synchronize()
+        per_step = sorted(e[0].elapsed_time(e[3]) for e in recs)
+        ms_try = t_all0.elapsed_time(t_all1) / steps
+        attempts.append(round(ms_try, 4))
+        if best is None or ms_try < best[0]:
+            best = (ms_try, recs)
+        if per_step[-1] <= 5.0 * per_step[len(per_step) // 2]:
+            break
+    ms_step, recs = best
     for e in recs:
         tot["fwd"] += e[0].elapsed_time(e[1])
         tot["bwd"] += e[1].elapsed_time(e[2])
         tot["adam"] += e[2].elapsed_time(e[3])
-    ms_step = t_all0.elapsed_time(t_all1) / steps
     out = {"fwd_ms": round(tot["fwd"] / steps, 4), "bwd_ms": round(tot["bwd"] / steps, 4),
            "adam_ms": round(tot["adam"] / steps, 4), "step_ms": round(ms_step, 4), "R": int(R), "steps": steps,
-           "warmup_steps": int(done),
+           "warmup_steps": int(warm_done), "attempts_ms_per_step": attempts,
            "what": "unmodified reference CUDA (forward.cu / backward.cu / rasterizer_impl.cu, nvcc -O3 sm_100) + torch "
                    "activations + torch losses + torch.optim.Adam (foreach), CUDA events on the launching stream; fwd "
                    "includes the reference's blocking num_rendered read, bwd its ten zero-filled gradient tensors"}
@@ -374,6 +391,9 @@ def run_reference(args, spec):
                 "reference_device": "cuda:0 — the reference has no CPU implementation of the rasteriser; this arm runs its "
                                     "unmodified CUDA sources recompiled for sm_100 (oracle/_ref) with its torch glue",
                 "stages_ms": {k: r[k] for k in ("fwd_ms", "bwd_ms", "adam_ms")},
+                "attempts_ms_per_step": r.get("attempts_ms_per_step"),
+                "stall_rule": "as in our arm: a bracket whose slowest step is > 5x its median step is measured again "
+                              "(at most 3 brackets), the fastest bracket is reported, all are listed",
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample},
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
