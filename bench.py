@@ -154,7 +154,7 @@ class ClockSampler:
                ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
                ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
-    def __init__(self, index, period_s=0.02):
+    def __init__(self, index, period_s=0.01):
         import threading
         self.samples, self.t0, self.t1, self.ok = [], None, None, False
         self._stop = threading.Event()
@@ -192,7 +192,19 @@ class ClockSampler:
     def begin(self):
         self.t0 = time.perf_counter()
 
+    def _sample(self):
+        nv, h = self.nv, self.h
+        self.samples.append((time.perf_counter(), float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)),
+                             nv.nvmlDeviceGetPowerUsage(h) / 1e3, int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+
     def end(self):
+        # a region shorter than the sampling period (few steps of a small configuration) may have caught no sample:
+        # take one now, the instant the region's closing synchronize has returned
+        if self.ok and not any(self.t0 is not None and r[0] >= self.t0 for r in list(self.samples)):
+            try:
+                self._sample()
+            except Exception:  # noqa: BLE001
+                pass
         self.t1 = time.perf_counter()
 
     def stop(self):
