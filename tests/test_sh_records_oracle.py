@@ -47,9 +47,7 @@ def test_staged_kernel_statements_on_the_cpu(built):
     import ctypes as C
     from oracle import cpu, sh_records
 
-    class AdamGroup(C.Structure):
-        _fields_ = [("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("lr", C.c_float),
-                    ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int), ("reserved", C.c_int)]
+    from wast3d_b200._lib import AdamGroup   # struct wast3d_adam_group (ABI v7 layout)
 
     lib = C.CDLL(str(built["cuda"]))
     f = lib.wast3d_staged_sh_adam_host_emulation
@@ -89,8 +87,8 @@ def test_staged_kernel_statements_on_the_cpu(built):
     for t in (1, 2):
         np_adam(e_dc, grad[:, :1], em[0], em[1], lrs[0], t)
         np_adam(e_rest, grad[:, 1:], em[2], em[3], lrs[1], t)
-        gd = AdamGroup(p_dc.ctypes.data, sm[0].ctypes.data, sm[1].ctypes.data, lrs[0], 0.9, 0.999, 1e-15, t, 0)
-        gr = AdamGroup(p_rest.ctypes.data, sm[2].ctypes.data, sm[3].ctypes.data, lrs[1], 0.9, 0.999, 1e-15, t, 0)
+        gd = AdamGroup(p_dc.ctypes.data, sm[0].ctypes.data, sm[1].ctypes.data, lrs[0], 0.9, 0.999, 1e-15, t, 0, None)
+        gr = AdamGroup(p_rest.ctypes.data, sm[2].ctypes.data, sm[3].ctypes.data, lrs[1], 0.9, 0.999, 1e-15, t, 0, None)
         assert f(P, degree, M, len(recs), ptrs, campos.ctypes.data, xyz.ctypes.data, float(scale), C.byref(gd), C.byref(gr)) == 0
     assert np.abs(p_dc - shs[:, :1]).max() > 1e-3  # something moved
     # moments carry the gradient itself: first moment after two steps = (1-b1)(1 + b1) g

@@ -1,24 +1,18 @@
-"""GPU test of the kernels STAGED for round 2 (csrc/sh_adam.cu, include/wast3d_b200_staged.h): gated by
-WAST3D_STAGED=1 because they have not run on a GPU yet — enable it on the first GPU visit of the next round.
+"""GPU tests of the colour-record optimizer's kernels (csrc/sh_adam.cu, include/wast3d_b200_staged.h; first run on
+hardware in round 2, profiles/r02_scaling.md).
 
 Three views of one scene: [per-view backward -> dL/dsh summed over the views -> dense fused Adam on _features_dc /
 _features_rest] against [16-byte colour record per view -> wast3d_staged_sh_adam_from_records]."""
 import ctypes as C
-import os
 
 import numpy as np
 import pytest
 import torch
 
 from tests.util import call_backward, call_forward, raster_case, to_cuda
+from wast3d_b200._lib import AdamGroup   # struct wast3d_adam_group (ABI v7 layout)
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("WAST3D_STAGED") != "1", reason="staged for round 2 (set WAST3D_STAGED=1)")]
-
-
-class AdamGroup(C.Structure):
-    _fields_ = [("param", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("lr", C.c_float),
-                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("step", C.c_int), ("reserved", C.c_int)]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("degree,P", [(3, 6000), (1, 4999), (0, 777)])
