@@ -89,3 +89,16 @@ def test_update_learning_rate_follows_the_reference_schedule():
         assert m.optimizer.param_groups[0]["lr"] == got
     assert [g["lr"] for g in m.optimizer.param_groups[1:]] == others
     assert m.update_learning_rate(-1) == 0.0
+
+
+def test_graphed_step_needs_the_optimizer_in_backward():
+    """GraphedStep captures render -> loss -> backward (+ Adam): without optim.BackwardFusedAdam the step has
+    step-dependent host values and a separate optimizer launch sequence; it refuses instead of capturing a wrong graph."""
+    from types import SimpleNamespace
+    from wast3d_b200.graphed import GraphedStep
+    from wast3d_b200.scene import GaussianModel, OptimizationParams, PipelineParams, synthetic_gaussians
+    m = GaussianModel.from_arrays(synthetic_gaussians(32, seed=0), device="cpu")
+    m.training_setup(OptimizationParams())     # torch.optim.Adam
+    cam = SimpleNamespace(image_height=8, image_width=8, FoVx=0.7, FoVy=0.7)
+    with pytest.raises(RuntimeError, match="optimizer-in-backward"):
+        GraphedStep(m, PipelineParams(), torch.zeros(3), cam, lambda out, t, d: out["render"].mean())
