@@ -158,7 +158,7 @@ int wast3d_raster_backward_raw(const wast3d_raster_params* prm, int num_rendered
 
 /* wast3d_raster_backward_raw with the optimizer folded in ("the Adam update into
  * K9's epilogue"): instead of writing the six leaf gradients and running torch.optim.Adam over them
- * (scene/gaussian_model.py:149-167, GaussianModel.optimizer.step() at train_st.py:317), the per-Gaussian
+ * (scene/gaussian_model.py:149-167, GaussianModel.optimizer.step() at train_st.py:342), the per-Gaussian
  * kernel applies the Adam update to every parameter element in place as soon as its gradient is known —
  * same arithmetic as wast3d_adam_step, dense semantics (culled Gaussians take the zero-gradient update).
  * groups[6] = xyz, features_dc, features_rest, opacity, scaling, rotation, in that order; groups[k].param

@@ -1,6 +1,6 @@
 """One optimisation step of the style-transfer loop as a replayable CUDA graph.
 
-The reference's step (train_st.py:300-320: render -> loss -> backward -> optimizer.step -> zero_grad) stalls once per
+The reference's step (train_st.py:271 render, :325 loss.backward(), :342-343 optimizer.step() / zero_grad()) stalls once per
 forward on the host read of num_rendered (rasterizer_impl.cu:283) and bakes the optimizer's step count into its Adam
 launches.  Here nothing in the step depends on a host value that changes from step to step: the forward sizes its
 binning buffer from a capacity (wast3d_raster_forward_async), the Adam step count and bias corrections live on the
