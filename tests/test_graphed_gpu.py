@@ -49,7 +49,7 @@ def test_graphed_step_equals_eager_step(built):
             loss.backward()
             a.optimizer.step()
             a.optimizer.zero_grad(set_to_none=True)
-            losses_a.append(float(loss))
+            losses_a.append(float(loss.detach()))
         # graphed
         b = model()
         gs = GraphedStep(b, pipe, bg, cams[0], _loss, target=tgts[0], depth_target=dtgts[0], sampling_offsets=offs)
